@@ -1,0 +1,65 @@
+// Shared device/host helpers for the cfnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define CF_OK 0
+#define CF_ERR_ARG 1
+#define CF_ERR_CUDA 2
+
+extern "C" const char* cf_last_error(void);
+void cf_set_error(const char* fmt, ...);
+
+#define CF_CHECK_ARG(cond, msg)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            cf_set_error("%s: %s", __func__, msg);                \
+            return CF_ERR_ARG;                                    \
+        }                                                         \
+    } while (0)
+
+#define CF_CHECK_LAUNCH()                                                        \
+    do {                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) {                                                \
+            cf_set_error("%s: launch failed: %s", __func__, cudaGetErrorString(e__)); \
+            return CF_ERR_CUDA;                                                  \
+        }                                                                        \
+    } while (0)
+
+// launch counter (read by bench.py -> "gpu_launches")
+extern unsigned long long g_cf_launches;
+#define CF_COUNT_LAUNCH(n) (g_cf_launches += (unsigned long long)(n))
+
+static inline int cf_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline long long cf_cdiv64(long long a, long long b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float cf_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 128-bit streaming accessors: inputs read once go through the read-only path, outputs
+// written once bypass L1 so they do not evict the small tables / reused frames.
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ void stcs4(float4* p, float4 v) { __stcs(p, v); }
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_axpby(float a, float4 x, float b, float4 y) {
+    return make_float4(a * x.x + b * y.x, a * x.y + b * y.y, a * x.z + b * y.z, a * x.w + b * y.w);
+}
+__device__ __forceinline__ void f4_fma(float4& acc, float a, float4 x) {
+    acc.x = fmaf(a, x.x, acc.x); acc.y = fmaf(a, x.y, acc.y);
+    acc.z = fmaf(a, x.z, acc.z); acc.w = fmaf(a, x.w, acc.w);
+}
+#endif

@@ -1,0 +1,282 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules
+(/root/reference/{x3d_fine,x3d_coarse,interp1d}.py) on CPU in the build container.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference hard-codes ``.cuda()`` (x3d_coarse.py:265,273,277,340,390,396-397,426-427,
+430-431,435); on this GPU-less container the harness patches ``torch.Tensor.cuda`` to the
+identity *in this script only*.  Nothing here is imported by the product or by the GPU box:
+the committed .npz files are the portable artefact.
+"""
+import os
+import sys
+import zlib
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = os.environ.get("CF_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(HERE, ".."))
+torch.Tensor.cuda = lambda self, *a, **k: self          # CPU harness patch (see docstring)
+
+import interp1d as ref_interp          # noqa: E402
+import x3d_coarse as ref_coarse        # noqa: E402
+import x3d_fine as ref_fine            # noqa: E402
+
+from synth import fill_state_dict, synth_tensor   # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: (npy(v) if torch.is_tensor(v) else np.asarray(v)) for k, v in arrays.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KB")
+
+
+def sd_arrays(mod, prefix="sd/"):
+    return {prefix + k: v for k, v in mod.state_dict().items()}
+
+
+def grads_of(mod, prefix="grad/"):
+    return {prefix + k: p.grad for k, p in mod.named_parameters() if p.grad is not None}
+
+
+# ---------------------------------------------------------------------------- interp1d
+def gen_interp1d():
+    g = torch.Generator().manual_seed(11)
+    x = torch.cumsum(torch.rand(5, 17, generator=g) + 1e-3, dim=1)
+    x = (x - x[:, :1]) / (x[:, -1:] - x[:, :1])
+    x[3, 5:9] = x[3, 5]                                   # a flat stretch (ties)
+    y = torch.arange(17, dtype=torch.float32).div(16.0).view(1, -1).repeat(5, 1)
+    xnew = y.clone()
+    ynew = ref_interp.Interp1d()(x, y, xnew, None)
+    ind = (torch.searchsorted(x.contiguous(), xnew.contiguous()) - 1).clamp(0, 15)
+    save("interp1d", x=x, y=y, xnew=xnew, ynew=ynew, ind=ind)
+
+
+# ---------------------------------------------------------------------------- grid pool
+def gen_gridpool():
+    torch.manual_seed(3)
+    m = ref_coarse.GridPoolLayer(4, 8)
+    fill_state_dict(m, seed=5)
+    with torch.no_grad():
+        m.conv3.weight.mul_(6.0)                          # spread the confidences
+    m.train()
+    x = synth_tensor((2, 8, 16, 12, 12), seed=7).requires_grad_(True)
+    cap = {}
+    h = m.conv3.register_forward_hook(lambda mod, i, o: cap.__setitem__("c3", o))
+    out, cdf = m(x)
+    h.remove()
+    g = cap["c3"].mean(dim=(3, 4)).squeeze(1)
+    gout = synth_tensor(tuple(out.shape), seed=8)
+    gcdf = synth_tensor(tuple(cdf.shape), seed=9)
+    (out * gout).sum().add((cdf * gcdf).sum()).backward()
+    # gather-only gradients for the kernel-level test: d/dx and d/dcdf of grid_sample alone
+    xs = x.detach().clone().requires_grad_(True)
+    cd = cdf.detach().clone().requires_grad_(True)
+    b, c, t, hh, ww = xs.shape
+    gx = (cd - 0.5) * 2
+    gh = (torch.arange(hh).float() / (hh - 1) - 0.5) * 2
+    gw = (torch.arange(ww).float() / (ww - 1) - 0.5) * 2
+    grid = torch.meshgrid([gx.view(-1), gh, gw], indexing="ij")
+    grid = torch.stack((grid[2], grid[1], grid[0]), dim=-1).view(b, cd.shape[1], hh, ww, 3)
+    o2 = F.grid_sample(xs, grid, align_corners=True)
+    (o2 * gout).sum().backward()
+    save("gridpool_layer", x=x, g=g, out=out, cdf=cdf, gout=gout, gcdf=gcdf, dx=x.grad,
+         gather_dx=xs.grad, gather_dcdf=cd.grad,
+         **sd_arrays(m, "sd_after/"), **grads_of(m))
+
+
+def gen_gridpool_cfgshape():
+    """Non-uniform confidences at the cfg-3 temporal geometry (T=64 -> 17 points), small space."""
+    torch.manual_seed(4)
+    m = ref_coarse.GridPoolLayer(4, 4)
+    fill_state_dict(m, seed=15)
+    with torch.no_grad():
+        m.conv3.weight.mul_(20.0)
+    m.eval()
+    x = synth_tensor((3, 4, 64, 8, 8), seed=17)
+    cap = {}
+    h = m.conv3.register_forward_hook(lambda mod, i, o: cap.__setitem__("c3", o))
+    with torch.no_grad():
+        out, cdf = m(x)
+    h.remove()
+    g = cap["c3"].mean(dim=(3, 4)).squeeze(1)
+    save("gridpool_t64", x=x, g=g, out=out, cdf=cdf, **sd_arrays(m))
+
+
+# ---------------------------------------------------------------------------- grid unpool
+def gen_gridunpool():
+    g = torch.Generator().manual_seed(21)
+    conf = torch.randn(3, 8, generator=g) * 2
+    p = 1 - torch.sigmoid(conf * 0.5)
+    cdf = torch.cat([torch.zeros(3, 1), torch.cumsum(p / (p.sum(1, keepdim=True) + 1e-16), 1)], 1)
+    cdf_l = cdf.clone().requires_grad_(True)
+    x = synth_tensor((3, 11, 9), seed=22).requires_grad_(True)
+    y = ref_coarse.GridUnpool([x, cdf_l, True])
+    y_up = F.interpolate(y, (y.shape[2] - 1) * 4, mode="linear", align_corners=True)
+    gout = synth_tensor(tuple(y_up.shape), seed=23)
+    (y_up * gout).sum().backward()
+    xf = synth_tensor((3, 4, 9, 6, 6), seed=24)
+    yf = ref_coarse.GridUnpool([xf, cdf, False])
+    save("gridunpool", cdf=cdf, x=x, y=y, y_up=y_up, gout=gout, dx=x.grad, dcdf=cdf_l.grad, xf=xf, yf=yf)
+
+
+# ---------------------------------------------------------------------------- gaussian
+def gen_gaussian():
+    g = torch.Generator().manual_seed(31)
+    conf = torch.randn(3, 8, generator=g)
+    p = 1 - torch.sigmoid(conf * 0.5)
+    cdf = torch.cat([torch.zeros(3, 1), torch.cumsum(p / (p.sum(1, keepdim=True) + 1e-16), 1)], 1).requires_grad_(True)
+    meta = torch.tensor([[4., 32., 40., 1.], [0., 32., 40., 1.], [8., 32., 40., 1.]])
+    mask = torch.ones(3, 40)
+    mask[1, 30:] = 0
+    GX = ref_coarse.Gaussian(ratio=1)([meta, mask, cdf, 32])
+    gout = synth_tensor(tuple(GX.shape), seed=32)
+    (GX * gout).sum().backward()
+    save("gaussian", cdf=cdf, meta=meta, mask=mask, tx=32, GX=GX, gout=gout, dcdf=cdf.grad)
+
+
+# ---------------------------------------------------------------------------- rewight / mixing
+def gen_rewight():
+    for tag, pool, is_mixing, height in (("rewight", False, True, 14), ("rewight_pool", True, False, 7)):
+        torch.manual_seed(41)
+        m = ref_coarse.RewightLayer(channels=6, g_channels=6, depth=5, height=height, pool=pool)
+        fill_state_dict(m, seed=42)
+        m.dropout.p = 0.0
+        m.train()
+        x = synth_tensor((2, 5, 10, 7, 7), seed=43).requires_grad_(True)
+        lx = torch.zeros(2, 6, 9, 1 if pool else height, 1 if pool else height)
+        mask = torch.ones(2, 10)
+        mask[1, 7:] = 0
+        GX = synth_tensor((2, 10, 9), seed=44).abs().requires_grad_(True)
+        bias, scale = m([x, lx, mask, None, 0, GX, is_mixing])
+        gb = synth_tensor(tuple(bias.shape), seed=45)
+        gs = synth_tensor(tuple(scale.shape), seed=46)
+        ((bias * gb).sum() + (scale * gs).sum()).backward()
+        save(tag, x=x, mask=mask, GX=GX, bias=bias, scale=scale, gb=gb, gs=gs, dx=x.grad, dGX=GX.grad,
+             height=height, **sd_arrays(m), **grads_of(m))
+
+
+def gen_mixing():
+    torch.manual_seed(51)
+    m = ref_coarse.MixingLayer(depth=12, learned=True, index=0)
+    fill_state_dict(m, seed=52)
+    m.train()
+    chans = (24, 48, 96, 192)
+    base = 2                                              # base resolution of all maps
+    bases_b = [synth_tensor((2, c, 3, base, base), seed=60 + i).requires_grad_(True) for i, c in enumerate(chans)]
+    bases_s = [synth_tensor((2, c, 3, base, base), seed=70 + i).requires_grad_(True) for i, c in enumerate(chans)]
+    up = lambda t, r: t.repeat_interleave(r, -2).repeat_interleave(r, -1)
+    # the network feeds maps replicated to 8x,4x,2x,1x of the base (56/28/14/7 <- 7)
+    bias = [up(t, r) for t, r in zip(bases_b, (8, 4, 2, 1))]
+    scale = [up(t, r) for t, r in zip(bases_s, (8, 4, 2, 1))]
+    x = torch.zeros(2, 12, 3, 4 * base, 4 * base)                        # h = 8 = base*4 (the "28" level)
+    cs, ms = m([x, bias, scale])
+    gc = synth_tensor(tuple(cs.shape), seed=80)
+    gm = synth_tensor(tuple(ms.shape), seed=81)
+    ((cs * gc).sum() + (ms * gm).sum()).backward()
+    arrays = {f"bias{i}": t for i, t in enumerate(bases_b)}
+    arrays.update({f"scale{i}": t for i, t in enumerate(bases_s)})
+    arrays.update({f"dbias{i}": t.grad for i, t in enumerate(bases_b)})
+    arrays.update({f"dscale{i}": t.grad for i, t in enumerate(bases_s)})
+    save("mixing", cs=cs, ms=ms, gc=gc, gm=gm, h=4 * base, **arrays, **sd_arrays(m), **grads_of(m))
+
+
+# ---------------------------------------------------------------------------- bottleneck
+def gen_bottleneck():
+    for tag, stride, index, splits in (("bottleneck_s2_se", 2, 0, 1), ("bottleneck_s1", 1, 1, 1), ("bottleneck_s1_se_split2", 1, 2, 2)):
+        torch.manual_seed(61)
+        inp, planes = 8, (18, 8)
+        down = None
+        if stride != 1:
+            down = torch.nn.Sequential(ref_fine.conv1x1x1(inp, planes[1], stride),
+                                       ref_fine.SubBatchNorm3d(num_splits=splits, num_features=planes[1], affine=True))
+        m = ref_fine.Bottleneck(inp, planes, stride=stride, downsample=down, index=index, base_bn_splits=splits)
+        fill_state_dict(m, seed=62)
+        m.train()
+        x = synth_tensor((4, inp, 4, 10, 10), seed=63).requires_grad_(True)
+        out = m(x)
+        gout = synth_tensor(tuple(out.shape), seed=64)
+        (out * gout).sum().backward()
+        m_eval_out = None
+        m.eval()
+        for mod in m.modules():
+            if isinstance(mod, ref_fine.SubBatchNorm3d):
+                mod.aggregate_stats()
+        with torch.no_grad():
+            m_eval_out = m(x.detach())
+        save(tag, x=x, out=out, gout=gout, dx=x.grad, out_eval=m_eval_out, stride=stride, index=index, splits=splits,
+             **sd_arrays(m, "sd_after/"), **grads_of(m))
+
+
+# ---------------------------------------------------------------------------- whole nets
+def gen_fine_net():
+    torch.manual_seed(71)
+    m = ref_fine.generate_model("S", n_classes=10, task="loc", base_bn_splits=1, dropout=0.0)
+    fill_state_dict(m, seed=72)
+    x = synth_tensor((2, 3, 4, 64, 64), seed=73)
+    m.eval()
+    with torch.no_grad():
+        out_eval = m([x, None])
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    out = m([xg, None])
+    gout = synth_tensor(tuple(out.shape), seed=74)
+    (out * gout).sum().backward()
+    keys = ["conv1_s.weight", "conv1_t.weight", "layer1.0.conv1.weight", "layer1.0.conv2.weight", "layer1.0.fc1.weight",
+            "layer1.0.bn2.weight", "layer2.1.conv3.weight", "layer3.4.conv2.weight", "layer4.6.bn3.bias",
+            "conv5.weight", "fc2.weight", "fc2.bias"]
+    gr = {"grad/" + k: dict(m.named_parameters())[k].grad for k in keys}
+    mg = ref_fine.generate_model("S", n_classes=10, task="loc", base_bn_splits=1, dropout=0.0, global_tower=True)
+    fill_state_dict(mg, seed=72)
+    mg.eval()
+    with torch.no_grad():
+        feats, _ = mg([x, None])
+    save("fine_net", out_eval=out_eval, out_train=out, dx_sum=xg.grad.sum(dim=(2, 3, 4)),
+         **{"feat/" + k: v for k, v in feats.items()}, **gr)
+
+
+def gen_coarse_net():
+    torch.manual_seed(81)
+    depth = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
+    m = ref_coarse.generate_model("M", n_classes=400, feat_depth=depth, task="loc", base_bn_splits=1, dropout=0.0,
+                                  t_pool="grid", learnedMixing=True, isMixing=True)
+    m.replace_logits(12)
+    m.rw6.dropout.p = 0.0
+    fill_state_dict(m, seed=82)
+    with torch.no_grad():
+        m.pool_1.conv3.weight.mul_(8.0)
+    B, T, Tf = 1, 8, 12
+    x = synth_tensor((B, 3, T, 224, 224), seed=83)
+    feat = {k: synth_tensor((B, c, Tf, 7, 7), seed=84 + i).abs() for i, (k, c) in enumerate(depth.items())}
+    mask = torch.ones(B, Tf)
+    meta = torch.tensor([[2., 8., 12., 1.]])
+    m.eval()
+    with torch.no_grad():
+        out_eval = m([x, feat, mask, 0, meta])
+    m.train()
+    out = m([x, feat, mask, 0, meta])
+    gout = synth_tensor(tuple(out.shape), seed=90)
+    (out * gout).sum().backward()
+    keys = ["pool_1.conv1.weight", "pool_1.conv3.weight", "pool_1.conv3.bias", "rw2.at1.weight", "rw2.fc2.weight",
+            "rw6.fc4.weight", "mix2.conv_at.weight", "mix5.conv_at2.weight", "layer1.0.conv1.weight",
+            "layer2.0.conv1.weight", "layer4.6.conv3.weight", "fc2.weight", "conv1_s.weight"]
+    gr = {"grad/" + k: dict(m.named_parameters())[k].grad for k in keys}
+    save("coarse_net", out_eval=out_eval, out_train=out, **gr)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["interp1d", "gridpool", "gridpool_cfgshape", "gridunpool", "gaussian", "rewight",
+                             "mixing", "bottleneck", "fine_net", "coarse_net"]
+    for w in which:
+        globals()["gen_" + w]()

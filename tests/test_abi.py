@@ -1,0 +1,51 @@
+"""CPU tests of the boundary: the C-ABI library loads without a GPU and exports every symbol
+that include/cfnet_b200.h declares; the package refuses to run on CPU tensors."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "cfnet_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cf_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_header_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from coarse_fine_networks_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/cfnet_b200.h but not exported"
+    assert _lib.lib.cf_abi_version() >= 1
+    assert set(_lib.PROTOS) == set(syms)
+
+
+def test_argument_errors_are_reported_not_crashes():
+    from coarse_fine_networks_b200 import _lib
+    with pytest.raises(RuntimeError) as e:
+        _lib.call("cf_gridpool_cdf_fwd", None, None, 0, 0, None)
+    assert "cf_gridpool_cdf_fwd" in str(e.value)
+
+
+def test_no_cpu_fallback():
+    from coarse_fine_networks_b200 import gridpool_ops
+    with pytest.raises(RuntimeError):
+        gridpool_ops.gridpool_cdf(torch.zeros(2, 4))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "coarse_fine_networks_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
