@@ -77,3 +77,58 @@ def call(name, *args):
 
 def launch_count():
     return int(lib.cf_launch_count())
+
+
+# ----------------------------------------------------------------------------------------
+# ctypes mirrors of the argument structs, generated from the header so they cannot drift
+# ----------------------------------------------------------------------------------------
+def _parse_structs():
+    txt = open(HEADER_PATH).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    structs = {}
+    for m in re.finditer(r"typedef struct\s*\{(.*?)\}\s*(cf_\w+)\s*;", txt, flags=re.S):
+        body, name = m.group(1), m.group(2)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            is_ptr = "*" in decl
+            decl = decl.replace("*", " ")
+            toks = decl.replace(",", " ").split()
+            names = []
+            while toks and (toks[-1] not in _CTYPES and toks[-1] not in structs and toks[-1] != "const"):
+                names.insert(0, toks.pop())
+            ty = " ".join(t for t in toks if t != "const")
+            if is_ptr:
+                ct = _c_ptr
+            elif ty in structs:
+                ct = structs[ty]
+            else:
+                ct = _CTYPES[ty]
+            fields += [(n, ct) for n in names]
+        structs[name] = type(name, (ctypes.Structure,), {"_fields_": fields})
+    return structs
+
+
+STRUCTS = _parse_structs()
+for _sname in ("cf_pw_args", "cf_pw_wgrad_args", "cf_dw_args"):
+    _sz = getattr(lib, "cf_sizeof_" + _sname[3:])()
+    if _sz != ctypes.sizeof(STRUCTS[_sname]):
+        raise ImportError(f"ABI mismatch for {_sname}: library {_sz} bytes, header {ctypes.sizeof(STRUCTS[_sname])}")
+
+
+def make(struct_name, **kw):
+    """Build an argument struct; tensors are converted to device pointers, None to NULL."""
+    s = STRUCTS[struct_name]()
+    for k, v in kw.items():
+        if torch.is_tensor(v):
+            v = ptr(v)
+        setattr(s, k, v)
+    return s
+
+
+def call_struct(name, s):
+    rc = getattr(lib, name)(ctypes.byref(s), stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.cf_last_error().decode()}")

@@ -1,0 +1,467 @@
+"""Autograd functions of the X3D conv stacks over the C ABI (cf_pw_conv, cf_pw_wgrad,
+cf_dw_conv_*, cf_bn_*, cf_se_*, cf_residual_*, cf_block_avgpool_*).
+
+Activations are channels-last fp32 ([B,C,T,H,W] logical shape, torch.channels_last_3d strides);
+BatchNorm / ReLU / SE / Swish never materialise: producers accumulate statistics, consumers
+apply per-(sample,channel) affine tables on load (see include/cfnet_b200.h)."""
+import torch
+
+from ._lib import STRUCTS, call, call_struct, make, ptr, stream_ptr
+
+CL3 = torch.channels_last_3d
+
+PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU, PRO_AFFINE_SWISH, PRO_AFFINE2 = 0, 1, 2, 3, 4
+EPI_NONE, EPI_RELU, EPI_DRELU, EPI_DSWISH, EPI_ADD_AUX = 0, 1, 2, 3, 4
+STATS_NONE, STATS_SUM_SQ, STATS_SUM_AUX = 0, 1, 2
+
+
+def cl(x):
+    """Dense channels-last view of a [B,C,T,H,W] tensor (no copy when already so)."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous(memory_format=CL3)
+
+
+def new_act(B, C, T, H, W, device):
+    return torch.empty((B, C, T, H, W), device=device, dtype=torch.float32, memory_format=CL3)
+
+
+def geom(T, H, W, Ti=None, Hi=None, Wi=None, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0), pos_stride=0, ch_stride=1,
+         sample_stride=0):
+    g = STRUCTS["cf_geom"]()
+    g.T, g.H, g.W = T, H, W
+    g.Ti, g.Hi, g.Wi = (T if Ti is None else Ti), (H if Hi is None else Hi), (W if Wi is None else Wi)
+    g.kt, g.kh, g.kw = k
+    g.st, g.sh, g.sw = s
+    g.pt, g.ph, g.pw = p
+    g.pos_stride, g.ch_stride, g.sample_stride = pos_stride, ch_stride, sample_stride
+    return g
+
+
+def pw_conv(x, w, y, B, K, N, g, *, w_sn=None, w_sk=1, x2=None, bias=None, pro=PRO_NONE, pro_tabs=(None, None, None),
+            epi=EPI_NONE, aux=None, epi_tabs=(None, None), stats=None, stats_mode=STATS_NONE, gather_in=0, scatter_out=0,
+            accumulate=0):
+    a = make("cf_pw_args", x=x, x2=x2, w=w, bias=bias, y=y, pro_a=pro_tabs[0], pro_b=pro_tabs[1], pro_c=pro_tabs[2],
+             aux=aux, epi_a=epi_tabs[0], epi_b=epi_tabs[1], stats=stats, w_sn=(K if w_sn is None else w_sn), w_sk=w_sk,
+             B=B, K=K, N=N, g=g, gather_in=gather_in, scatter_out=scatter_out, accumulate=accumulate, pro_mode=pro,
+             epi_mode=epi, stats_mode=stats_mode)
+    call_struct("cf_pw_conv", a)
+    return y
+
+
+def pw_wgrad(dy, x, dw, B, K, N, g, *, dy2=None, dy_mode=PRO_NONE, dy_tabs=(None, None, None), x_mode=PRO_NONE,
+             x_tabs=(None, None), dbias=None, gather_in=0):
+    a = make("cf_pw_wgrad_args", dy=dy, dy2=dy2, dy_a=dy_tabs[0], dy_b=dy_tabs[1], dy_c=dy_tabs[2], x=x, x_a=x_tabs[0],
+             x_b=x_tabs[1], dw=dw, dbias=dbias, B=B, K=K, N=N, g=g, gather_in=gather_in, dy_mode=dy_mode, x_mode=x_mode)
+    call_struct("cf_pw_wgrad", a)
+    return dw
+
+
+def dw_call(fn, x, w, y, B, C, g, *, x2=None, pro=PRO_NONE, pro_tabs=(None, None, None), aux=None, epi=EPI_NONE,
+            epi_tabs=(None, None), stats=None, stats_mode=STATS_NONE):
+    a = make("cf_dw_args", x=x, x2=x2, w=w, y=y, pro_a=pro_tabs[0], pro_b=pro_tabs[1], pro_c=pro_tabs[2], aux=aux,
+             epi_a=epi_tabs[0], epi_b=epi_tabs[1], stats=stats, B=B, C=C, g=g, pro_mode=pro, epi_mode=epi,
+             stats_mode=stats_mode)
+    call_struct(fn, a)
+    return y
+
+
+class BNCfg:
+    """What the kernels need to know about one SubBatchNorm3d (x3d_fine.py:13-62)."""
+
+    def __init__(self, module):
+        self.m = module
+
+    @property
+    def splits(self):
+        return self.m.num_splits
+
+
+def bn_finalize(stats, bn, B, C, rows, training, device):
+    """-> (tab_a, tab_b, mean, invstd); updates split_bn running statistics in training."""
+    m = bn.m
+    splits = m.num_splits if training else 1
+    tabs = torch.empty(2, B, C, device=device, dtype=torch.float32)
+    ms = torch.empty(2, splits, C, device=device, dtype=torch.float32)
+    if training:
+        rm, rv = m.split_bn.running_mean, m.split_bn.running_var
+        m._pending_batches = getattr(m, "_pending_batches", 0) + 1
+    else:
+        rm, rv = m.bn.running_mean, m.bn.running_var
+    a = make("cf_bn_args", stats=stats, gamma=m.weight, beta=m.bias, running_mean=rm, running_var=rv, tab_a=tabs[0],
+             tab_b=tabs[1], mean=ms[0], invstd=ms[1], B=B, C=C, splits=splits, rows_per_sample=rows,
+             momentum=float(m.split_bn.momentum if m.split_bn.momentum is not None else 0.1), eps=float(m.split_bn.eps),
+             training=int(training))
+    call_struct("cf_bn_finalize", a)
+    return tabs[0], tabs[1], ms[0], ms[1]
+
+
+def bn_bwd_coeffs(sums, gamma, mean, invstd, dgamma, dbeta, B, C, rows, training, gate=None, cst=None):
+    tabs = torch.empty(3, B, C, device=sums.device, dtype=torch.float32)
+    a = make("cf_bn_bwd_args", sums=sums, gamma=gamma, mean=mean, invstd=invstd, gate=gate, cst=cst, dgamma=dgamma,
+             dbeta=dbeta, tab_p=tabs[0], tab_q=tabs[1], tab_r=tabs[2], B=B, C=C, splits=mean.shape[0],
+             rows_per_sample=rows, training=int(training))
+    call_struct("cf_bn_bwd_coeffs", a)
+    return tabs[0], tabs[1], tabs[2]
+
+
+def residual_fwd(y, ta, tb, out, B, C, rows, res=None, ra=None, rb=None):
+    a = make("cf_residual_args", y=y, tab_a=ta, tab_b=tb, res=res, res_a=ra, res_b=rb, out=out, B=B, C=C,
+             rows_per_sample=rows)
+    call_struct("cf_residual_fwd", a)
+    return out
+
+
+def residual_bwd(dout, out, y, dz, sums_y, B, C, rows, res=None, sums_res=None):
+    a = make("cf_residual_bwd_args", dout=dout, out=out, y=y, res=res, dz=dz, sums_y=sums_y, sums_res=sums_res, B=B, C=C,
+             rows_per_sample=rows)
+    call_struct("cf_residual_bwd", a)
+    return dz
+
+
+def _flat_grads(params, device):
+    """One zero-filled buffer carved into per-parameter gradient views (a single memset)."""
+    sizes = [p.numel() if p is not None else 0 for p in params]
+    flat = torch.zeros(sum(sizes), device=device, dtype=torch.float32)
+    out, o = [], 0
+    for p, n in zip(params, sizes):
+        out.append(flat[o:o + n].view(p.shape) if p is not None else None)
+        o += n
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+class BottleneckFn(torch.autograd.Function):
+    """Bottleneck.forward (x3d_fine.py:146-175): conv1->bn1->relu->conv2(dw)->bn2->[SE]->swish->
+    conv3->bn3->(+res)->relu, as 7-10 kernel launches forward and 12-16 backward."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, w1, g1, b1, w2, g2, b2, w3, g3, b3, fw1, fb1, fw2, fb2, wd, gd, bd):
+        x = cl(x)
+        dev = x.device
+        B, Cin, T, H, W = x.shape
+        Ce, Co = w1.shape[0], w3.shape[0]
+        s, ts = cfg.stride, cfg.t_stride
+        To, Ho, Wo = (T - 1) // ts + 1, (H - 1) // s + 1, (W - 1) // s + 1
+        Rin, Rout = T * H * W, To * Ho * Wo
+        tr = cfg.training
+        has_se, has_ds = fw1 is not None, wd is not None
+        Cmax = max(Ce, Co)
+        need_stats = tr or has_se                      # eval: only the SE pool needs sum(y2)
+        stats = torch.zeros(4, B, Cmax, 2, device=dev, dtype=torch.float64) if need_stats else None
+        st = (lambda i, C: stats[i].view(-1)[: B * C * 2]) if need_stats else (lambda i, C: None)
+        smode = STATS_SUM_SQ if tr else STATS_NONE
+        g_in, g_out = geom(T, H, W), geom(To, Ho, Wo)
+        g_dw = geom(To, Ho, Wo, T, H, W, k=(3, 3, 3), s=(ts, s, s), p=(1, 1, 1))
+        g_ds = geom(To, Ho, Wo, T, H, W, s=(ts, s, s), pos_stride=Cin, ch_stride=1, sample_stride=Rin * Cin)
+
+        y1 = new_act(B, Ce, T, H, W, dev)
+        pw_conv(x, w1, y1, B, Cin, Ce, g_in, stats=st(0, Ce) if tr else None, stats_mode=smode)
+        a1, bb1, m1, i1 = bn_finalize(st(0, Ce) if tr else None, cfg.bn1, B, Ce, Rin, tr, dev)
+        y2 = new_act(B, Ce, To, Ho, Wo, dev)
+        dw_call("cf_dw_conv_fwd", y1, w2, y2, B, Ce, g_dw, pro=PRO_AFFINE_RELU, pro_tabs=(a1, bb1, None),
+                stats=st(1, Ce), stats_mode=STATS_SUM_SQ if need_stats else STATS_NONE)
+        a2, bb2, m2, i2 = bn_finalize(st(1, Ce) if tr else None, cfg.bn2, B, Ce, Rout, tr, dev)
+        se_saved = None
+        ga, gb = a2, bb2
+        if has_se:
+            Wd = fw1.shape[0]
+            sv = torch.empty(4, B, Ce, device=dev, dtype=torch.float32)     # pooled, gate, out_a, out_b
+            hid = torch.empty(B, Wd, device=dev, dtype=torch.float32)
+            a = make("cf_se_args", stats=st(1, Ce), tab_a=a2, tab_b=bb2, w1=fw1, b1=fb1, w2=fw2, b2=fb2, pooled=sv[0],
+                     hidden=hid, gate=sv[1], out_a=sv[2], out_b=sv[3], B=B, C=Ce, Wd=Wd, rows_per_sample=Rout)
+            call_struct("cf_se_fwd", a)
+            ga, gb = sv[2], sv[3]
+            se_saved = (sv[0], hid, sv[1])
+        y3 = new_act(B, Co, To, Ho, Wo, dev)
+        pw_conv(y2, w3, y3, B, Ce, Co, g_out, pro=PRO_AFFINE_SWISH, pro_tabs=(ga, gb, None), stats=st(2, Co) if tr else None,
+                stats_mode=smode)
+        a3, bb3, m3, i3 = bn_finalize(st(2, Co) if tr else None, cfg.bn3, B, Co, Rout, tr, dev)
+        yd = ad = bbd = md = idd = None
+        if has_ds:
+            yd = new_act(B, Co, To, Ho, Wo, dev)
+            pw_conv(x, wd, yd, B, Cin, Co, g_ds, gather_in=1, stats=st(3, Co) if tr else None, stats_mode=smode)
+            ad, bbd, md, idd = bn_finalize(st(3, Co) if tr else None, cfg.bnd, B, Co, Rout, tr, dev)
+        out = new_act(B, Co, To, Ho, Wo, dev)
+        residual_fwd(y3, a3, bb3, out, B, Co, Rout, res=yd if has_ds else x, ra=ad, rb=bbd)
+
+        ctx.cfg = cfg
+        ctx.dims = (B, Cin, Ce, Co, T, H, W, To, Ho, Wo, s, ts)
+        ctx.se_saved = se_saved
+        ctx.aux = (a1, bb1, m1, i1, a2, bb2, m2, i2, ga, gb, a3, bb3, m3, i3, ad, bbd, md, idd, st(1, Ce))
+        ctx.save_for_backward(x, y1, y2, y3, yd, out, w1, g1, w2, g2, w3, g3, fw1, fw2, wd, gd)
+        ctx.param_shapes = [p for p in (w1, g1, b1, w2, g2, b2, w3, g3, b3, fw1, fb1, fw2, fb2, wd, gd, bd)]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y1, y2, y3, yd, out, w1, g1, w2, g2, w3, g3, fw1, fw2, wd, gd = ctx.saved_tensors
+        (a1, bb1, m1, i1, a2, bb2, m2, i2, ga, gb, a3, bb3, m3, i3, ad, bbd, md, idd, stats2) = ctx.aux
+        B, Cin, Ce, Co, T, H, W, To, Ho, Wo, s, ts = ctx.dims
+        cfg = ctx.cfg
+        tr = cfg.training
+        dev = x.device
+        has_se, has_ds = fw1 is not None, wd is not None
+        Rin, Rout = T * H * W, To * Ho * Wo
+        dout = cl(dout)
+        grads = _flat_grads(ctx.param_shapes, dev)
+        (dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dfw1, dfb1, dfw2, dfb2, dwd, dgd, dbd) = grads
+        Cmax = max(Ce, Co)
+        sums = torch.zeros(4, B, Cmax, 2, device=dev, dtype=torch.float64)
+        sm = lambda i, C: sums[i].view(-1)[: B * C * 2]
+        g_in, g_out = geom(T, H, W), geom(To, Ho, Wo)
+        g_dw = geom(To, Ho, Wo, T, H, W, k=(3, 3, 3), s=(ts, s, s), p=(1, 1, 1))
+        g_ds = geom(To, Ho, Wo, T, H, W, s=(ts, s, s), pos_stride=Cin, ch_stride=1, sample_stride=Rin * Cin)
+
+        # join: dz3 = dout*[out>0]; sums vs y3 (bn3) and vs yd (downsample bn)
+        dz3 = torch.empty_like(out)
+        residual_bwd(dout, out, y3, dz3, sm(0, Co), B, Co, Rout, res=yd, sums_res=sm(3, Co) if has_ds else None)
+        P3, Q3, R3 = bn_bwd_coeffs(sm(0, Co), g3, m3, i3, dg3, db3, B, Co, Rout, tr)
+        # conv3
+        pw_wgrad(dz3, y2, dw3, B, Ce, Co, g_out, dy2=y3, dy_mode=PRO_AFFINE2, dy_tabs=(P3, Q3, R3), x_mode=PRO_AFFINE_SWISH,
+                 x_tabs=(ga, gb))
+        dU = torch.empty_like(y2)
+        pw_conv(dz3, w3, dU, B, Co, Ce, g_out, w_sn=1, w_sk=Ce, x2=y3, pro=PRO_AFFINE2, pro_tabs=(P3, Q3, R3), epi=EPI_DSWISH,
+                aux=y2, epi_tabs=(ga, gb), stats=sm(1, Ce), stats_mode=STATS_SUM_AUX)
+        gate = cst = None
+        if has_se:
+            pooled, hid, gate = ctx.se_saved
+            cst = torch.empty(B, Ce, device=dev, dtype=torch.float32)
+            a = make("cf_se_bwd_args", sums=sm(1, Ce), stats_y=stats2, tab_a=a2, tab_b=bb2, w1=fw1, w2=fw2, pooled=pooled,
+                     hidden=hid, gate=gate, dw1=dfw1, db1=dfb1, dw2=dfw2, db2=dfb2, cst=cst, B=B, C=Ce, Wd=fw1.shape[0],
+                     rows_per_sample=Rout)
+            call_struct("cf_se_bwd", a)
+        P2, Q2, R2 = bn_bwd_coeffs(sm(1, Ce), g2, m2, i2, dg2, db2, B, Ce, Rout, tr, gate=gate, cst=cst)
+        # conv2 (depthwise)
+        dw_call("cf_dw_conv_wgrad", dU, w2, dw2, B, Ce, g_dw, x2=y2, pro=PRO_AFFINE2, pro_tabs=(P2, Q2, R2), aux=y1,
+                epi_tabs=(a1, bb1))
+        dz1 = torch.empty_like(y1)
+        dw_call("cf_dw_conv_dgrad", dU, w2, dz1, B, Ce, g_dw, x2=y2, pro=PRO_AFFINE2, pro_tabs=(P2, Q2, R2), aux=y1,
+                epi=EPI_DRELU, epi_tabs=(a1, bb1), stats=sm(2, Ce), stats_mode=STATS_SUM_AUX)
+        P1, Q1, R1 = bn_bwd_coeffs(sm(2, Ce), g1, m1, i1, dg1, db1, B, Ce, Rin, tr)
+        # conv1
+        pw_wgrad(dz1, x, dw1, B, Cin, Ce, g_in, dy2=y1, dy_mode=PRO_AFFINE2, dy_tabs=(P1, Q1, R1))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            pw_conv(dz1, w1, dx, B, Ce, Cin, g_in, w_sn=1, w_sk=Cin, x2=y1, pro=PRO_AFFINE2, pro_tabs=(P1, Q1, R1),
+                    epi=EPI_NONE if has_ds else EPI_ADD_AUX, aux=None if has_ds else dz3)
+        if has_ds:
+            Pd, Qd, Rd = bn_bwd_coeffs(sm(3, Co), gd, md, idd, dgd, dbd, B, Co, Rout, tr)
+            pw_wgrad(dz3, x, dwd, B, Cin, Co, g_ds, dy2=yd, dy_mode=PRO_AFFINE2, dy_tabs=(Pd, Qd, Rd), gather_in=1)
+            if dx is not None:
+                pw_conv(dz3, wd, dx, B, Co, Cin, g_ds, w_sn=1, w_sk=Cin, x2=yd, pro=PRO_AFFINE2, pro_tabs=(Pd, Qd, Rd),
+                        scatter_out=1, accumulate=1)
+        return (dx, None, dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dfw1, dfb1, dfw2, dfb2, dwd, dgd, dbd)
+
+
+# ----------------------------------------------------------------------------------------
+class StemFn(torch.autograd.Function):
+    """conv1_s (1x3x3, stride (1,2,2), 3->24) -> conv1_t (5x1x1 depthwise) -> bn1 -> relu
+    (x3d_fine.py:210-223, 334-337).  Input is the network's NCTHW clip, output channels-last."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, ws, wt, gamma, beta):
+        x = x.contiguous().float()
+        dev = x.device
+        B, Ci, T, H, W = x.shape
+        C = ws.shape[0]
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        R = T * Ho * Wo
+        tr = cfg.training
+        g_s = geom(T, Ho, Wo, T, H, W, k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1), pos_stride=1, ch_stride=T * H * W,
+                   sample_stride=Ci * T * H * W)
+        g_t = geom(T, Ho, Wo, k=(5, 1, 1), p=(2, 0, 0))
+        y0 = new_act(B, C, T, Ho, Wo, dev)
+        pw_conv(x, ws, y0, B, Ci * 9, C, g_s, gather_in=1)
+        yt = new_act(B, C, T, Ho, Wo, dev)
+        stats = torch.zeros(B, C, 2, device=dev, dtype=torch.float64) if tr else None
+        dw_call("cf_dw_conv_fwd", y0, wt, yt, B, C, g_t, stats=stats, stats_mode=STATS_SUM_SQ if tr else STATS_NONE)
+        a, b, m, i = bn_finalize(stats, cfg.bn1, B, C, R, tr, dev)
+        out = new_act(B, C, T, Ho, Wo, dev)
+        residual_fwd(yt, a, b, out, B, C, R)
+        ctx.cfg, ctx.dims, ctx.geoms, ctx.bn = cfg, (B, Ci, C, T, H, W, Ho, Wo), (g_s, g_t), (m, i)
+        ctx.save_for_backward(x, y0, yt, out, ws, wt, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y0, yt, out, ws, wt, gamma = ctx.saved_tensors
+        B, Ci, C, T, H, W, Ho, Wo = ctx.dims
+        g_s, g_t = ctx.geoms
+        m, i = ctx.bn
+        dev = x.device
+        R = T * Ho * Wo
+        dout = cl(dout)
+        dws, dwt, dgam, dbet = _flat_grads([ws, wt, gamma, gamma], dev)
+        sums = torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
+        dz = torch.empty_like(out)
+        residual_bwd(dout, out, yt, dz, sums, B, C, R)
+        P, Q, Rr = bn_bwd_coeffs(sums, gamma, m, i, dgam, dbet, B, C, R, ctx.cfg.training)
+        dw_call("cf_dw_conv_wgrad", dz, wt, dwt, B, C, g_t, x2=yt, pro=PRO_AFFINE2, pro_tabs=(P, Q, Rr), aux=y0)
+        dy0 = torch.empty_like(y0)
+        dw_call("cf_dw_conv_dgrad", dz, wt, dy0, B, C, g_t, x2=yt, pro=PRO_AFFINE2, pro_tabs=(P, Q, Rr))
+        pw_wgrad(dy0, x, dws, B, Ci * 9, C, g_s, gather_in=1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.zeros_like(x)
+            pw_conv(dy0, ws, dx, B, C, Ci * 9, g_s, w_sn=1, w_sk=Ci * 9, scatter_out=1)
+        return dx, None, dws, dwt, dgam, dbet
+
+
+class ConvBNReluPoolFn(torch.autograd.Function):
+    """conv5 (1x1x1) -> bn5 -> relu -> block average pool over (H,W)
+    (x3d_fine.py:356-366; pool to 7x7 for the global tower, :360)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, w, gamma, beta, rh, rw):
+        x = cl(x)
+        dev = x.device
+        B, Cin, T, H, W = x.shape
+        C = w.shape[0]
+        R = T * H * W
+        tr = cfg.training
+        y = new_act(B, C, T, H, W, dev)
+        stats = torch.zeros(B, C, 2, device=dev, dtype=torch.float64) if tr else None
+        pw_conv(x, w, y, B, Cin, C, geom(T, H, W), stats=stats, stats_mode=STATS_SUM_SQ if tr else STATS_NONE)
+        a, b, m, i = bn_finalize(stats, cfg.bn, B, C, R, tr, dev)
+        out = new_act(B, C, T, H // rh, W // rw, dev)
+        call_struct("cf_block_avgpool_fwd", make("cf_pool_args", x=y, y=out, tab_a=a, tab_b=b, B=B, C=C, T=T, H=H, W=W, rh=rh, rw=rw))
+        ctx.cfg, ctx.dims, ctx.tabs = cfg, (B, Cin, C, T, H, W, rh, rw), (a, b, m, i)
+        ctx.save_for_backward(x, y, w, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, w, gamma = ctx.saved_tensors
+        B, Cin, C, T, H, W, rh, rw = ctx.dims
+        a, b, m, i = ctx.tabs
+        dev = x.device
+        R = T * H * W
+        dout = cl(dout)
+        dw, dgam, dbet = _flat_grads([w, gamma, gamma], dev)
+        sums = torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
+        dz = torch.empty_like(y)
+        call_struct("cf_block_avgpool_bwd", make("cf_pool_bwd_args", dy=dout, x=y, tab_a=a, tab_b=b, dz=dz, sums=sums, B=B, C=C,
+                                                 T=T, H=H, W=W, rh=rh, rw=rw, accumulate=0))
+        P, Q, Rr = bn_bwd_coeffs(sums, gamma, m, i, dgam, dbet, B, C, R, ctx.cfg.training)
+        g = geom(T, H, W)
+        pw_wgrad(dz, x, dw, B, Cin, C, g, dy2=y, dy_mode=PRO_AFFINE2, dy_tabs=(P, Q, Rr))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            pw_conv(dz, w, dx, B, C, Cin, g, w_sn=1, w_sk=Cin, x2=y, pro=PRO_AFFINE2, pro_tabs=(P, Q, Rr))
+        return dx, None, dw, dgam, dbet, None, None
+
+
+class AvgPoolFn(torch.autograd.Function):
+    """F.adaptive_avg_pool3d(x, (None, H/rh, W/rw)) for H,W multiples of the output (x3d_fine.py:345-354)."""
+
+    @staticmethod
+    def forward(ctx, x, rh, rw):
+        x = cl(x)
+        B, C, T, H, W = x.shape
+        out = new_act(B, C, T, H // rh, W // rw, x.device)
+        call_struct("cf_block_avgpool_fwd", make("cf_pool_args", x=x, y=out, tab_a=None, tab_b=None, B=B, C=C, T=T, H=H, W=W, rh=rh, rw=rw))
+        ctx.dims = (B, C, T, H, W, rh, rw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, C, T, H, W, rh, rw = ctx.dims
+        dout = cl(dout)
+        dz = new_act(B, C, T, H, W, dout.device)
+        call_struct("cf_block_avgpool_bwd", make("cf_pool_bwd_args", dy=dout, x=None, tab_a=None, tab_b=None, dz=dz, sums=None, B=B,
+                                                 C=C, T=T, H=H, W=W, rh=rh, rw=rw, accumulate=0))
+        return dz, None, None
+
+
+class LinearRowsFn(torch.autograd.Function):
+    """y[b,r,:] = act(W x[b,r,:] + bias) on a [B,R,K] row tensor: fc1 (1x1x1 conv, no bias, + ReLU)
+    and fc2 (nn.Linear) of the head (x3d_fine.py:370-380), k=1 Conv1d layers of the fusion block."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, relu):
+        x = x.contiguous().float()
+        B, R, K = x.shape
+        w2 = w.reshape(w.shape[0], -1)
+        N = w2.shape[0]
+        y = torch.empty(B, R, N, device=x.device, dtype=torch.float32)
+        pw_conv(x, w2, y, B, K, N, geom(R, 1, 1), bias=bias, epi=EPI_RELU if relu else EPI_NONE)
+        ctx.relu, ctx.dims, ctx.wshape, ctx.has_bias = relu, (B, R, K, N), w.shape, bias is not None
+        ctx.save_for_backward(x, w2, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w2, y = ctx.saved_tensors
+        B, R, K, N = ctx.dims
+        dy = dy.contiguous().float()
+        g = geom(R, 1, 1)
+        if ctx.relu:                      # dy *= [y > 0]
+            dyr = torch.empty_like(dy)
+            call("cf_relu_bwd", ptr(dy), ptr(y), ptr(dyr), dy.numel(), stream_ptr())
+            dy = dyr
+        dw, db = _flat_grads([w2, torch.empty(N) if ctx.has_bias else None], dy.device)
+        pw_wgrad(dy, x, dw, B, K, N, g, dbias=db)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            pw_conv(dy, w2, dx, B, N, K, g, w_sn=1, w_sk=K)
+        return dx, dw.view(ctx.wshape), db, None
+
+
+class SwishFn(torch.autograd.Function):
+    """SwishEfficient (x3d_fine.py:74-86): saves only x."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous() if not x.is_contiguous(memory_format=CL3) else x
+        out = torch.empty_like(x)
+        call("cf_swish_fwd", ptr(x), ptr(out), x.numel(), stream_ptr())
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=CL3) if (x.dim() == 5 and not x.is_contiguous()) else dy.contiguous()
+        dx = torch.empty_like(x)
+        call("cf_swish_bwd", ptr(x), ptr(dy), ptr(dx), x.numel(), stream_ptr())
+        return dx
+
+
+class StandaloneBNFn(torch.autograd.Function):
+    """SubBatchNorm3d.forward called on its own (x3d_fine.py:51-62): statistics kernel +
+    table + affine apply; backward through the same affine-map formulation."""
+
+    @staticmethod
+    def forward(ctx, x, bn, training, gamma, beta):
+        x = cl(x)
+        B, C, T, H, W = x.shape
+        R = T * H * W
+        stats = None
+        if training:
+            stats = torch.zeros(B, C, 2, device=x.device, dtype=torch.float64)
+            call("cf_channel_stats", ptr(x), None, ptr(stats), B, C, R, stream_ptr())
+        a, b, m, i = bn_finalize(stats, bn, B, C, R, training, x.device)
+        out = torch.empty_like(x)
+        call_struct("cf_affine_apply", make("cf_affine_args", x=x, x2=None, tab_a=a, tab_b=b, tab_c=None, out=out, B=B, C=C,
+                                            rows_per_sample=R, mode=PRO_AFFINE))
+        ctx.save_for_backward(x, gamma)
+        ctx.misc = (m, i, training, B, C, R)
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, gamma = ctx.saved_tensors
+        m, i, training, B, C, R = ctx.misc
+        dz = cl(dz)
+        sums = torch.zeros(B, C, 2, device=x.device, dtype=torch.float64)
+        call("cf_channel_stats", ptr(dz), ptr(x), ptr(sums), B, C, R, stream_ptr())
+        dgam, dbet = _flat_grads([gamma, gamma], x.device)
+        P, Q, Rr = bn_bwd_coeffs(sums, gamma, m, i, dgam, dbet, B, C, R, training)
+        dx = torch.empty_like(x)
+        call_struct("cf_affine_apply", make("cf_affine_args", x=dz, x2=x, tab_a=P, tab_b=Q, tab_c=Rr, out=dx, B=B, C=C,
+                                            rows_per_sample=R, mode=PRO_AFFINE2))
+        return dx, None, None, dgam, dbet

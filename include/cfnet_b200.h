@@ -71,6 +71,295 @@ int cf_temporal_gather_bwd_coord(const float* gout, const float* x, const int32_
                                  int64_t outer, int64_t outer_per_b, int T, int K, int64_t inner, float scale,
                                  cudaStream_t stream);
 
+/* ====================================================================================== */
+/* X3D conv stacks.  Activations are channels-last fp32: a [B,C,T,H,W] tensor is stored as   */
+/* [B, R, C] rows with R = T*H*W ("rows per sample").  Train-mode BatchNorm / SE / FiLM are   */
+/* never materialised: every producer kernel accumulates per-(sample,channel) statistics in  */
+/* its epilogue and every consumer applies a per-(sample,channel) affine + activation in its  */
+/* prologue (tables of shape [B,C]).                                                         */
+/* ====================================================================================== */
+
+/* prologue applied to an input element x (and x2) of channel k of sample b */
+#define CF_PRO_NONE 0          /* x                                   */
+#define CF_PRO_AFFINE 1        /* a[b,k]*x + b[b,k]                   */
+#define CF_PRO_AFFINE_RELU 2   /* relu(a*x + b)     bn+ReLU  (x3d_fine.py:150-151) */
+#define CF_PRO_AFFINE_SWISH 3  /* swish(a*x + b)    bn+SE+Swish (x3d_fine.py:154-164) */
+#define CF_PRO_AFFINE2 4       /* a*x + b*x2 + c    BatchNorm backward as an affine map of (dz, y) */
+/* epilogue applied to an output element acc of channel n of sample b */
+#define CF_EPI_NONE 0          /* acc (+bias)                         */
+#define CF_EPI_RELU 1          /* relu(acc + bias)                    */
+#define CF_EPI_DRELU 2         /* acc * [ea*aux + eb > 0]             */
+#define CF_EPI_DSWISH 3        /* acc * swish'(ea*aux + eb)           */
+#define CF_EPI_ADD_AUX 4       /* acc + aux                           */
+/* statistics accumulated (double atomics) into stats[b][n][0..1] */
+#define CF_STATS_NONE 0
+#define CF_STATS_SUM_SQ 1      /* sum y, sum y^2      (forward: BatchNorm + SE pooling) */
+#define CF_STATS_SUM_AUX 2     /* sum y, sum y*aux    (backward: BatchNorm/SE reductions) */
+
+/* Geometry of the row <-> position map shared by the conv kernels.  The "dense" side has one
+ * row per position (t,h,w) of a [T,H,W] volume (rows per sample R = T*H*W).  The "gathered"
+ * side is a [Ti,Hi,Wi] volume addressed at (t*st-pt+dt, h*sh-ph+dh, w*sw-pw+dw) for tap
+ * (dt,dh,dw) of a kt x kh x kw window; positions outside the volume read as zero (after the
+ * prologue) / are skipped on scatter.  Element (position p, channel c) of sample b lives at
+ * base + b*sample_stride + p*pos_stride + c*ch_stride, so both channels-last activations
+ * (pos_stride=C, ch_stride=1) and the NCTHW network input (pos_stride=1, ch_stride=Ti*Hi*Wi)
+ * can be gathered.  With taps > 1 the GEMM reduction index is k = c*taps + tap, which is the
+ * native [Cout][Cin][kt][kh][kw] weight layout of nn.Conv3d.  1x1x1 stride-1: all taps 1,
+ * strides 1, pads 0, (Ti,Hi,Wi) = (T,H,W). */
+typedef struct {
+    int T, H, W;
+    int Ti, Hi, Wi;
+    int kt, kh, kw;
+    int st, sh, sw;
+    int pt, ph, pw;
+    int64_t pos_stride, ch_stride, sample_stride;
+} cf_geom;
+
+/* Convolution as a GEMM over rows (pointwise 1x1x1 convs, linear layers, and -- through the
+ * tap gather -- the small dense convs of the stem and of the Grid Pool confidence branch):
+ *   y[b,r,n] = epi( sum_k pro(x[b, gather(r,k)]) * w[n*w_sn + k*w_sk] (+ bias[n]) )
+ * forward  : conv1/conv3/downsample/conv5/fc1/fc2 (x3d_fine.py:149,166,286,356,370,380),
+ *            conv1_s (x3d_fine.py:210-215), pool_1.conv1-3 (x3d_coarse.py:362-366)
+ * backward : data gradient = the same GEMM with (w_sn,w_sk) swapped; for strided / windowed
+ *            convs the result is scattered (scatter_out) to the gathered side. */
+typedef struct {
+    const float* x;      /* dense [B,R,K], or the gathered tensor when gather_in */
+    const float* x2;     /* second input for CF_PRO_AFFINE2 (dense only), else NULL */
+    const float* w;
+    const float* bias;   /* [N] or NULL */
+    float* y;            /* dense [B,R,N], or the gathered-side tensor when scatter_out */
+    const float* pro_a;  /* [B,Cin] tables (NULL when pro_mode == NONE) */
+    const float* pro_b;
+    const float* pro_c;
+    const float* aux;    /* dense [B,R,N] for DRELU/DSWISH/ADD_AUX/STATS_SUM_AUX */
+    const float* epi_a;  /* [B,N] tables for DRELU/DSWISH */
+    const float* epi_b;
+    double* stats;       /* [B,N,2] or NULL */
+    int64_t w_sn, w_sk;
+    int B, K, N;         /* K (or N when scatter_out) = channels * taps of the gathered side */
+    cf_geom g;
+    int gather_in;       /* 1: x is addressed through g (strided and/or windowed conv forward) */
+    int scatter_out;     /* 1: y is addressed through g; taps > 1 => atomic accumulation */
+    int accumulate;      /* 1: y += result */
+    int pro_mode, epi_mode, stats_mode;
+} cf_pw_args;
+int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream);
+
+/* weight gradient:
+ *   dw[n*K + k] += sum_{b,r} pro_dy(dy[b,r,n], dy2[b,r,n]) * pro_x(x[b, gather(r,k)]);
+ *   dbias[n]    += sum_{b,r} pro_dy(...) */
+typedef struct {
+    const float* dy;     /* dense [B,R,N] */
+    const float* dy2;    /* second input for CF_PRO_AFFINE2 or NULL */
+    const float* dy_a;   /* [B,N] tables */
+    const float* dy_b;
+    const float* dy_c;
+    const float* x;      /* dense [B,R,K] or gathered tensor */
+    const float* x_a;    /* [B,Cin] tables */
+    const float* x_b;
+    float* dw;           /* [N,K] (+=, caller zero-fills once per step) */
+    float* dbias;        /* [N] or NULL (+=) */
+    int B, K, N;
+    cf_geom g;
+    int gather_in;
+    int dy_mode, x_mode;
+} cf_pw_wgrad_args;
+int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream);
+size_t cf_sizeof_pw_args(void);
+size_t cf_sizeof_pw_wgrad_args(void);
+
+/* depthwise conv (channels-last).  g.(T,H,W) = output volume, g.(Ti,Hi,Wi) = input volume.
+ *   fwd  : y[B,T,H,W,C]   = sum_taps pro(x[B,Ti,Hi,Wi,C]) * w[C,taps]        (x3d_fine.py:89-97,153; conv1_t :216-222)
+ *   dgrad: y[B,Ti,Hi,Wi,C] = epi( sum_taps pro(x[B,T,H,W,C], x2) * w[C,taps] ),  aux/epi tables at the
+ *          input positions (the pre-activation the forward prologue consumed)
+ *   wgrad: y[C,taps] += sum_pos pro(x[pos], x2[pos]) * act(aux[pos_in(tap)]),  act = relu(epi_a*aux+epi_b)
+ *          when epi_a != NULL (x = output gradient, aux = forward input) */
+typedef struct {
+    const float* x;
+    const float* x2;
+    const float* w;
+    float* y;
+    const float* pro_a;
+    const float* pro_b;
+    const float* pro_c;
+    const float* aux;
+    const float* epi_a;
+    const float* epi_b;
+    double* stats;       /* [B,C,2] */
+    int B, C;
+    cf_geom g;
+    int pro_mode, epi_mode, stats_mode;
+} cf_dw_args;
+int cf_dw_conv_fwd(const cf_dw_args* a, cudaStream_t stream);
+int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream);
+int cf_dw_conv_wgrad(const cf_dw_args* a, cudaStream_t stream);
+size_t cf_sizeof_dw_args(void);
+
+/* SubBatchNorm3d (x3d_fine.py:13-62): per-sample statistics -> per-(sample,channel) affine
+ * tables tab_a*y + tab_b == weight*BN(y)+bias.  training: batch statistics per split group
+ * (sample b belongs to group b % splits, channel index g*C+c of split_bn), running stats of
+ * split_bn updated with `momentum` (unbiased variance); eval: running stats of `bn`. */
+typedef struct {
+    const double* stats;     /* [B,C,2] (sum y, sum y^2) per sample; unused in eval */
+    const float* gamma;      /* [C] */
+    const float* beta;       /* [C] */
+    float* running_mean;     /* training: [splits*C] (updated); eval: [C] (read) */
+    float* running_var;
+    float* tab_a;            /* [B,C] out */
+    float* tab_b;            /* [B,C] out */
+    float* mean;             /* [splits,C] out (saved for backward) */
+    float* invstd;           /* [splits,C] out */
+    int B, C, splits;
+    int64_t rows_per_sample;
+    float momentum, eps;
+    int training;
+} cf_bn_args;
+int cf_bn_finalize(const cf_bn_args* a, cudaStream_t stream);
+
+/* BatchNorm backward as an affine map: dy = P*d + Q*y + R per (sample,channel), where d is the
+ * tensor the sums were taken of.  sums[b,c] = (sum dz, sum dz*y) of the gradient w.r.t. the BN
+ * output.  Optional SE coupling: dz = gate*d + cst (see cf_se_bwd) => P = c1*gate, R += c1*cst.
+ * dgamma/dbeta accumulate (+=).  training==0: running-stat BN, dy = a*dz. */
+typedef struct {
+    const double* sums;      /* [B,C,2] */
+    const float* gamma;      /* [C] */
+    const float* mean;       /* [splits,C] */
+    const float* invstd;     /* [splits,C] */
+    const float* gate;       /* [B,C] or NULL */
+    const float* cst;        /* [B,C] or NULL */
+    float* dgamma;           /* [C] += */
+    float* dbeta;            /* [C] += */
+    float* tab_p;            /* [B,C] out */
+    float* tab_q;
+    float* tab_r;
+    int B, C, splits;
+    int64_t rows_per_sample;
+    int training;
+} cf_bn_bwd_args;
+int cf_bn_bwd_coeffs(const cf_bn_bwd_args* a, cudaStream_t stream);
+
+/* Squeeze-and-Excitation (x3d_fine.py:157-163): pooled = mean_thw(bn2(y2)) from the statistics,
+ * hidden = relu(fc1 pooled), gate = sigmoid(fc2 hidden); the gate is folded into the tables
+ * (out_a = gate*tab_a, out_b = gate*tab_b) that the Swish prologue of conv3 consumes. */
+typedef struct {
+    const double* stats;     /* [B,C,2] of y2 */
+    const float* tab_a;      /* [B,C] BN2 tables */
+    const float* tab_b;
+    const float* w1;         /* fc1.weight [Wd,C] */
+    const float* b1;         /* [Wd] */
+    const float* w2;         /* fc2.weight [C,Wd] */
+    const float* b2;         /* [C] */
+    float* pooled;           /* [B,C]  saved */
+    float* hidden;           /* [B,Wd] saved */
+    float* gate;             /* [B,C]  saved */
+    float* out_a;            /* [B,C] */
+    float* out_b;            /* [B,C] */
+    int B, C, Wd;
+    int64_t rows_per_sample;
+} cf_se_args;
+int cf_se_fwd(const cf_se_args* a, cudaStream_t stream);
+
+/* SE backward.  In: sums[b,c] = (sum dU, sum dU*y2) with dU = dL/d(gate*bn2(y2)).  Out (in
+ * place): sums of dz = gate*dU + cst w.r.t. bn2's output, cst[b,c] = dL/dpooled / R; fc grads +=. */
+typedef struct {
+    double* sums;            /* [B,C,2] in/out */
+    const double* stats_y;   /* [B,C,2] forward statistics of y2 */
+    const float* tab_a;      /* BN2 tables [B,C] (before the gate) */
+    const float* tab_b;
+    const float* w1;
+    const float* w2;
+    const float* pooled;
+    const float* hidden;
+    const float* gate;
+    float* dw1;              /* += */
+    float* db1;
+    float* dw2;
+    float* db2;
+    float* cst;              /* [B,C] out */
+    int B, C, Wd;
+    int64_t rows_per_sample;
+} cf_se_bwd_args;
+int cf_se_bwd(const cf_se_bwd_args* a, cudaStream_t stream);
+
+/* residual join (x3d_fine.py:169-173): out = relu(a3*y3 + b3 + res'),
+ * res' = ar*res + br (downsample branch, tables) or res (identity) or 0 (res == NULL). */
+typedef struct {
+    const float* y;          /* [B,R,C] */
+    const float* tab_a;      /* [B,C] */
+    const float* tab_b;
+    const float* res;        /* [B,R,C] or NULL */
+    const float* res_a;      /* [B,C] or NULL */
+    const float* res_b;
+    float* out;              /* [B,R,C] */
+    int B, C;
+    int64_t rows_per_sample;
+} cf_residual_args;
+int cf_residual_fwd(const cf_residual_args* a, cudaStream_t stream);
+
+/* backward of the join: dz = dout * [out > 0]; sums_y[b,c] = (sum dz, sum dz*y);
+ * sums_res likewise against `res` (downsample branch pre-BN tensor) when given. */
+typedef struct {
+    const float* dout;
+    const float* out;
+    const float* y;
+    const float* res;        /* or NULL */
+    float* dz;
+    double* sums_y;          /* [B,C,2] */
+    double* sums_res;        /* [B,C,2] or NULL */
+    int B, C;
+    int64_t rows_per_sample;
+} cf_residual_bwd_args;
+int cf_residual_bwd(const cf_residual_bwd_args* a, cudaStream_t stream);
+
+/* block average pooling over (H,W) of a channels-last tensor with an optional bn+relu
+ * prologue: AdaptiveAvgPool3d((None,1,1)) (x3d_fine.py:255,366) and
+ * adaptive_avg_pool3d(x,(None,7,7)) (x3d_fine.py:345-360) when H,W are multiples of the output.
+ * x [B,T,H,W,C] -> y [B,T,H/rh,W/rw,C]. */
+typedef struct {
+    const float* x;
+    float* y;
+    const float* tab_a;      /* [B,C] or NULL (no prologue) */
+    const float* tab_b;
+    int B, C, T, H, W, rh, rw;
+} cf_pool_args;
+int cf_block_avgpool_fwd(const cf_pool_args* a, cudaStream_t stream);
+/* backward: dz[B,T,H,W,C] = dy/(rh*rw) * [tab_a*x+tab_b > 0] (x = pre-activation, when tables given);
+ * sums[b,c] = (sum dz, sum dz*x).  `accumulate`: dz += ... */
+typedef struct {
+    const float* dy;         /* [B,T,H/rh,W/rw,C] */
+    const float* x;          /* pre-activation [B,T,H,W,C] or NULL */
+    const float* tab_a;
+    const float* tab_b;
+    float* dz;               /* [B,T,H,W,C] */
+    double* sums;            /* [B,C,2] or NULL */
+    int B, C, T, H, W, rh, rw;
+    int accumulate;
+} cf_pool_bwd_args;
+int cf_block_avgpool_bwd(const cf_pool_bwd_args* a, cudaStream_t stream);
+
+/* out = dy * [y > 0]  (backward of a materialised ReLU, e.g. after fc1: x3d_fine.py:371) */
+int cf_relu_bwd(const float* dy, const float* y, float* out, int64_t n, cudaStream_t stream);
+
+/* standalone module surfaces (SubBatchNorm3d.forward x3d_fine.py:51-62, Swish :65-86) */
+/* stats[b,c] += (sum x, sum x*y) (y == NULL: sum x^2) over the rows of sample b */
+int cf_channel_stats(const float* x, const float* y, double* stats, int B, int C, int64_t rows_per_sample,
+                     cudaStream_t stream);
+/* out = pro(x, x2) with per-(sample,channel) tables, mode = CF_PRO_* */
+typedef struct {
+    const float* x;
+    const float* x2;
+    const float* tab_a;
+    const float* tab_b;
+    const float* tab_c;
+    float* out;
+    int B, C;
+    int64_t rows_per_sample;
+    int mode;
+} cf_affine_args;
+int cf_affine_apply(const cf_affine_args* a, cudaStream_t stream);
+int cf_swish_fwd(const float* x, float* out, int64_t n, cudaStream_t stream);
+int cf_swish_bwd(const float* x, const float* dy, float* dx, int64_t n, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
