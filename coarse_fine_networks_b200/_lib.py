@@ -112,7 +112,9 @@ def _parse_structs():
 
 
 STRUCTS = _parse_structs()
-for _sname in ("cf_pw_args", "cf_pw_wgrad_args", "cf_dw_args"):
+for _sname in STRUCTS:
+    if ("cf_sizeof_" + _sname[3:]) not in PROTOS:
+        continue
     _sz = getattr(lib, "cf_sizeof_" + _sname[3:])()
     if _sz != ctypes.sizeof(STRUCTS[_sname]):
         raise ImportError(f"ABI mismatch for {_sname}: library {_sz} bytes, header {ctypes.sizeof(STRUCTS[_sname])}")

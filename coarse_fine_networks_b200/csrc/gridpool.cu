@@ -149,6 +149,58 @@ __global__ void inverse_cdf_bwd_kernel(const float* __restrict__ cdf, const int*
 }
 
 // ---------------------------------------------------------------------------------------
+// general Interp1d (interp1d.py:100-141): D rows, N knots, P queries; a row stride of 0
+// broadcasts a single row ("flat" inputs of the reference)
+// ---------------------------------------------------------------------------------------
+__global__ void interp1d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                    const float* __restrict__ xnew, float* __restrict__ ynew, int* __restrict__ ind,
+                                    int D, int N, int P, int xrs, int yrs, int qrs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * P) return;
+    int d = i / P, j = i - d * P;
+    const float* xr = x + (size_t)d * xrs;
+    const float* yr = y + (size_t)d * yrs;
+    float q = xnew[(size_t)d * qrs + j];
+    int lo = 0, hi = N;                               // lower_bound: first index with x >= q
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (xr[mid] < q) lo = mid + 1; else hi = mid;
+    }
+    int id = lo - 1;
+    id = id < 0 ? 0 : (id > N - 2 ? N - 2 : id);
+    const float eps = 1.1920928955078125e-07f;
+    float slope = __fdiv_rn(__fsub_rn(yr[id + 1], yr[id]), __fadd_rn(eps, __fsub_rn(xr[id + 1], xr[id])));
+    ynew[i] = __fadd_rn(yr[id], __fmul_rn(slope, __fsub_rn(q, xr[id])));
+    ind[i] = id;
+}
+
+__global__ void interp1d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                    const float* __restrict__ xnew, const int* __restrict__ ind,
+                                    const float* __restrict__ dynew, float* dx, float* dy, float* dq, int D, int N, int P,
+                                    int xrs, int yrs, int qrs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * P) return;
+    int d = i / P, j = i - d * P;
+    const float* xr = x + (size_t)d * xrs;
+    const float* yr = y + (size_t)d * yrs;
+    int id = ind[i];
+    float q = xnew[(size_t)d * qrs + j], go = dynew[i];
+    const float eps = 1.1920928955078125e-07f;
+    float Dn = eps + (xr[id + 1] - xr[id]);
+    float slope = (yr[id + 1] - yr[id]) / Dn;
+    float r = (q - xr[id]) / Dn;
+    if (dx) {
+        atomicAdd(dx + (size_t)d * xrs + id, go * slope * (r - 1.0f));
+        atomicAdd(dx + (size_t)d * xrs + id + 1, -go * slope * r);
+    }
+    if (dy) {
+        atomicAdd(dy + (size_t)d * yrs + id, go * (1.0f - r));
+        atomicAdd(dy + (size_t)d * yrs + id + 1, go * r);
+    }
+    if (dq) atomicAdd(dq + (size_t)d * qrs + j, go * slope);
+}
+
+// ---------------------------------------------------------------------------------------
 // K11 forward: out[o,k,:] = (1-w1) x[o,i0,:] + w1 x[o,i0+1,:]   (zero padding outside [0,T-1])
 // ---------------------------------------------------------------------------------------
 template <typename V> struct VecOps;
@@ -365,6 +417,28 @@ int cf_inverse_cdf_bwd(const float* cdf, const int32_t* ind, const float* dinv, 
                        cudaStream_t stream) {
     CF_CHECK_ARG(cdf && ind && dinv && dcdf_accum && B > 0 && K > 1, "bad argument");
     inverse_cdf_bwd_kernel<<<cf_cdiv(B, 64), 64, 0, stream>>>(cdf, ind, dinv, dcdf_accum, B, K);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}
+
+int cf_interp1d_fwd(const float* x, const float* y, const float* xnew, float* ynew, int32_t* ind, int D, int N, int P,
+                    int x_row_stride, int y_row_stride, int xnew_row_stride, cudaStream_t stream) {
+    CF_CHECK_ARG(x && y && xnew && ynew && ind && D > 0 && N > 1 && P > 0, "bad argument");
+    interp1d_fwd_kernel<<<cf_cdiv((long long)D * P, 128), 128, 0, stream>>>(x, y, xnew, ynew, ind, D, N, P, x_row_stride,
+                                                                         y_row_stride, xnew_row_stride);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}
+
+int cf_interp1d_bwd(const float* x, const float* y, const float* xnew, const int32_t* ind, const float* dynew, float* dx_accum,
+                    float* dy_accum, float* dxnew_accum, int D, int N, int P, int x_row_stride, int y_row_stride,
+                    int xnew_row_stride, cudaStream_t stream) {
+    CF_CHECK_ARG(x && y && xnew && ind && dynew && D > 0 && N > 1 && P > 0, "bad argument");
+    interp1d_bwd_kernel<<<cf_cdiv((long long)D * P, 128), 128, 0, stream>>>(x, y, xnew, ind, dynew, dx_accum, dy_accum,
+                                                                         dxnew_accum, D, N, P, x_row_stride, y_row_stride,
+                                                                         xnew_row_stride);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

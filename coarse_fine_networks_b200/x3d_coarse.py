@@ -1,0 +1,254 @@
+"""Coarse stream (X3D + Grid Pool + Multi-stage Fusion + Grid Unpool) -- drop-in for the
+reference's ``x3d_coarse.py`` module surface (x3d_coarse.py:175-750).
+
+Same constructor arguments, ``forward([x, feat, feat_masks, i, meta])`` convention, helper
+methods and state-dict key layout as the reference, so ``train_coarse_fineFEAT.py`` call sites
+and the shipped ``coarse_fineFEAT_charades_*.pt`` checkpoint work unchanged.  nn.Conv1d / nn.Conv3d
+/ nn.Linear sub-modules are parameter holders only; all arithmetic runs in libcfnet_b200.so.
+
+What differs from the reference on purpose (same results):
+  * the whole fusion block is evaluated at the 7x7 resolution of the fine features; the
+    reference's up-sampled 6-D broadcast products are never built;
+  * Grid Pool sampling is a temporal lerp gather (no meshgrid, no 5-D grid tensor);
+  * activations are channels-last in HBM; the module boundary accepts and returns the
+    reference's logical NCTHW shapes.
+"""
+import torch
+import torch.nn as nn
+
+from . import fusion_ops as FU
+from . import gridpool_ops as G
+from . import x3d_ops as X
+from .interp1d import Interp1d  # noqa: F401  (re-exported like the reference's import)
+from .x3d_fine import (Bottleneck, SubBatchNorm3d, Swish, SwishEfficient, _SimpleCfg, conv1x1x1,  # noqa: F401
+                       conv3x3x3, get_blocks, get_inplanes)
+from .x3d_fine import ResNet as _FineResNet
+
+
+# ----------------------------------------------------------------------------------------
+class RewightLayer(nn.Module):
+    """Self-attention filter + Gaussian-aligned aggregation + the two k=1 MLPs that emit the
+    shift ("bias") and scale maps (x3d_coarse.py:175-247)."""
+
+    def __init__(self, channels, g_channels, depth, height, pool=False):
+        super().__init__()
+        self.at1 = nn.Conv1d(depth, depth, kernel_size=1)
+        self.at2 = nn.Conv1d(depth, 1, kernel_size=1)
+        self.fc1 = nn.Conv1d(depth, depth, kernel_size=1)
+        self.fc2 = nn.Conv1d(depth, channels, kernel_size=1)
+        if g_channels is not None:
+            self.fc3 = nn.Conv1d(depth, depth, kernel_size=1)
+            self.fc4 = nn.Conv1d(depth, g_channels, kernel_size=1)
+        self.dropout = nn.Dropout(0.5)
+        self.depth, self.height, self.channels, self.g_channels, self.pool = depth, height, channels, g_channels, pool
+
+    def forward_base(self, x, mask, GX, isMixing):
+        """x [B,C,Tf,h,w] -> (bias, scale) at the base resolution: [B,ch,Tl,h,w] ([B,ch,Tl,1,1] if pool)."""
+        x = X.cl(x)
+        B, C, Tf, h, w = x.shape
+        if mask.shape[1] != Tf:
+            raise NotImplementedError("mask / feature length mismatch (x3d_coarse.py:205-207) is not built")
+        Tl = GX.shape[2]
+        P = h * w
+        rows = FU.rows_of(x)                                               # [B, Tf*P, C]
+        att = FU.linear_rows(FU.linear_rows(rows, self.at1, X.ACT_RELU), self.at2, X.ACT_SIGMOID)      # :216-219
+        agg = FU.RewightAggFn.apply(rows.view(B, Tf, P, C), att.view(B, Tf, P), GX, mask)               # :221-225
+        if self.pool:                                                      # :227-228
+            agg = X.AvgPoolFn.apply(agg.view(B, Tl, h, w, C).permute(0, 4, 1, 2, 3), h, w)
+            agg = agg.permute(0, 2, 3, 4, 1).reshape(B, Tl, C)
+            h = w = 1
+        else:
+            agg = agg.view(B, Tl * P, C)
+        x1 = FU.linear_rows(agg, self.fc1, X.ACT_RELU)
+        if self.pool:
+            x1 = self.dropout(x1)
+        x1 = FU.from_rows(FU.linear_rows(x1, self.fc2), Tl, h, w)
+        if self.g_channels is None:
+            return x1, None
+        x2 = FU.linear_rows(agg, self.fc3, X.ACT_RELU)
+        if self.pool:
+            x2 = self.dropout(x2)
+        x2 = FU.from_rows(FU.linear_rows(x2, self.fc4, X.ACT_NONE if isMixing else X.ACT_SIGMOID), Tl, h, w)
+        return x1, x2
+
+    def forward(self, inp):
+        x, lx, mask, gx, i, GX, isMixing = inp
+        if x.shape[0] != lx.shape[0]:
+            raise NotImplementedError("multi-crop testing (x3d_coarse.py:209-211) is not built")
+        x1, x2 = self.forward_base(x, mask, GX, isMixing)
+        if not self.pool and x.shape[3] != self.height:
+            x1 = FU.NearestUpFn.apply(x1, self.height, self.height)
+            x2 = FU.NearestUpFn.apply(x2, self.height, self.height) if x2 is not None else None
+        return x1 if x2 is None else (x1, x2)
+
+
+class Gaussian(nn.Module):
+    """Temporal alignment weights between fine steps and coarse sample points (x3d_coarse.py:251-286)."""
+
+    def __init__(self, ratio=1):
+        super().__init__()
+        self.ratio = ratio
+
+    def forward(self, inp):
+        meta, mask, gx, tx = inp
+        if tx is None:
+            raise NotImplementedError("Gaussian without a Grid Pool CDF (t_pool != 'grid') is not built")
+        if gx.shape[0] != meta.shape[0]:
+            raise NotImplementedError("multi-crop testing (x3d_coarse.py:264-266) is not built")
+        return FU.GaussianFn.apply(gx, meta[:, 0].float(), mask, float(tx), float(self.ratio))
+
+
+class MixingLayer(nn.Module):
+    """Mixes the four stage-wise shift / scale maps into the one applied at this stage
+    (x3d_coarse.py:289-351)."""
+
+    def __init__(self, depth, learned=False, index=0, isLogit=False):
+        super().__init__()
+        self.learned, self.index, self.isLogit = learned, index, isLogit
+        self.in_depth = 432 if isLogit else (24 + 48 + 96 + 192)
+        self.range = 1 if isLogit else 4
+        self.dropout = nn.Dropout(0.5)
+        if learned:
+            self.conv_at = nn.Conv1d(self.in_depth, depth, kernel_size=1)
+            self.conv_at2 = nn.Conv1d(self.in_depth, depth, kernel_size=1)
+
+    def mix(self, bias, scale, h, w):
+        """bias/scale: lists of [B,c_i,Tl,h,w] maps at one common resolution -> (cs, ms) [B,depth,Tl,h,w]."""
+        Tl = bias[0].shape[2]
+        cs = torch.cat([FU.rows_of(t) for t in bias[:self.range]], dim=2)          # :327
+        ms = torch.cat([FU.rows_of(t) for t in scale[:self.range]], dim=2)         # :328
+        if not self.learned:
+            raise NotImplementedError("learnedMixing=False (one-hot stage select, x3d_coarse.py:339-344) is not built")
+        if self.isLogit:
+            cs, ms = self.dropout(cs), self.dropout(ms)
+        cs = FU.linear_rows(cs, self.conv_at)                                      # :335
+        ms = FU.linear_rows(ms, self.conv_at2, X.ACT_SIGMOID)                      # :336
+        return FU.from_rows(cs, Tl, h, w), FU.from_rows(ms, Tl, h, w)
+
+    def forward(self, inp):
+        x, bias, scale = inp
+        h, w = x.shape[3], x.shape[4]
+        bias = [FU.resize_map(t, h, w) for t in bias[:self.range]]                 # :312-325
+        scale = [FU.resize_map(t, h, w) for t in scale[:self.range]]
+        return self.mix(bias, scale, h, w)
+
+
+class _PoolCfg:
+    def __init__(self, training, bn1, bn2):
+        self.training, self.bn1, self.bn2 = training, X.BNCfg(bn1), X.BNCfg(bn2)
+
+
+class GridPoolLayer(nn.Module):
+    """Learnable temporal Grid Pool (x3d_coarse.py:355-416): per-interval confidence -> CDF ->
+    inverse-transform sample points -> temporal lerp gather.  Returns (x_pooled, cdf)."""
+
+    def __init__(self, ratio, depth):
+        super().__init__()
+        self.ratio = 4                                       # hard-coded in the reference (:359)
+        self.depth = depth
+        self.conv1 = nn.Conv3d(depth, depth, kernel_size=3, stride=(self.ratio // 2, 2, 2), padding=1)
+        self.bn1 = SubBatchNorm3d(num_splits=1, num_features=depth, affine=True)
+        self.conv2 = nn.Conv3d(depth, depth, kernel_size=3, stride=(self.ratio // 2, 2, 2), padding=1)
+        self.bn2 = SubBatchNorm3d(num_splits=1, num_features=depth, affine=True)
+        self.conv3 = nn.Conv3d(depth, 1, kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1))
+        self.relu = nn.ReLU(inplace=True)
+        self.sigmoid = nn.Sigmoid()
+
+    def confidence(self, x):
+        return FU.ConfidenceFn.apply(x, _PoolCfg(self.training, self.bn1, self.bn2), self.conv1.weight, self.conv1.bias,
+                                     self.bn1.weight, self.bn1.bias, self.conv2.weight, self.conv2.bias, self.bn2.weight,
+                                     self.bn2.bias, self.conv3.weight, self.conv3.bias)
+
+    def forward(self, inp):
+        x = X.cl(inp)
+        cdf = G.gridpool_cdf(self.confidence(x))             # :379-392
+        return G.temporal_sample(x, cdf), cdf                # :394-403
+
+
+def GridUnpool(inp):
+    """Inverse of the Grid Pool re-sampling (x3d_coarse.py:419-451)."""
+    x, gx, is_logit = inp
+    return G.grid_unpool(x, gx, bool(is_logit), ratio=4)
+
+
+# ----------------------------------------------------------------------------------------
+class ResNet(_FineResNet):
+    """Coarse-stream X3D with Grid Pool after layer1, Multi-stage Fusion of the fine features
+    before layer2..layer4 / conv5 and on the logits, Grid Unpool at the end (x3d_coarse.py:455-727)."""
+
+    def __init__(self, block, layers, block_inplanes, n_input_channels=3, feat_depth={}, conv1_t_size=7, conv1_t_stride=1,
+                 shortcut_type='B', widen_factor=1.0, dropout=0.5, n_classes=400, base_bn_splits=8, task='class',
+                 extract_feat=False, t_pool=None, learnedMixing=False, isMixing=False):
+        super().__init__(block, layers, block_inplanes, n_input_channels=n_input_channels, conv1_t_size=conv1_t_size,
+                         conv1_t_stride=conv1_t_stride, shortcut_type=shortcut_type, widen_factor=widen_factor,
+                         dropout=dropout, n_classes=n_classes, base_bn_splits=base_bn_splits, task=task,
+                         extract_feat=extract_feat, global_tower=False, t_downsample=False)
+        planes = [(int(a * widen_factor), int(b * widen_factor)) for a, b in block_inplanes]
+        self.feat_depth = feat_depth
+        self.learnedMixing, self.isMixing, self.t_pool = learnedMixing, isMixing, t_pool
+        if t_pool == 'avg':
+            self.pool_1 = nn.AvgPool3d((4, 1, 1), stride=(4, 1, 1))
+        elif t_pool == 'max':
+            self.pool_1 = nn.MaxPool3d((4, 1, 1), stride=(4, 1, 1))
+        elif t_pool == 'grid':
+            self.pool_1 = GridPoolLayer(ratio=4, depth=planes[0][1])
+        self.rw2 = RewightLayer(planes[0][1], planes[0][1], feat_depth['layer1'], height=56)
+        self.rw3 = RewightLayer(planes[1][1], planes[1][1], feat_depth['layer2'], height=28)
+        self.rw4 = RewightLayer(planes[2][1], planes[2][1], feat_depth['layer3'], height=14)
+        self.rw5 = RewightLayer(planes[3][1], planes[3][1], feat_depth['layer4'], height=7)
+        self.rw6 = RewightLayer(157, 157, feat_depth['conv5'], height=7, pool=True)
+        if isMixing:
+            for i in range(4):
+                setattr(self, f"mix{i + 2}", MixingLayer(depth=planes[i][1], learned=learnedMixing, index=i))
+        self.gauss = Gaussian(ratio=1)
+        for m in self.modules():                             # same init rule as the reference (:557-561)
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+
+    def replace_logits(self, n_classes):
+        dev = self.fc1.weight.device
+        self.fc2 = nn.Linear(2048, n_classes).to(dev)
+        self.rw6 = RewightLayer(n_classes, n_classes, self.feat_depth['conv5'], height=7, pool=True).to(dev)
+
+    def forward(self, inp):
+        x, feat, feat_masks, i, meta = inp
+        t_in = x.shape[2]
+        if self.t_pool != 'grid':
+            raise NotImplementedError("only t_pool='grid' (the configuration of train_coarse_fineFEAT.py:107-109) is built")
+        x = self.layer1(self._stem(x))                                         # :633-638
+        x, gx = self.pool_1(x)                                                 # :646-649
+        GX = self.gauss([meta, feat_masks, gx, t_in])                          # :650
+        keys = ('layer1', 'layer2', 'layer3', 'layer4')
+        rws = (self.rw2, self.rw3, self.rw4, self.rw5)
+        layers = (self.layer2, self.layer3, self.layer4, None)
+        if self.isMixing:                                                      # :655-679
+            maps = [rw.forward_base(feat[k], feat_masks, GX, True) for rw, k in zip(rws, keys)]
+            bias, scale = [m[0] for m in maps], [m[1] for m in maps]
+            hb, wb = bias[0].shape[3], bias[0].shape[4]
+            for j, layer in enumerate(layers):
+                c, m = getattr(self, f"mix{j + 2}").mix(bias, scale, hb, wb)
+                x = FU.FilmFn.apply(x, m, c)
+                if layer is not None:
+                    x = layer(x)
+        else:                                                                  # :681-699
+            for rw, k, layer in zip(rws, keys, layers):
+                c, m = rw.forward_base(feat[k], feat_masks, GX, False)
+                x = FU.FilmFn.apply(x, m, c)
+                if layer is not None:
+                    x = layer(x)
+        B, _, Tl, H, W = x.shape
+        pooled = self._conv5_pool(x, H, W)                                     # :700-702
+        if self.task == 'class':
+            pooled = pooled.mean(dim=2, keepdim=True)
+        if self.extract_feat:
+            return pooled
+        logits = self._head(pooled)                                            # [B,n_cls,Tl]  :706-716
+        b6, s6 = self.rw6.forward_base(feat['conv5'], feat_masks, GX, False)   # :719-720
+        lg = logits.unsqueeze(3).unsqueeze(4)
+        x = FU.FilmFn.apply(lg, s6, b6).squeeze(4).squeeze(3)                  # :721
+        x = GridUnpool([x, gx, True])                                          # :724
+        return G.linear_upsample_t(x, (x.shape[2] - 1) * 4)                    # :725
+
+
+def generate_model(x3d_version, **kwargs):
+    return ResNet(Bottleneck, get_blocks(x3d_version), get_inplanes(x3d_version), **kwargs)

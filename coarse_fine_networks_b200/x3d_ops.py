@@ -11,7 +11,7 @@ from ._lib import STRUCTS, call, call_struct, make, ptr, stream_ptr
 CL3 = torch.channels_last_3d
 
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU, PRO_AFFINE_SWISH, PRO_AFFINE2 = 0, 1, 2, 3, 4
-EPI_NONE, EPI_RELU, EPI_DRELU, EPI_DSWISH, EPI_ADD_AUX = 0, 1, 2, 3, 4
+EPI_NONE, EPI_RELU, EPI_DRELU, EPI_DSWISH, EPI_ADD_AUX, EPI_SIGMOID = 0, 1, 2, 3, 4, 5
 STATS_NONE, STATS_SUM_SQ, STATS_SUM_AUX = 0, 1, 2
 
 
@@ -376,20 +376,25 @@ class AvgPoolFn(torch.autograd.Function):
         return dz, None, None
 
 
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+
 class LinearRowsFn(torch.autograd.Function):
     """y[b,r,:] = act(W x[b,r,:] + bias) on a [B,R,K] row tensor: fc1 (1x1x1 conv, no bias, + ReLU)
-    and fc2 (nn.Linear) of the head (x3d_fine.py:370-380), k=1 Conv1d layers of the fusion block."""
+    and fc2 (nn.Linear) of the head (x3d_fine.py:370-380), and the k=1 Conv1d layers of the fusion
+    block (x3d_coarse.py:216-219,232-246,335-336).  act: ACT_NONE / ACT_RELU / ACT_SIGMOID."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, relu):
+    def forward(ctx, x, w, bias, act):
+        act = int(act)
         x = x.contiguous().float()
         B, R, K = x.shape
         w2 = w.reshape(w.shape[0], -1)
         N = w2.shape[0]
         y = torch.empty(B, R, N, device=x.device, dtype=torch.float32)
-        pw_conv(x, w2, y, B, K, N, geom(R, 1, 1), bias=bias, epi=EPI_RELU if relu else EPI_NONE)
-        ctx.relu, ctx.dims, ctx.wshape, ctx.has_bias = relu, (B, R, K, N), w.shape, bias is not None
-        ctx.save_for_backward(x, w2, y if relu else None)
+        pw_conv(x, w2, y, B, K, N, geom(R, 1, 1), bias=bias, epi=(EPI_NONE, EPI_RELU, EPI_SIGMOID)[act])
+        ctx.act, ctx.dims, ctx.wshape, ctx.has_bias = act, (B, R, K, N), w.shape, bias is not None
+        ctx.save_for_backward(x, w2, y if act else None)
         return y
 
     @staticmethod
@@ -398,10 +403,11 @@ class LinearRowsFn(torch.autograd.Function):
         B, R, K, N = ctx.dims
         dy = dy.contiguous().float()
         g = geom(R, 1, 1)
-        if ctx.relu:                      # dy *= [y > 0]
-            dyr = torch.empty_like(dy)
-            call("cf_relu_bwd", ptr(dy), ptr(y), ptr(dyr), dy.numel(), stream_ptr())
-            dy = dyr
+        if ctx.act:                       # dy *= act'(y)
+            dya = torch.empty_like(dy)
+            call("cf_relu_bwd" if ctx.act == ACT_RELU else "cf_sigmoid_bwd", ptr(dy), ptr(y), ptr(dya), dy.numel(),
+                 stream_ptr())
+            dy = dya
         dw, db = _flat_grads([w2, torch.empty(N) if ctx.has_bias else None], dy.device)
         pw_wgrad(dy, x, dw, B, K, N, g, dbias=db)
         dx = None

@@ -55,6 +55,16 @@ int cf_inverse_cdf_fwd(const float* cdf, float* inv, int32_t* ind, int B, int K,
 int cf_inverse_cdf_bwd(const float* cdf, const int32_t* ind, const float* dinv, float* dcdf_accum, int B, int K,
                        cudaStream_t stream);
 
+/* ---- general Interp1d()(x, y, xnew) (interp1d.py:4-141): D rows of N knots, P queries per row;
+ * ind = clamp(searchsorted(x,xnew)-1, 0, N-2); ynew = y[ind] + slope[ind]*(xnew - x[ind]),
+ * slope = (y[1:]-y[:-1])/(eps + x[1:]-x[:-1]).  A row stride of 0 broadcasts one row. */
+int cf_interp1d_fwd(const float* x, const float* y, const float* xnew, float* ynew, int32_t* ind, int D, int N, int P,
+                    int x_row_stride, int y_row_stride, int xnew_row_stride, cudaStream_t stream);
+/* gradients accumulate (+=) into zero-filled buffers laid out like the inputs; NULL skips one */
+int cf_interp1d_bwd(const float* x, const float* y, const float* xnew, const int32_t* ind, const float* dynew, float* dx_accum,
+                    float* dy_accum, float* dxnew_accum, int D, int N, int P, int x_row_stride, int y_row_stride,
+                    int xnew_row_stride, cudaStream_t stream);
+
 /* ---- temporal lerp gather = F.grid_sample along T (x3d_coarse.py:396-403, 442-445) ---- */
 /* out[o,k,:] = (1-w1[b,k]) x[o,i0[b,k],:] + w1[b,k] x[o,i0[b,k]+1,:],  b = o / outer_per_b,
  * frames outside [0,T-1] contribute zero.  x [outer,T,inner] -> out [outer,K,inner]. */
@@ -91,6 +101,7 @@ int cf_temporal_gather_bwd_coord(const float* gout, const float* x, const int32_
 #define CF_EPI_DRELU 2         /* acc * [ea*aux + eb > 0]             */
 #define CF_EPI_DSWISH 3        /* acc * swish'(ea*aux + eb)           */
 #define CF_EPI_ADD_AUX 4       /* acc + aux                           */
+#define CF_EPI_SIGMOID 5       /* sigmoid(acc + bias)                 */
 /* statistics accumulated (double atomics) into stats[b][n][0..1] */
 #define CF_STATS_NONE 0
 #define CF_STATS_SUM_SQ 1      /* sum y, sum y^2      (forward: BatchNorm + SE pooling) */
@@ -359,6 +370,94 @@ typedef struct {
 int cf_affine_apply(const cf_affine_args* a, cudaStream_t stream);
 int cf_swish_fwd(const float* x, float* out, int64_t n, cudaStream_t stream);
 int cf_swish_bwd(const float* x, const float* dy, float* dx, int64_t n, cudaStream_t stream);
+
+/* out = dy * y * (1 - y)  (backward of a materialised sigmoid: x3d_coarse.py:219,245,336) */
+int cf_sigmoid_bwd(const float* dy, const float* y, float* out, int64_t n, cudaStream_t stream);
+
+/* ====================================================================================== */
+/* Multi-stage Fusion (x3d_coarse.py:175-351).  Fine-stream features are channels-last     */
+/* [B,Tf,P,C] row tensors with P = 7*7 pixels; everything is evaluated at that 7x7 base     */
+/* resolution (the reference's adaptive_max_pool2d up-sampling at :214,315,322 is an exact   */
+/* nearest replication, so every later op is constant over the replicated blocks) and only   */
+/* the final scale/shift (FiLM) kernel reads the base maps through an index map.             */
+/* ====================================================================================== */
+
+/* Gaussian.forward with tx given (x3d_coarse.py:256-286):
+ *   mu[b,k] = (cdf[b,k]*tx + start[b]) / ratio; sigma_b = sum_t mask[b,t] / 8;
+ *   f = exp(-(t-mu)^2 / (2 sigma^2 + 1e-16)); gx[b,t,k] = f / (max_t f + 1e-16). */
+int cf_gaussian_fwd(const float* cdf, const float* start, const float* mask, float* gx, int B, int Tf, int Tl,
+                    float tx, float ratio, cudaStream_t stream);
+/* dcdf_accum[b,k] += d gx / d cdf ^T dgx (through mu and through the max) */
+int cf_gaussian_bwd(const float* cdf, const float* start, const float* mask, const float* dgx, float* dcdf_accum,
+                    int B, int Tf, int Tl, float tx, float ratio, cudaStream_t stream);
+
+/* RewightLayer aligned aggregation (x3d_coarse.py:221-225):
+ *   A[t,k,p] = att[t,p]*gx[t,k];  den[k,p] = sum_t A*mask + 1e-6;
+ *   agg[k,p,c] = sum_t x[t,p,c] * A[t,k,p] * mask[t] / den[k,p]          (per sample b) */
+typedef struct {
+    const float* x;          /* [B,Tf,P,C] */
+    const float* att;        /* [B,Tf,P]  sigmoid attention */
+    const float* gx;         /* [B,Tf,Tl] */
+    const float* mask;       /* [B,Tf] */
+    float* agg;              /* [B,Tl,P,C] out */
+    float* den;              /* [B,Tl,P] out (saved for backward) */
+    int B, C, Tf, Tl, P;
+} cf_rewight_args;
+int cf_rewight_agg_fwd(const cf_rewight_args* a, cudaStream_t stream);
+typedef struct {
+    const float* x;
+    const float* att;
+    const float* gx;
+    const float* mask;
+    const float* agg;
+    const float* den;
+    const float* dagg;       /* [B,Tl,P,C] */
+    float* dx;               /* [B,Tf,P,C] out, or NULL (fine features detached) */
+    float* datt;             /* [B,Tf,P] out */
+    float* dgx;              /* [B,Tf,Tl] += (caller zero-fills) */
+    int B, C, Tf, Tl, P;
+} cf_rewight_bwd_args;
+int cf_rewight_agg_bwd(const cf_rewight_bwd_args* a, cudaStream_t stream);
+size_t cf_sizeof_rewight_args(void);
+size_t cf_sizeof_rewight_bwd_args(void);
+
+/* scale/shift modulation x*m + c (x3d_coarse.py:664,669,674,679,721) with m, c given at a
+ * base resolution (Hb,Wb) dividing (H,W): out[b,t,y,x,ch] = x * scale[b,t,y/rh,x/rw,ch] + shift[...]. */
+typedef struct {
+    const float* x;          /* [B,T,H,W,C] */
+    const float* scale;      /* [B,T,Hb,Wb,C] */
+    const float* shift;      /* [B,T,Hb,Wb,C] */
+    float* out;              /* [B,T,H,W,C] */
+    int B, C, T, H, W, Hb, Wb;
+} cf_film_args;
+int cf_film_fwd(const cf_film_args* a, cudaStream_t stream);
+typedef struct {
+    const float* dout;       /* [B,T,H,W,C] */
+    const float* x;
+    const float* scale;
+    float* dx;               /* [B,T,H,W,C] out or NULL */
+    float* dscale;           /* [B,T,Hb,Wb,C] out */
+    float* dshift;           /* [B,T,Hb,Wb,C] out */
+    int B, C, T, H, W, Hb, Wb;
+} cf_film_bwd_args;
+int cf_film_bwd(const cf_film_bwd_args* a, cudaStream_t stream);
+size_t cf_sizeof_film_args(void);
+size_t cf_sizeof_film_bwd_args(void);
+
+/* nearest replication of a base map to (H,W) (what F.adaptive_max_pool2d computes at
+ * x3d_coarse.py:214,315,322 when H,W are multiples of Hb,Wb); module-surface outputs only. */
+int cf_nearest_up(const float* x, float* out, int B, int T, int Hb, int Wb, int H, int W, int C, cudaStream_t stream);
+/* backward: dx[b,t,yb,xb,c] = sum over the replicated block of dout */
+int cf_nearest_up_bwd(const float* dout, float* dx, int B, int T, int Hb, int Wb, int H, int W, int C,
+                      cudaStream_t stream);
+
+/* block max pooling over (H,W) of a channels-last map: F.adaptive_max_pool2d as a down-sampler
+ * (x3d_coarse.py:315,322, H,W multiples of the target).  idx = position of the (first) maximum
+ * inside the block, saved for the backward scatter.  x [B,T,H,W,C] -> out [B,T,H/rh,W/rw,C]. */
+int cf_block_maxpool_fwd(const float* x, float* out, int32_t* idx, int B, int T, int H, int W, int C, int rh, int rw,
+                         cudaStream_t stream);
+int cf_block_maxpool_bwd(const float* dout, const int32_t* idx, float* dx, int B, int T, int H, int W, int C, int rh, int rw,
+                         cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,7 @@ StateDict = Dict[str, Tensor]
 
 BN_EPS = 1e-5          # nn.BatchNorm3d default, x3d_fine.py:27-29
 BN_MOMENTUM = 0.1
+FP32_EPS = 1.1920928955078125e-07   # kept in every dtype so that an fp64 run referees the fp32 semantics
 
 
 # ----------------------------------------------------------------------------------------
@@ -228,7 +229,7 @@ def interp1d(x: Tensor, y: Tensor, xnew: Tensor) -> Tuple[Tensor, Tensor]:
     ind = clamp(searchsorted(x, xnew) - 1, 0, N-2) (:100-110, right=False);
     slope = (y[1:]-y[:-1]) / (eps + x[1:]-x[:-1]) with eps = fp32 machine eps (:37,133-137);
     ynew = y[ind] + slope[ind]*(xnew - x[ind]) (:140-141)."""
-    eps = torch.finfo(y.dtype).eps
+    eps = FP32_EPS            # torch.finfo(torch.float32).eps: the reference runs in fp32 (interp1d.py:37)
     ind = torch.searchsorted(x.detach().contiguous(), xnew.detach().contiguous()) - 1
     ind = ind.clamp(0, x.shape[1] - 2)
     slopes = (y[:, 1:] - y[:, :-1]) / (eps + (x[:, 1:] - x[:, :-1]))
@@ -239,7 +240,7 @@ def interp1d(x: Tensor, y: Tensor, xnew: Tensor) -> Tuple[Tensor, Tensor]:
 def inverse_cdf(cdf: Tensor) -> Tuple[Tensor, Tensor]:
     """x3d_coarse.py:435-438: mid = arange(N)/(N-1); gx_ = Interp1d()(cdf, mid, mid)."""
     n = cdf.shape[1]
-    mid = torch.arange(n, dtype=torch.float32, device=cdf.device)
+    mid = torch.arange(n, dtype=cdf.dtype, device=cdf.device)
     mid = (mid / (n - 1.0)).view(1, -1).repeat(cdf.shape[0], 1)
     return interp1d(cdf, mid, mid)
 
@@ -250,11 +251,11 @@ def linear_upsample_t(x: Tensor, t_out: int) -> Tensor:
     unchanged, hence identity in (H,W))."""
     t_in = x.shape[2]
     scale = (t_in - 1) / (t_out - 1) if t_out > 1 else 0.0
-    u = torch.arange(t_out, dtype=torch.float32, device=x.device)
-    src = u * torch.tensor(scale, dtype=torch.float32)
+    u = torch.arange(t_out, dtype=x.dtype, device=x.device)
+    src = u * torch.tensor(scale, dtype=x.dtype)
     j0 = src.to(torch.int64).clamp(max=t_in - 1)
     j1 = (j0 + 1).clamp(max=t_in - 1)
-    lam = (src - j0.to(torch.float32))
+    lam = (src - j0.to(x.dtype))
     shp = (1, 1, t_out) + (1,) * (x.dim() - 3)
     return x.index_select(2, j0) * (1 - lam).view(shp) + x.index_select(2, j1) * lam.view(shp)
 
@@ -279,10 +280,10 @@ def gaussian(meta: Tensor, mask: Tensor, cdf: Tensor, tx: int, ratio: float = 1.
     f = exp(-(t-mu)^2 / (2 sigma^2 + 1e-16)) (:280-282), divided by (max_t f + 1e-16) (:283).
     -> [B, Tf, K]."""
     b, tf = mask.shape
-    st = meta[:, 0].to(torch.float32)
+    st = meta[:, 0].to(cdf.dtype)
     mu = (cdf * tx + st.view(b, 1)) / ratio                      # [B,K]
     std = mask.sum(dim=1) / 8.0                                  # [B]
-    t = torch.arange(tf, dtype=torch.float32, device=cdf.device).view(1, tf, 1)
+    t = torch.arange(tf, dtype=cdf.dtype, device=cdf.device).view(1, tf, 1)
     d = t - mu.view(b, 1, -1)
     f = torch.exp(-(d ** 2) / (2 * (std ** 2).view(b, 1, 1) + 1e-16))
     return f / (f.max(dim=1, keepdim=True)[0] + 1e-16)
