@@ -1,13 +1,15 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the cfnet_b200 hot path (contract: see DESIGN.md section 5).
+"""bench.py -- headline benchmark of the cfnet_b200 hot path (contract: DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload auto|gridpool|fine|coarse_fine]
-    python bench.py --impl reference ...      # the CPU oracle port on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload auto|coarse_fine|fine|gridpool]
+    python bench.py --impl reference ...      # the reference algorithm (CPU oracle port) on the host cores
 
-One JSON line on stdout (rank 0).  `value` = whole-job clips/s with inputs resident in HBM;
-`e2e` = the same through the public module call with pinned-host inputs (H2D + D2H inside the
-timed region); `roofline` = achieved algorithmic GB/s of the dominant kernel, timed live with
-CUDA events on the launching stream; `cpu_baseline` = oracle port on a bounded sample.
+One JSON line on stdout (rank 0).  A "step" is one training step of the workload on one batch of
+synthetic clips: forward, Charades loss, backward, flat-gradient all-reduce, fused SGD.
+`value` = whole-job clips/s with inputs resident in HBM; `e2e` = the same through the public module
+call with pinned-host inputs (H2D of the clips and labels + D2H of the loss inside the timed region);
+`roofline` = achieved algorithmic GB/s of the dominant kernel, timed live with CUDA events on the
+launching stream; `cpu_baseline` = the oracle port on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -19,9 +21,13 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.dont_write_bytecode = True
 
 import torch  # noqa: E402
+
+DEPTH = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
+N_CLASSES = 157
 
 
 # ----------------------------------------------------------------------------------------
@@ -85,137 +91,339 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def flush_l2(buf):
-    buf.zero_()
+def time_kernel(fn, flush, reps=10):
+    """Average device time (ms) of fn() with CUDA events on the launching stream, L2 flushed in between."""
+    for _ in range(3):
+        fn()
+    ev = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    return sum(ms) / len(ms)
 
 
 # ----------------------------------------------------------------------------------------
-# Workload: Grid Pool (BASELINE cfg 3): cdf + temporal gather fwd + bwd on [32,24,64,56,56]
+# Grid Pool gather (BASELINE cfg 3): [32,24,64,56,56] -> [32,24,17,56,56]
 # ----------------------------------------------------------------------------------------
+def gridpool_gather_roofline(device, peaks, flush, batch=32):
+    from coarse_fine_networks_b200 import gridpool_ops as G
+    B, C, T, H, W = batch, 24, 64, 56, 56
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, C, T, H, W, generator=g).to(device)
+    conf = (torch.randn(B, T // 4, generator=g) * 2).to(device)
+    cdf = G.gridpool_cdf(conf)
+    i0, w1 = G.sample_bins(cdf, T)
+    i0c, w1c = i0.cpu(), w1.cpu()
+    n_src = 0
+    for b in range(B):
+        s = set()
+        for k in range(i0c.shape[1]):
+            a = int(i0c[b, k])
+            if 0 <= a < T:
+                s.add(a)
+            if 0 <= a + 1 < T and float(w1c[b, k]) != 0.0:
+                s.add(a + 1)
+        n_src += len(s)
+    alg = 4 * C * H * W * (n_src + B * i0c.shape[1])
+    ms = time_kernel(lambda: G._gather_fwd(x, i0, w1, True), flush)
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "temporal_gather_fwd_kernel<float4,4>", "workload": "cfg3 [32,24,64,56,56]->17 points",
+            "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+            "peak_basis": peaks["basis"], "algorithmic_bytes": alg, "kernel_ms": ms}
+
+
 class GridPoolWorkload:
     name = "cfg3 GridPool cdf+gather fwd+bwd on [32,24,64,56,56] fp32 NCTHW (T=64 -> 17 sample points)"
     dtype = "f32"
-    reference_sample_clips = 2
 
-    def __init__(self, device, batch=32, seed=0):
+    def __init__(self, device, rank=0, batch=32, **_):
+        from coarse_fine_networks_b200 import gridpool_ops as G
+        self.G = G
         self.B, self.C, self.T, self.H, self.W = batch, 24, 64, 56, 56
-        g = torch.Generator().manual_seed(seed)
+        g = torch.Generator().manual_seed(rank)
         self.host_x = torch.randn(self.B, self.C, self.T, self.H, self.W, generator=g)
         self.host_conf = torch.randn(self.B, self.T // 4, generator=g) * 2
         self.device = device
+        self.clips_per_step = self.B
+        self.trainer = None
         if device.type == "cuda":
             self.host_x, self.host_conf = self.host_x.pin_memory(), self.host_conf.pin_memory()
             self.x = self.host_x.to(device)
             self.conf = self.host_conf.to(device)
             self.gout = torch.randn(self.B, self.C, self.T // 4 + 1, self.H, self.W, device=device)
-        self.clips_per_step = self.B
-        self.kernel_ms = []
+        self.h2d_bytes = self.host_x.numel() * 4 + self.host_conf.numel() * 4
+        self.d2h_bytes = self.host_conf.numel() * 4
+        self.graphed = False
 
-    def step(self, x=None, conf=None, time_kernel=False):
-        from coarse_fine_networks_b200 import gridpool_ops as G
-        x = (self.x if x is None else x).requires_grad_(True)
-        conf = (self.conf if conf is None else conf).requires_grad_(True)
-        cdf = G.gridpool_cdf(conf)
-        if time_kernel:                       # dominant kernel: temporal_gather_fwd (sample_bins is ~2 us)
-            coord = cdf.detach()
-            i0, w1 = G.sample_bins(coord, self.T)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            G._gather_fwd(x.detach(), i0, w1, True)
-            e1.record()
-            self.kernel_ms.append((e0, e1))
-        out = G.temporal_sample(x, cdf)
+    def prepare(self, use_graph):
+        pass
+
+    def step(self):
+        x = self.x.requires_grad_(True)
+        conf = self.conf.requires_grad_(True)
+        out = self.G.temporal_sample(x, self.G.gridpool_cdf(conf))
         out.backward(self.gout)
-        res = conf.grad
+        self.res = conf.grad
         x.grad = None
-        return out, res
+        conf.grad = None
 
     def e2e_step(self):
-        x = self.host_x.to(self.device, non_blocking=True)
-        conf = self.host_conf.to(self.device, non_blocking=True)
-        out, res = self.step(x, conf)
-        return res.to("cpu", non_blocking=False)
+        self.x = self.host_x.to(self.device, non_blocking=True)
+        self.conf = self.host_conf.to(self.device, non_blocking=True)
+        self.step()
+        return self.res.cpu()
 
-    h2d_bytes = property(lambda s: s.host_x.numel() * 4 + s.host_conf.numel() * 4)
-    d2h_bytes = property(lambda s: s.host_conf.numel() * 4)
+    def roofline(self, peaks, flush):
+        return gridpool_gather_roofline(self.device, peaks, flush, self.B)
 
-    def roofline(self, peaks):
-        from coarse_fine_networks_b200 import gridpool_ops as G
-        cdf = G.gridpool_cdf(self.conf)
-        i0, w1 = G.sample_bins(cdf, self.T)
-        i0c, w1c = i0.cpu(), w1.cpu()
-        n_src = 0
-        for b in range(self.B):
-            s = set()
-            for k in range(i0c.shape[1]):
-                a = int(i0c[b, k])
-                if 0 <= a < self.T:
-                    s.add(a)
-                if 0 <= a + 1 < self.T and float(w1c[b, k]) != 0.0:
-                    s.add(a + 1)
-            n_src += len(s)
-        tl = i0c.shape[1]
-        alg = 4 * self.C * self.H * self.W * (n_src + self.B * tl)
-        ms = [a.elapsed_time(b) for a, b in self.kernel_ms]
-        avg = sum(ms) / max(len(ms), 1)
-        ach = alg / (avg * 1e-3) / 1e9 if ms else None
-        return {"bound": "hbm", "kernel": "temporal_gather_fwd_kernel<float4,4>", "achieved": ach,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (ach / peaks["hbm_gbs"]) if ach else None,
-                "traffic": None, "peak_basis": peaks["basis"], "algorithmic_bytes": alg, "kernel_ms": avg}
+    def config(self):
+        return {"l2": "inputs (617 MB) larger than the 126 MB L2"}
 
-    # CPU oracle on a bounded sample
-    def cpu_sample(self, n_clips=2, reps=2):
+    @staticmethod
+    def cpu_step(budget_s, full=True):
         from oracle import cf_oracle as O
-        x = self.host_x[:n_clips].clone()
-        conf = self.host_conf[:n_clips].clone()
-        gout = torch.randn(n_clips, self.C, self.T // 4 + 1, self.H, self.W)
-        best = 1e30
-        for _ in range(reps + 1):
-            xr = x.clone().requires_grad_(True)
-            cr = conf.clone().requires_grad_(True)
-            t0 = time.perf_counter()
-            out = O.temporal_lerp(xr, O.gridpool_cdf(cr))
-            out.backward(gout)
-            best = min(best, time.perf_counter() - t0)
-        return n_clips / best, f"{n_clips} of {self.B} clips of the same workload, best of {reps + 1}"
+        n = 2
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(n, 24, 64, 56, 56, generator=g).requires_grad_(True)
+        conf = (torch.randn(n, 16, generator=g) * 2).requires_grad_(True)
+        gout = torch.randn(n, 24, 17, 56, 56, generator=g)
+        t0 = time.perf_counter()
+        O.temporal_lerp(x, O.gridpool_cdf(conf)).backward(gout)
+        return n, time.perf_counter() - t0, f"{n} of 32 clips of the same workload per step"
 
 
-WORKLOADS = {"gridpool": GridPoolWorkload}
+# ----------------------------------------------------------------------------------------
+# Joint Coarse-Fine two-stream training step (BASELINE cfg 4 / cfg 5) and the fine stream alone (cfg 2)
+# ----------------------------------------------------------------------------------------
+def build_models(which, device, seed=0):
+    from coarse_fine_networks_b200 import x3d_coarse, x3d_fine
+    torch.manual_seed(seed)                      # identical initial weights on every rank (data-parallel replicas)
+    fine = coarse = None
+    if which == "fine":
+        fine = x3d_fine.generate_model("M", n_classes=N_CLASSES, task="loc", base_bn_splits=1, dropout=0.0)
+    else:
+        fine = x3d_fine.generate_model("M", n_classes=N_CLASSES, task="loc", base_bn_splits=1, dropout=0.0, global_tower=True)
+        coarse = x3d_coarse.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0,
+                                           t_pool="grid", learnedMixing=True, isMixing=True)
+        coarse.replace_logits(N_CLASSES)
+        coarse.rw6.dropout.p = 0.0
+    mods = [m.to(device).train() for m in (fine, coarse) if m is not None]
+    return fine, coarse, mods
 
 
-def pick_workload(name):
-    if name != "auto":
-        return WORKLOADS[name]
-    for k in ("coarse_fine", "fine", "gridpool"):
-        if k in WORKLOADS:
-            return WORKLOADS[k]
+class TrainWorkload:
+    """fwd + Charades loss + bwd (+ all-reduce) + fused SGD; the fwd/loss/bwd part replayed from a CUDA graph."""
+    dtype = "f32"
+
+    def __init__(self, device, rank=0, which="coarse_fine", batch=None):
+        from coarse_fine_networks_b200 import train
+        self.train = train
+        self.which, self.device = which, device
+        if which == "fine":
+            self.B, self.Tf, self.Tc, self.start = batch or 8, 16, 16, 0
+            self.name = f"cfg2 X3D-M fine stream train step, synthetic [{self.B},3,16,224,224] fp32, 157 classes"
+        else:
+            self.B, self.Tf, self.Tc, self.start = batch or 4, 256, 64, 96
+            self.name = (f"cfg4 joint Coarse-Fine X3D-M two-stream + Multi-stage Fusion train step: fine [{self.B},3,256,224,224] "
+                         f"(global tower) -> coarse window [{self.B},3,64,224,224] -> Grid Pool Tl=17 -> logits [{self.B},157,64], "
+                         "gradients through BOTH streams, fp32")
+        self.TL = self.Tc * 10                                   # labels at the raw-frame rate (stride-10 clips)
+        g = torch.Generator().manual_seed(1000 + rank)           # a distinct shard of clips per rank
+        self.host_x = torch.randn(self.B, 3, self.Tf, 224, 224, generator=g)
+        self.host_labels = (torch.rand(self.B, N_CLASSES, self.TL, generator=g) < 0.05).float()
+        self.clips_per_step = self.B
+        self.h2d_bytes = (self.host_x.numel() + self.host_labels.numel()) * 4
+        self.d2h_bytes = 4
+        self.graph = None
+        self.graphed = False
+        if device.type != "cuda":
+            return
+        self.host_x, self.host_labels = self.host_x.pin_memory(), self.host_labels.pin_memory()
+        self.x = self.host_x.to(device)
+        self.labels = self.host_labels.to(device)
+        self.lmask = torch.ones(self.B, self.TL, device=device)
+        self.fmask = torch.ones(self.B, self.Tf, device=device)
+        self.meta = torch.tensor([[float(self.start), float(self.Tc), float(self.Tf), 1.0]]).repeat(self.B, 1).to(device)
+        self.fine, self.coarse, mods = build_models(which, device)
+        lr = 0.01 if which == "fine" else 0.02                  # train_fine.py:45, train_coarse_fineFEAT.py:46
+        self.trainer = train.FlatTrainer(mods, lr=lr, momentum=0.9, weight_decay=1e-5)
+
+    def fwd_bwd(self):
+        if self.which == "fine":
+            logits = self.fine([self.x, None])
+        else:
+            logits = self.train.coarse_fine_forward(self.fine, self.coarse, self.x, self.start, self.Tc, self.fmask,
+                                                    meta=self.meta)
+        loss, _ = self.train.charades_loss(logits, self.labels, self.lmask)
+        loss.backward()
+        self.loss = loss.detach()
+
+    def prepare(self, use_graph):
+        if not use_graph:
+            return
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self.fwd_bwd()
+                    self.trainer.step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.fwd_bwd()
+            self.trainer.zero_grad()
+            self.graphed = True
+        except Exception as e:                                    # report, fall back to eager launches
+            self.graph, self.graphed = None, False
+            self.graph_error = repr(e)[:200]
+            torch.cuda.synchronize()
+            self.trainer.zero_grad()
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.fwd_bwd()
+        self.trainer.step()
+
+    def e2e_step(self):
+        self.x.copy_(self.host_x, non_blocking=True)
+        self.labels.copy_(self.host_labels, non_blocking=True)
+        self.step()
+        return self.loss.cpu()
+
+    def config(self):
+        c = {"per_gpu_batch": self.B, "cuda_graph": self.graphed, "optimizer": "fused flat SGD momentum 0.9 wd 1e-5",
+             "loss": "Charades BCE cls+loc (train_fine.py:199-212)", "params": self.trainer.n_params,
+             "allreduce_bytes": self.trainer.n * 4,
+             "l2": "per-step activations (tens of GB) exceed the 126 MB L2; explicit 256 MB flush before each kernel-timed launch"}
+        if getattr(self, "graph_error", None):
+            c["cuda_graph_error"] = self.graph_error
+        return c
+
+    def roofline(self, peaks, flush):
+        """Dominant kernel = the pointwise-conv GEMM (pw_conv_kernel); timed on its largest launch of the
+        step: fine-stream layer1.0.conv1 (24 -> 54 channels at 112x112, all B*Tf frames) with the BatchNorm
+        statistics epilogue.  Algorithmic bytes = read x once + write y once (weights 5 KB)."""
+        from coarse_fine_networks_b200 import x3d_ops as X
+        B, T, H, W, K, N = self.B, self.Tf, 112, 112, 24, 54
+        x = torch.randn(B, K, T, H, W, device=self.device).contiguous(memory_format=torch.channels_last_3d)
+        w = torch.randn(N, K, device=self.device) * 0.1
+        y = X.new_act(B, N, T, H, W, self.device)
+        stats = torch.zeros(B, N, 2, device=self.device, dtype=torch.float64)
+        g = X.geom(T, H, W)
+        ms = time_kernel(lambda: X.pw_conv(x, w, y, B, K, N, g, stats=stats, stats_mode=X.STATS_SUM_SQ), flush)
+        alg = B * T * H * W * (K + N) * 4
+        ach = alg / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "pw_conv_kernel<64,false> (layer1.0.conv1 24->54 @112x112, BN-stat epilogue)",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                "peak_basis": peaks["basis"], "algorithmic_bytes": alg, "kernel_ms": ms}
+
+    # ---- the reference algorithm on the host CPU (oracle port), one bounded sample per step
+    _cpu_state = {}
+
+    @classmethod
+    def cpu_step(cls, budget_s, which="coarse_fine", full=True):
+        """One fwd + loss + bwd of the oracle on ONE clip.  `full`: the workload's own shapes (Tf=256, T=64);
+        otherwise a quarter-length clip (Tf=64, T=16: a quarter of the conv work), reported as 0.25 clip."""
+        from oracle import cf_oracle as O
+        from synth import synth_state_dict
+        import torch.nn.functional as F
+        st = cls._cpu_state
+        if "sd_f" not in st:
+            from coarse_fine_networks_b200 import x3d_coarse, x3d_fine   # shapes of the state dicts only
+            f = x3d_fine.generate_model("M", n_classes=N_CLASSES, task="loc", base_bn_splits=1, dropout=0.0)
+            st["sd_f"] = synth_state_dict(f.state_dict(), 1)
+            c = x3d_coarse.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0,
+                                          t_pool="grid", learnedMixing=True, isMixing=True)
+            c.replace_logits(N_CLASSES)
+            st["sd_c"] = synth_state_dict(c.state_dict(), 2)
+        if which == "fine":
+            Tf, Tc, start, frac = 16, 16, 0, 1.0
+        else:
+            Tf, Tc, start, frac = (256, 64, 96, 1.0) if full else (64, 16, 24, 0.25)
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(1, 3, Tf, 224, 224, generator=g)
+        labels = (torch.rand(1, N_CLASSES, Tc * 10, generator=g) < 0.05).float()
+        req = lambda sd: {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+                          for k, v in sd.items()}
+        t0 = time.perf_counter()
+        sd_f = req(st["sd_f"])
+        if which == "fine":
+            logits = O.fine_forward(sd_f, x, True)
+        else:
+            sd_c = req(st["sd_c"])
+            feat = O.fine_forward(sd_f, x, True, global_tower=True)
+            meta = torch.tensor([[float(start), float(Tc), float(Tf), 1.0]])
+            logits = O.coarse_forward(sd_c, x[:, :, start:start + Tc], feat, torch.ones(1, Tf), meta, True)
+        pl = F.interpolate(logits, labels.shape[2], mode="linear", align_corners=True)
+        probs = torch.sigmoid(pl)
+        loss = (F.binary_cross_entropy(probs.max(dim=2)[0], labels.max(dim=2)[0]) +
+                F.binary_cross_entropy(probs, labels, reduction="sum") / (labels.shape[2] * N_CLASSES)) / 2
+        loss.backward()
+        dt = time.perf_counter() - t0
+        what = ("1 clip of the same workload (full shapes) per step" if frac == 1.0 else
+                "a quarter-length clip (fine Tf=64, coarse T=16 -> Tl=5) per step, counted as 0.25 clip")
+        return frac, dt, what + "; fwd + loss + bwd through both streams, no optimizer step"
+
+
+WORKLOADS = {"gridpool": GridPoolWorkload, "fine": TrainWorkload, "coarse_fine": TrainWorkload}
+
+
+def make_workload(name, device, rank):
+    if name == "auto":
+        name = "coarse_fine"
+    cls = WORKLOADS[name]
+    return (cls(device, rank=rank, which=name) if cls is TrainWorkload else cls(device, rank=rank)), name
+
+
+def cpu_step_fn(name):
+    if name == "auto":
+        name = "coarse_fine"
+    if name == "gridpool":
+        return lambda budget, full: GridPoolWorkload.cpu_step(budget, full)
+    return lambda budget, full: TrainWorkload.cpu_step(budget, which=name, full=full)
 
 
 # ----------------------------------------------------------------------------------------
 def run_reference(args, rank):
-    """--impl reference: the reference's algorithm for this path on the host CPU (the oracle port:
-    the reference is pure Python/PyTorch, nothing to compile into oracle/_ref), all host threads,
-    each step a bounded sample (2 clips) of the same workload."""
+    """--impl reference: the reference's algorithm for this path on the host CPU.  The reference is pure
+    Python/PyTorch (nothing to compile into oracle/_ref) and /root/reference does not exist on the GPU box,
+    so this is the oracle port (pinned to the reference's outputs by tests/golden), with all host threads.
+    Each step is a bounded sample of the workload; the run is additionally bounded in wall time
+    (--ref-budget seconds): at least one timed step, at most --steps."""
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    cls = pick_workload(args.workload)
-    n = cls.reference_sample_clips
-    wl = cls(torch.device("cpu"), batch=n)
-    times = []
-    for i in range(args.warmup + args.steps):
-        v, _ = wl.cpu_sample(n_clips=n, reps=0)
-        if i >= args.warmup:
-            times.append(n / v)
+    name = "coarse_fine" if args.workload == "auto" else args.workload
+    fn = cpu_step_fn(name)
+    t_start = time.perf_counter()
+    units, dt, sample = fn(args.ref_budget, False)               # probe / warm-up on the small sample
+    full = name != "coarse_fine" or dt * 5.0 < args.ref_budget / 3
+    times, n_units = [], 0.0
+    for i in range(max(args.warmup - 1, 0) + args.steps):
+        if times and time.perf_counter() - t_start > args.ref_budget:
+            break
+        units, dt, sample = fn(args.ref_budget, full)
+        if i >= max(args.warmup - 1, 0) or time.perf_counter() - t_start > args.ref_budget:
+            times.append(dt)
+            n_units = units
     ms = 1e3 * sum(times) / len(times)
-    val = n / (ms * 1e-3)
-    sample = f"{n} clips per step of the same workload"
+    val = n_units / (ms * 1e-3)
+    wl_name = make_workload(name, torch.device("cpu"), 0)[0].name
     line = {"impl": "reference", "metric": "clips/sec fwd+bwd", "value": val, "unit": "clips/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": cls.dtype, "data": "synthetic",
-            "config": {"workload": cls.name, "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
+            "steps": len(times), "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "sample": sample, "time_budget_s": args.ref_budget},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -223,11 +431,14 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto")
+    ap.add_argument("--workload", default="auto", choices=["auto", "coarse_fine", "fine", "gridpool"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="wall-time bound (s) of the CPU reference arm")
+    ap.add_argument("--cpu-budget", type=float, default=60.0, help="wall-time bound (s) of the cpu_baseline leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -238,36 +449,47 @@ def main():
         run_reference(args, rank)
         return
 
-    import __graft_entry__ as ge
-    if rank == 0:
-        ge.build()
     import torch.distributed as dist
+    import __graft_entry__ as ge
     if world > 1:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if rank == 0:
+            ge.build()
         dist.barrier()
     else:
         torch.cuda.set_device(0)
+        ge.build()
     from coarse_fine_networks_b200 import _lib
     device = torch.device("cuda", local_rank if world > 1 else 0)
     peaks = measured_peaks()
-    cls = pick_workload(args.workload)
-    wl = cls(device, seed=rank)
+    wl, wl_key = make_workload(args.workload, device, rank)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=device)      # 256 MB > 126 MB L2
+    warmup = max(args.warmup, 3)
+
+    # launches of OUR kernels per step, counted on one eager step (graph replays do not pass through the C ABI)
+    n0 = _lib.launch_count()
+    if isinstance(wl, TrainWorkload):
+        wl.fwd_bwd()
+        wl.trainer.step()
+    else:
+        wl.step()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+    wl.prepare(use_graph=not args.no_graph)
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, time_kernel=False):
-        for _ in range(warmup):
+    def timed(fn, steps, nwarm):
+        for _ in range(nwarm):
             fn()
         sync()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -275,45 +497,49 @@ def main():
         e1.record()
         sync()
         ms = e0.elapsed_time(e1)
-        launches = _lib.launch_count() - n0
         clocks = sampler.stop() if rank == 0 else None
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, clocks
+        return float(t.item()), clocks
 
-    # --- device-resident throughput (inputs already in HBM; inputs (617 MB) exceed L2) ---
-    ms_total, launches, clocks = timed(lambda: wl.step(), args.steps, max(args.warmup, 3))
+    # --- device-resident throughput ---
+    ms_total, clocks = timed(wl.step, args.steps, warmup)
     ms_step = ms_total / args.steps
     value = world * wl.clips_per_step / (ms_step * 1e-3)
-    # --- dominant-kernel timing (separate short pass so its events do not perturb `value`) ---
-    for _ in range(3):
-        wl.step(time_kernel=False)
-    wl.kernel_ms = []
-    for _ in range(min(args.steps, 10)):
-        flush_l2(flush)
-        wl.step(time_kernel=True)
-    torch.cuda.synchronize()
-    roof = wl.roofline(peaks)
     # --- end to end through the public API with pinned-host inputs ---
-    ms_e2e, _, _ = timed(lambda: wl.e2e_step(), max(args.steps // 2, 3), 3)
-    ms_e2e_step = ms_e2e / max(args.steps // 2, 3)
+    n_e2e = max(args.steps // 2, 3)
+    ms_e2e, _ = timed(wl.e2e_step, n_e2e, 3)
+    ms_e2e_step = ms_e2e / n_e2e
     e2e = {"value": world * wl.clips_per_step / (ms_e2e_step * 1e-3), "unit": "clips/s",
            "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": ms_e2e_step}
+    # --- dominant-kernel roofline (separate pass; rank 0) + the Grid Pool gather the metric also names ---
+    roof = gp = None
+    if rank == 0:
+        roof = wl.roofline(peaks, flush)
+        if wl_key != "gridpool":
+            gp = gridpool_gather_roofline(device, peaks, flush)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        v, sample = wl.cpu_sample()
-        cpu = {"value": v, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+        fn = cpu_step_fn(wl_key)
+        units, dt, sample = fn(args.cpu_budget, False)              # quarter-length probe (also the warm-up)
+        if wl_key == "coarse_fine" and dt * 5.0 < args.cpu_budget:  # the full clip fits the budget: time it
+            units, dt, sample = fn(args.cpu_budget, True)
+        elif wl_key != "coarse_fine":
+            units, dt, sample = fn(args.cpu_budget, True)
+        cpu = {"value": units / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
     if rank == 0:
+        cfg = {"workload": wl.name, "parallelism": f"dp{world}"}
+        cfg.update(wl.config())
         line = {"metric": "clips/sec fwd+bwd", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-                "config": {"workload": wl.name, "per_gpu_batch": wl.clips_per_step, "parallelism": f"dp{world}",
-                           "l2": "inputs (617 MB) larger than the 126 MB L2; explicit 256 MB flush before each kernel-timed launch"},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": cfg,
+                "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+                "clocks": clocks, "roofline": roof, "gridpool_roofline": gp, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

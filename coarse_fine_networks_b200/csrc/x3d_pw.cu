@@ -329,9 +329,11 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const cf_pw_wgrad_args a,
 extern "C" size_t cf_sizeof_pw_args(void) { return sizeof(cf_pw_args); }
 size_t cf_sizeof_pw_wgrad_args(void) { return sizeof(cf_pw_wgrad_args); }
 
-static bool geom_ok(const cf_geom& g) {
-    return g.T > 0 && g.H > 0 && g.W > 0 && g.T < 1024 && g.H < 2048 && g.W < 2048 && g.kt > 0 && g.kh > 0 && g.kw > 0 &&
-           g.st > 0 && g.sh > 0 && g.sw > 0;
+// the packed (t,h,w) position (10+11+11 bits) is only used by the gathered / scattered paths
+static bool geom_ok(const cf_geom& g, bool packed) {
+    if (!(g.T > 0 && g.H > 0 && g.W > 0 && (long long)g.T * g.H * g.W < (1LL << 31))) return false;
+    if (!packed) return true;
+    return g.T < 1024 && g.H < 2048 && g.W < 2048 && g.kt > 0 && g.kh > 0 && g.kw > 0 && g.st > 0 && g.sh > 0 && g.sw > 0;
 }
 
 template <int BN_, bool GATHER>
@@ -357,7 +359,7 @@ static int launch_pw(const cf_pw_args* a, int R, cudaStream_t stream) {
 
 extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->x && a->w && a->y, "null pointer");
-    CF_CHECK_ARG(a->B > 0 && a->K > 0 && a->N > 0 && geom_ok(a->g), "bad shape");
+    CF_CHECK_ARG(a->B > 0 && a->K > 0 && a->N > 0 && geom_ok(a->g, a->gather_in || a->scatter_out), "bad shape");
     CF_CHECK_ARG(a->pro_mode == CF_PRO_NONE || a->pro_a, "prologue tables missing");
     CF_CHECK_ARG(a->pro_mode != CF_PRO_AFFINE2 || (a->x2 && !a->gather_in), "AFFINE2 needs a dense second input");
     CF_CHECK_ARG(((a->epi_mode < CF_EPI_DRELU || a->epi_mode > CF_EPI_ADD_AUX) && a->stats_mode != CF_STATS_SUM_AUX) || a->aux, "aux tensor missing");
@@ -379,7 +381,7 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
 
 extern "C" int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->dy && a->x && a->dw, "null pointer");
-    CF_CHECK_ARG(a->B > 0 && a->K > 0 && a->N > 0 && geom_ok(a->g), "bad shape");
+    CF_CHECK_ARG(a->B > 0 && a->K > 0 && a->N > 0 && geom_ok(a->g, a->gather_in != 0), "bad shape");
     CF_CHECK_ARG(a->dy_mode == CF_PRO_NONE || a->dy_a, "dy tables missing");
     CF_CHECK_ARG(a->dy_mode != CF_PRO_AFFINE2 || a->dy2, "AFFINE2 needs dy2");
     CF_CHECK_ARG(a->x_mode == CF_PRO_NONE || a->x_a, "x tables missing");

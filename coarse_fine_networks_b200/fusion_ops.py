@@ -174,6 +174,7 @@ class ConfidenceFn(torch.autograd.Function):
         ctx.geoms = (g1g, g2g, g3g)
         ctx.tabs = (a1, bb1, m1, i1, a2, bb2, m2, i2)
         ctx.save_for_backward(x, y1, y2, w1, g1, w2, g2, w3)
+        ctx.params = (w1, c1b, g1, b1, w2, c2b, g2, b2, w3, c3b)
         return g.view(B, T2)
 
     @staticmethod
@@ -185,8 +186,7 @@ class ConfidenceFn(torch.autograd.Function):
         tr = ctx.cfg.training
         dev = x.device
         R1, R2 = T1 * H1 * W1, T2 * H2 * W2
-        (dw1, dc1b, dg1, db1, dw2, dc2b, dg2, db2, dw3, dc3b) = X._flat_grads(
-            [w1, g1, g1, g1, w2, g2, g2, g2, w3, torch.empty(1)], dev)
+        (dw1, dc1b, dg1, db1, dw2, dc2b, dg2, db2, dw3, dc3b), rets = X._flat_grads(ctx.params, dev)
         sums = torch.zeros(2, B, C, 2, device=dev, dtype=torch.float64)
         # mean over (H3,W3)
         dy3 = X.new_act(B, 1, T2, H3, W3, dev)
@@ -218,7 +218,7 @@ class ConfidenceFn(torch.autograd.Function):
             dx = torch.zeros_like(x)
             X.pw_conv(dz1, w1, dx, B, C, C * 27, g1g, w_sn=1, w_sk=C * 27, x2=y1, pro=X.PRO_AFFINE2, pro_tabs=(P1, Q1, R1c),
                       scatter_out=1)
-        return (dx, None, dw1, dc1b, dg1, db1, dw2, dc2b, dg2, db2, dw3, dc3b.view_as(dc3b))
+        return (dx, None, *rets)
 
 
 def linear_rows(x, conv, act=X.ACT_NONE):

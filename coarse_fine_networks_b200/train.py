@@ -1,0 +1,127 @@
+"""Training-step glue for the scripts' hot loop (train_fine.py:173-237,
+train_coarse_fineFEAT.py:190-281): the Charades localisation loss, one flat parameter / gradient /
+momentum buffer per job, a single NCCL all-reduce of the flat gradient per step, a fused SGD kernel,
+and a joint two-stream step (fine stream feeding the coarse stream in memory instead of through
+extract_fineFEAT.py's files).
+
+Data parallelism = one process per GPU (torch.distributed, NCCL over NVLink); clips are sharded by
+rank, BatchNorm statistics stay per rank exactly as under the reference's nn.DataParallel
+(x3d_fine.py:27-29 is a plain BatchNorm3d), and the only collective is the gradient sum."""
+import torch
+import torch.distributed as dist
+
+from ._lib import call, ptr, stream_ptr
+
+FUSION_LR_MULT = 10.0        # train_coarse_fineFEAT.py:141
+
+
+class CharadesLossFn(torch.autograd.Function):
+    """(cls_loss + loc_loss) * scale with scale = 1/(2*num_steps_per_update) (train_fine.py:199-212,226).
+    Returns (loss, parts) with parts = [cls_loss, loc_loss] (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, masks, scale):
+        logits = logits.contiguous().float()
+        labels = labels.contiguous().float()
+        masks = masks.contiguous().float()
+        B, C, T = logits.shape
+        TL = labels.shape[2]
+        parts = torch.zeros(2, device=logits.device, dtype=torch.float32)
+        dlogits = torch.empty_like(logits)
+        call("cf_charades_loss", ptr(logits), ptr(labels), ptr(masks), ptr(parts), ptr(dlogits), B, C, T, TL, float(scale),
+             stream_ptr())
+        ctx.save_for_backward(dlogits)
+        ctx.mark_non_differentiable(parts)
+        return parts.sum() * float(scale), parts
+
+    @staticmethod
+    def backward(ctx, dloss, _dparts):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * dloss, None, None, None
+
+
+def charades_loss(logits, labels, masks, num_steps_per_update=1):
+    return CharadesLossFn.apply(logits, labels, masks, 1.0 / (2.0 * num_steps_per_update))
+
+
+def is_fusion_param(name):
+    """The 10x learning-rate group of train_coarse_fineFEAT.py:137-141."""
+    return "rw" in name or "mix" in name
+
+
+class FlatTrainer:
+    """Owns ONE flat fp32 buffer each for parameters, gradients and momentum of a set of modules.
+
+    Every parameter becomes a view of the flat parameter buffer and gets ``_cf_grad``, a view of the
+    flat gradient buffer that the weight-gradient kernels accumulate into directly (x3d_ops._flat_grads);
+    ``param.grad`` aliases the same view so inspection / checkpointing code keeps working.  ``step()``
+    = [one all-reduce of the flat gradient over the data-parallel group] + one fused SGD kernel that
+    also re-zeroes the gradient buffer.  Base parameters come first, fusion ('rw'/'mix') parameters
+    last, so the two learning-rate groups are two contiguous ranges."""
+
+    def __init__(self, modules, lr, momentum=0.9, weight_decay=1e-5, fusion_lr_mult=FUSION_LR_MULT, process_group=None):
+        named = []
+        for mi, m in enumerate(modules):
+            named += [(f"{mi}.{n}", p) for n, p in m.named_parameters() if p.requires_grad]
+        base = [(n, p) for n, p in named if not is_fusion_param(n.split(".", 1)[1])]
+        fus = [(n, p) for n, p in named if is_fusion_param(n.split(".", 1)[1])]
+        self.names = [n for n, _ in base + fus]
+        self.params = [p for _, p in base + fus]
+        dev = self.params[0].device
+        al = lambda n: (n + 3) // 4 * 4                       # 16-byte aligned segments
+        offs, o = [], 0
+        for i, p in enumerate(self.params):
+            if i == len(base):
+                self.n_split = o
+            offs.append(o)
+            o += al(p.numel())
+        if not fus:
+            self.n_split = o
+        self.n = o
+        self.flat_p = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        for p, off in zip(self.params, offs):
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + n].view(p.shape)
+            p._cf_grad = self.flat_g[off:off + n].view(p.shape)
+            p.grad = p._cf_grad
+        self.lr, self.momentum, self.weight_decay, self.fusion_lr_mult = lr, momentum, weight_decay, fusion_lr_mult
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.n_params = sum(p.numel() for p in self.params)
+
+    def allreduce(self):
+        """The one collective of the data-parallel step: sum of the flat gradient over all ranks."""
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+
+    def sgd(self):
+        call("cf_sgd_flat", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_v), self.n, self.n_split, float(self.lr),
+             float(self.lr * self.fusion_lr_mult), float(self.momentum), float(self.weight_decay), 1.0 / self.world,
+             stream_ptr())
+
+    def step(self):
+        self.allreduce()
+        self.sgd()
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+
+def coarse_fine_forward(fine_net, coarse_net, x_fine, start, n_coarse, feat_masks, detach_fine=False, meta=None):
+    """Joint two-stream forward.  The fine stream (global_tower=True) runs over the whole clip
+    x_fine [B,3,Tf,H,W]; the coarse stream sees the window x_fine[:, :, start:start+n_coarse] and the
+    fine features directly from HBM (the reference hands them over through files:
+    extract_fineFEAT.py:168-173 -> charades_coarse_fineFEAT.py:84-87, 199-200).  meta = [start,
+    n_coarse, Tf, 1] as in charades_coarse_fineFEAT.py:199-200.  detach_fine=True reproduces the
+    reference's training semantics (no gradient into the fine stream)."""
+    B, _, Tf = x_fine.shape[:3]
+    feat, _ = fine_net([x_fine, None])
+    if detach_fine:
+        feat = {k: v.detach() for k, v in feat.items()}
+    if meta is None:                     # pass a prebuilt device tensor when capturing the step in a CUDA graph
+        meta = torch.tensor([[float(start), float(n_coarse), float(Tf), 1.0]], device=x_fine.device).repeat(B, 1)
+    x_coarse = x_fine[:, :, start:start + n_coarse]
+    return coarse_net([x_coarse, feat, feat_masks, 0, meta])

@@ -120,14 +120,30 @@ def residual_bwd(dout, out, y, dz, sums_y, B, C, rows, res=None, sums_res=None):
 
 
 def _flat_grads(params, device):
-    """One zero-filled buffer carved into per-parameter gradient views (a single memset)."""
-    sizes = [p.numel() if p is not None else 0 for p in params]
-    flat = torch.zeros(sum(sizes), device=device, dtype=torch.float32)
-    out, o = [], 0
-    for p, n in zip(params, sizes):
-        out.append(flat[o:o + n].view(p.shape) if p is not None else None)
-        o += n
-    return out
+    """Gradient targets for a list of parameters (None entries allowed) -> (buffers, returns).
+
+    ``buffers[i]`` is what the weight-gradient kernels accumulate (+=) into; ``returns[i]`` is what
+    the autograd Function hands back.  A parameter owned by a ``train.FlatTrainer`` carries
+    ``_cf_grad``, a view of the flat gradient buffer (zeroed by the fused SGD kernel): kernels
+    accumulate into it directly and autograd gets None -- no per-parameter AccumulateGrad kernel, no
+    memset.  Any other parameter gets a view of one zero-filled scratch buffer (a single memset)."""
+    own = [p for p in params if p is not None and getattr(p, "_cf_grad", None) is None]
+    flat = torch.zeros(sum(p.numel() for p in own), device=device, dtype=torch.float32) if own else None
+    bufs, rets, o = [], [], 0
+    for p in params:
+        if p is None:
+            bufs.append(None)
+            rets.append(None)
+        elif getattr(p, "_cf_grad", None) is not None:
+            bufs.append(p._cf_grad)
+            rets.append(None)
+        else:
+            n = p.numel()
+            v = flat[o:o + n].view(p.shape)
+            o += n
+            bufs.append(v)
+            rets.append(v)
+    return bufs, rets
 
 
 # ----------------------------------------------------------------------------------------
@@ -204,7 +220,7 @@ class BottleneckFn(torch.autograd.Function):
         has_se, has_ds = fw1 is not None, wd is not None
         Rin, Rout = T * H * W, To * Ho * Wo
         dout = cl(dout)
-        grads = _flat_grads(ctx.param_shapes, dev)
+        grads, rets = _flat_grads(ctx.param_shapes, dev)
         (dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dfw1, dfb1, dfw2, dfb2, dwd, dgd, dbd) = grads
         Cmax = max(Ce, Co)
         sums = torch.zeros(4, B, Cmax, 2, device=dev, dtype=torch.float64)
@@ -252,7 +268,7 @@ class BottleneckFn(torch.autograd.Function):
             if dx is not None:
                 pw_conv(dz3, wd, dx, B, Co, Cin, g_ds, w_sn=1, w_sk=Cin, x2=yd, pro=PRO_AFFINE2, pro_tabs=(Pd, Qd, Rd),
                         scatter_out=1, accumulate=1)
-        return (dx, None, dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dfw1, dfb1, dfw2, dfb2, dwd, dgd, dbd)
+        return (dx, None, *rets)
 
 
 # ----------------------------------------------------------------------------------------
@@ -262,15 +278,17 @@ class StemFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cfg, ws, wt, gamma, beta):
-        x = x.contiguous().float()
+        x = x.float()
         dev = x.device
         B, Ci, T, H, W = x.shape
+        if not (x.stride(4) == 1 and x.stride(3) == W and x.stride(2) == H * W):
+            x = x.contiguous()           # a temporal window x_full[:, :, a:b] of an NCTHW clip is gathered in place
         C = ws.shape[0]
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         R = T * Ho * Wo
         tr = cfg.training
-        g_s = geom(T, Ho, Wo, T, H, W, k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1), pos_stride=1, ch_stride=T * H * W,
-                   sample_stride=Ci * T * H * W)
+        g_s = geom(T, Ho, Wo, T, H, W, k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1), pos_stride=1, ch_stride=x.stride(1),
+                   sample_stride=x.stride(0))
         g_t = geom(T, Ho, Wo, k=(5, 1, 1), p=(2, 0, 0))
         y0 = new_act(B, C, T, Ho, Wo, dev)
         pw_conv(x, ws, y0, B, Ci * 9, C, g_s, gather_in=1)
@@ -282,6 +300,7 @@ class StemFn(torch.autograd.Function):
         residual_fwd(yt, a, b, out, B, C, R)
         ctx.cfg, ctx.dims, ctx.geoms, ctx.bn = cfg, (B, Ci, C, T, H, W, Ho, Wo), (g_s, g_t), (m, i)
         ctx.save_for_backward(x, y0, yt, out, ws, wt, gamma)
+        ctx.params = (ws, wt, gamma, beta)
         return out
 
     @staticmethod
@@ -293,7 +312,7 @@ class StemFn(torch.autograd.Function):
         dev = x.device
         R = T * Ho * Wo
         dout = cl(dout)
-        dws, dwt, dgam, dbet = _flat_grads([ws, wt, gamma, gamma], dev)
+        (dws, dwt, dgam, dbet), rets = _flat_grads(ctx.params, dev)
         sums = torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
         dz = torch.empty_like(out)
         residual_bwd(dout, out, yt, dz, sums, B, C, R)
@@ -304,9 +323,11 @@ class StemFn(torch.autograd.Function):
         pw_wgrad(dy0, x, dws, B, Ci * 9, C, g_s, gather_in=1)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.zeros_like(x)
-            pw_conv(dy0, ws, dx, B, C, Ci * 9, g_s, w_sn=1, w_sk=Ci * 9, scatter_out=1)
-        return dx, None, dws, dwt, dgam, dbet
+            dx = torch.zeros(x.shape, device=dev, dtype=torch.float32)
+            g_dx = geom(T, Ho, Wo, T, H, W, k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1), pos_stride=1, ch_stride=T * H * W,
+                        sample_stride=Ci * T * H * W)
+            pw_conv(dy0, ws, dx, B, C, Ci * 9, g_dx, w_sn=1, w_sk=Ci * 9, scatter_out=1)
+        return (dx, None, *rets)
 
 
 class ConvBNReluPoolFn(torch.autograd.Function):
@@ -329,6 +350,7 @@ class ConvBNReluPoolFn(torch.autograd.Function):
         call_struct("cf_block_avgpool_fwd", make("cf_pool_args", x=y, y=out, tab_a=a, tab_b=b, B=B, C=C, T=T, H=H, W=W, rh=rh, rw=rw))
         ctx.cfg, ctx.dims, ctx.tabs = cfg, (B, Cin, C, T, H, W, rh, rw), (a, b, m, i)
         ctx.save_for_backward(x, y, w, gamma)
+        ctx.params = (w, gamma, beta)
         return out
 
     @staticmethod
@@ -339,7 +361,7 @@ class ConvBNReluPoolFn(torch.autograd.Function):
         dev = x.device
         R = T * H * W
         dout = cl(dout)
-        dw, dgam, dbet = _flat_grads([w, gamma, gamma], dev)
+        (dw, dgam, dbet), rets = _flat_grads(ctx.params, dev)
         sums = torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
         dz = torch.empty_like(y)
         call_struct("cf_block_avgpool_bwd", make("cf_pool_bwd_args", dy=dout, x=y, tab_a=a, tab_b=b, dz=dz, sums=sums, B=B, C=C,
@@ -351,7 +373,7 @@ class ConvBNReluPoolFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             pw_conv(dz, w, dx, B, C, Cin, g, w_sn=1, w_sk=Cin, x2=y, pro=PRO_AFFINE2, pro_tabs=(P, Q, Rr))
-        return dx, None, dw, dgam, dbet, None, None
+        return (dx, None, *rets, None, None)
 
 
 class AvgPoolFn(torch.autograd.Function):
@@ -395,6 +417,7 @@ class LinearRowsFn(torch.autograd.Function):
         pw_conv(x, w2, y, B, K, N, geom(R, 1, 1), bias=bias, epi=(EPI_NONE, EPI_RELU, EPI_SIGMOID)[act])
         ctx.act, ctx.dims, ctx.wshape, ctx.has_bias = act, (B, R, K, N), w.shape, bias is not None
         ctx.save_for_backward(x, w2, y if act else None)
+        ctx.params = (w, bias)
         return y
 
     @staticmethod
@@ -408,13 +431,13 @@ class LinearRowsFn(torch.autograd.Function):
             call("cf_relu_bwd" if ctx.act == ACT_RELU else "cf_sigmoid_bwd", ptr(dy), ptr(y), ptr(dya), dy.numel(),
                  stream_ptr())
             dy = dya
-        dw, db = _flat_grads([w2, torch.empty(N) if ctx.has_bias else None], dy.device)
+        (dw, db), rets = _flat_grads(ctx.params, dy.device)
         pw_wgrad(dy, x, dw, B, K, N, g, dbias=db)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             pw_conv(dy, w2, dx, B, N, K, g, w_sn=1, w_sk=K)
-        return dx, dw.view(ctx.wshape), db, None
+        return (dx, *rets, None)
 
 
 class SwishFn(torch.autograd.Function):
@@ -455,6 +478,7 @@ class StandaloneBNFn(torch.autograd.Function):
         call_struct("cf_affine_apply", make("cf_affine_args", x=x, x2=None, tab_a=a, tab_b=b, tab_c=None, out=out, B=B, C=C,
                                             rows_per_sample=R, mode=PRO_AFFINE))
         ctx.save_for_backward(x, gamma)
+        ctx.params = (gamma, beta)
         ctx.misc = (m, i, training, B, C, R)
         return out
 
@@ -465,9 +489,9 @@ class StandaloneBNFn(torch.autograd.Function):
         dz = cl(dz)
         sums = torch.zeros(B, C, 2, device=x.device, dtype=torch.float64)
         call("cf_channel_stats", ptr(dz), ptr(x), ptr(sums), B, C, R, stream_ptr())
-        dgam, dbet = _flat_grads([gamma, gamma], x.device)
+        (dgam, dbet), rets = _flat_grads(ctx.params, x.device)
         P, Q, Rr = bn_bwd_coeffs(sums, gamma, m, i, dgam, dbet, B, C, R, training)
         dx = torch.empty_like(x)
         call_struct("cf_affine_apply", make("cf_affine_args", x=dz, x2=x, tab_a=P, tab_b=Q, tab_c=Rr, out=dx, B=B, C=C,
                                             rows_per_sample=R, mode=PRO_AFFINE2))
-        return dx, None, None, dgam, dbet
+        return (dx, None, None, *rets)

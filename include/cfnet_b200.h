@@ -459,6 +459,24 @@ int cf_block_maxpool_fwd(const float* x, float* out, int32_t* idx, int B, int T,
 int cf_block_maxpool_bwd(const float* dout, const int32_t* idx, float* dx, int B, int T, int H, int W, int C, int rh, int rw,
                          cudaStream_t stream);
 
+/* ====================================================================================== */
+/* Training-step glue                                                                       */
+/* ====================================================================================== */
+/* Charades localisation loss of the scripts (train_fine.py:199-212,226; train_coarse_fineFEAT.py:226-247):
+ * logits [B,C,T] are linearly interpolated to the label length TL (align_corners=True),
+ * probs = sigmoid * mask; loss2[0] += BCE_mean(max_t probs, max_t labels), loss2[1] += BCE_sum(probs,
+ * labels)/(sum(mask)*C) (caller zero-fills loss2); dlogits [B,C,T] = d(scale*(loss2[0]+loss2[1]))/dlogits,
+ * i.e. scale = 1/(2*num_steps_per_update) reproduces the scripts.  dlogits may be NULL (evaluation). */
+int cf_charades_loss(const float* logits, const float* labels, const float* masks, float* loss2, float* dlogits, int B, int C,
+                     int T, int TL, float scale, cudaStream_t stream);
+
+/* fused SGD with momentum over flat fp32 buffers (optim.SGD, train_fine.py:130): g = grad_scale*g + wd*p;
+ * v = momentum*v + g; p -= lr*v; g = 0.  Elements [0,n_split) use lr0, the rest lr1 (the 'rw'/'mix'
+ * parameter group at 10x, train_coarse_fineFEAT.py:137-141).  grad_scale = 1/world folds the
+ * data-parallel mean into the update. */
+int cf_sgd_flat(float* p, float* g, float* v, int64_t n, int64_t n_split, float lr0, float lr1, float momentum,
+                float weight_decay, float grad_scale, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

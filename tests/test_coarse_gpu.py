@@ -216,6 +216,10 @@ def test_gridpool_layer_golden(mods):
     relmax(x.grad, g["dx"], 2e-3, "dx")
     params = dict(m.named_parameters())
     for k, gr in sub(g, "grad/").items():
+        if k in ("conv1.bias", "conv2.bias"):
+            # a bias in front of train-mode BatchNorm has an exactly-zero gradient; both sides hold rounding noise
+            assert params[k].grad.abs().max().item() <= 1e-3 * params[k.replace("bias", "weight")].grad.abs().max().item()
+            continue
         relmax(params[k].grad, gr, 5e-3, "grad " + k)
     after = m.state_dict()
     for k in ("bn1.split_bn.running_mean", "bn1.split_bn.running_var", "bn2.split_bn.running_mean", "bn2.split_bn.running_var"):

@@ -1,0 +1,68 @@
+"""CPU tests of the host-side data-parallel logic: flat buffer layout and the world_size-2
+gradient all-reduce over gloo (the NCCL path is the same call on CUDA tensors)."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _model():
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv1d(3, 5, 1)
+            self.rw2 = torch.nn.Linear(5, 3)
+            self.mix2 = torch.nn.Linear(3, 2, bias=False)
+            self.bn_w = torch.nn.Parameter(torch.ones(7))
+    torch.manual_seed(0)
+    return M()
+
+
+def test_flat_layout_and_groups():
+    from coarse_fine_networks_b200 import train
+    m = _model()
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    tr = train.FlatTrainer([m], lr=0.1)
+    assert tr.n % 4 == 0 and tr.n_split % 4 == 0 and 0 < tr.n_split < tr.n
+    names = [n.split(".", 1)[1] for n in tr.names]
+    first_fusion = min(i for i, n in enumerate(names) if train.is_fusion_param(n))
+    assert all(train.is_fusion_param(n) for n in names[first_fusion:])          # fusion group is the tail range
+    assert not any(train.is_fusion_param(n) for n in names[:first_fusion])
+    lo, hi = tr.flat_p.data_ptr(), tr.flat_p.data_ptr() + tr.n * 4
+    for n, p in m.named_parameters():
+        assert torch.equal(p.detach(), before[n])                               # values preserved
+        assert lo <= p.data_ptr() < hi and p.data_ptr() % 16 == 0               # views of the flat buffer, 16 B aligned
+        assert p.grad.data_ptr() == p._cf_grad.data_ptr()
+    tr.flat_p.add_(1.0)
+    assert torch.allclose(m.conv.weight.detach(), before["conv.weight"] + 1.0)  # aliasing
+    assert tr.n_params == sum(p.numel() for p in m.parameters())
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from coarse_fine_networks_b200 import train
+    m = _model()
+    tr = train.FlatTrainer([m], lr=0.1)
+    assert tr.world == world
+    for i, p in enumerate(tr.params):
+        p._cf_grad.fill_(float((rank + 1) * (i + 1)))
+    tr.allreduce()                                   # the one collective of the step
+    ok = all(torch.all(p._cf_grad == float(sum(r + 1 for r in range(world)) * (i + 1))) for i, p in enumerate(tr.params))
+    q.put((rank, bool(ok), float(tr.flat_g.sum())))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_flat_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] == res[1][2]                     # identical reduced buffers on both ranks
