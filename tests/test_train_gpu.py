@@ -135,6 +135,9 @@ def test_joint_two_stream_step_and_cuda_graph(pk):
     tr.step()
     p_eager = tr.flat_p.clone()
     loss_eager = loss.item()
+    # The eager autograd graph must be gone before capture: while it lives, its AccumulateGrad nodes (bound to the
+    # stream they were created on) are reused by later forwards and would pull that stream into the capture.
+    del logits, loss
     # same step again from the same state, captured in a CUDA graph
     fine.load_state_dict(state[0])
     coarse.load_state_dict(state[1])
