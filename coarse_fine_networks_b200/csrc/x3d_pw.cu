@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const cf_pw_wgrad_args a,
 }
 
 // ---------------------------------------------------------------------------------------
+int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream);      // x3d_pw_tc.cu
+
 extern "C" size_t cf_sizeof_pw_args(void) { return sizeof(cf_pw_args); }
 size_t cf_sizeof_pw_wgrad_args(void) { return sizeof(cf_pw_wgrad_args); }
 
@@ -369,6 +371,7 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(!a->gather_in || a->K % taps == 0, "K must be channels*taps");
     CF_CHECK_ARG(!a->scatter_out || a->N % taps == 0, "N must be channels*taps");
     int R = a->g.T * a->g.H * a->g.W;
+    if (a->wpack && !a->gather_in && !a->scatter_out) return cf_pw_conv_tc(a, stream);
     if (a->gather_in) {
         if (a->N <= 32) return launch_pw<32, true>(a, R, stream);
         if (a->N <= 64) return launch_pw<64, true>(a, R, stream);

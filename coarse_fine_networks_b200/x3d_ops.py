@@ -4,9 +4,11 @@ cf_dw_conv_*, cf_bn_*, cf_se_*, cf_residual_*, cf_block_avgpool_*).
 Activations are channels-last fp32 ([B,C,T,H,W] logical shape, torch.channels_last_3d strides);
 BatchNorm / ReLU / SE / Swish never materialise: producers accumulate statistics, consumers
 apply per-(sample,channel) affine tables on load (see include/cfnet_b200.h)."""
+import os
+
 import torch
 
-from ._lib import STRUCTS, call, call_struct, make, ptr, stream_ptr
+from ._lib import STRUCTS, call, call_struct, lib, make, ptr, stream_ptr
 
 CL3 = torch.channels_last_3d
 
@@ -38,13 +40,22 @@ def geom(T, H, W, Ti=None, Hi=None, Wi=None, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 
     return g
 
 
+# Dense pointwise GEMMs run on the tcgen05 tensor cores (3xTF32).  CFNET_PW_SIMT=1 forces the fp32 CUDA-core
+# kernel (used by the tests to cross-check the two paths; not a fallback: both are sm_100a kernels of the library).
+USE_TC = os.environ.get("CFNET_PW_SIMT", "0") != "1"
+
+
 def pw_conv(x, w, y, B, K, N, g, *, w_sn=None, w_sk=1, x2=None, bias=None, pro=PRO_NONE, pro_tabs=(None, None, None),
             epi=EPI_NONE, aux=None, epi_tabs=(None, None), stats=None, stats_mode=STATS_NONE, gather_in=0, scatter_out=0,
-            accumulate=0):
+            accumulate=0, tc=None):
+    wpack, wbytes = None, 0
+    if (USE_TC if tc is None else tc) and not gather_in and not scatter_out:
+        wbytes = int(lib.cf_pw_tc_ws_bytes(K, N))
+        wpack = torch.empty(wbytes // 4, device=y.device, dtype=torch.float32)
     a = make("cf_pw_args", x=x, x2=x2, w=w, bias=bias, y=y, pro_a=pro_tabs[0], pro_b=pro_tabs[1], pro_c=pro_tabs[2],
              aux=aux, epi_a=epi_tabs[0], epi_b=epi_tabs[1], stats=stats, w_sn=(K if w_sn is None else w_sn), w_sk=w_sk,
              B=B, K=K, N=N, g=g, gather_in=gather_in, scatter_out=scatter_out, accumulate=accumulate, pro_mode=pro,
-             epi_mode=epi, stats_mode=stats_mode)
+             epi_mode=epi, stats_mode=stats_mode, wpack=wpack, wpack_bytes=wbytes)
     call_struct("cf_pw_conv", a)
     return y
 

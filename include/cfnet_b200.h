@@ -153,8 +153,14 @@ typedef struct {
     int scatter_out;     /* 1: y is addressed through g; taps > 1 => atomic accumulation */
     int accumulate;      /* 1: y += result */
     int pro_mode, epi_mode, stats_mode;
+    float* wpack;        /* workspace of cf_pw_tc_ws_bytes(K,N) bytes (128-B aligned) or NULL.  When given and the
+                          * problem is dense (no gather / scatter) the GEMM runs on the tcgen05 tensor cores
+                          * (3xTF32, fp32 accumulation in TMEM); NULL selects the fp32 CUDA-core kernel. */
+    int64_t wpack_bytes;
 } cf_pw_args;
 int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream);
+/* bytes of the packed (hi/lo split, swizzled) weight workspace of the tensor-core path */
+size_t cf_pw_tc_ws_bytes(int K, int N);
 
 /* weight gradient:
  *   dw[n*K + k] += sum_{b,r} pro_dy(dy[b,r,n], dy2[b,r,n]) * pro_x(x[b, gather(r,k)]);

@@ -197,11 +197,10 @@ def test_gridpool_layer_golden(mods):
     m = mods.C.GridPoolLayer(4, 8).cuda()
     sd_after = sub(g, "sd_after/")
     sd = {k: v.clone() for k, v in sd_after.items()}
-    for k in sd:                                   # restore pre-step running statistics
-        if k.endswith("running_mean"):
-            sd[k] = torch.zeros_like(sd[k])
-        elif k.endswith("running_var"):
-            sd[k] = torch.ones_like(sd[k])
+    pre = synth_state_dict(m.state_dict(), 5)      # the generator's fill_state_dict(m, seed=5): pre-step running statistics
+    for k in sd:
+        if "running_" in k:
+            sd[k] = pre[k]
         elif k.endswith("num_batches_tracked"):
             sd[k] = torch.zeros_like(sd[k])
     m.load_state_dict(sd, strict=True)

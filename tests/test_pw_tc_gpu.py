@@ -1,0 +1,105 @@
+"""tcgen05 (3xTF32) pointwise GEMM against an fp64 reference and against the fp32 CUDA-core kernel."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from synth import synth_tensor
+
+pytestmark = pytest.mark.gpu
+CL3 = torch.channels_last_3d
+
+
+@pytest.fixture(scope="module")
+def X():
+    import __graft_entry__ as ge
+    ge.build()
+    from coarse_fine_networks_b200 import x3d_ops
+    return x3d_ops
+
+
+def rows(x):
+    return x.cuda().contiguous(memory_format=CL3)
+
+
+def relerr(a, ref):
+    return ((a.detach().cpu().double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("K,N", [(24, 54), (54, 24), (48, 108), (108, 48), (96, 216), (216, 96), (192, 432), (432, 192),
+                                 (432, 2048), (2048, 157), (360, 24), (7, 5), (33, 130), (8, 16)])
+def test_tc_forward_dgrad_stats_vs_fp64(X, K, N):
+    B, T, H, W = 2, 2, 13, 11                               # R = 286 rows per sample: 3 row tiles, ragged tail
+    x = synth_tensor((B, K, T, H, W), 1)
+    w = synth_tensor((N, K), 2, 0.1)
+    ref = torch.einsum("nk,bkthw->bnthw", w.double(), x.double())
+    g = X.geom(T, H, W)
+    out = {}
+    for tc in (True, False):
+        y = X.new_act(B, N, T, H, W, "cuda")
+        stats = torch.zeros(B, N, 2, device="cuda", dtype=torch.float64)
+        X.pw_conv(rows(x), w.cuda(), y, B, K, N, g, stats=stats, stats_mode=X.STATS_SUM_SQ, tc=tc)
+        out[tc] = (relerr(y, ref), relerr(stats[..., 0], ref.sum(dim=(2, 3, 4))), relerr(stats[..., 1], (ref ** 2).sum(dim=(2, 3, 4))))
+    # 3xTF32 must be as accurate as an fp32 FMA chain (well inside the 1e-3 parity bar; single-pass TF32 would give ~1e-3)
+    assert out[True][0] <= max(4.0 * out[False][0], 3e-6), out
+    assert out[True][1] <= 1e-5 and out[True][2] <= 1e-5, out
+    gy = synth_tensor((B, N, T, H, W), 3)
+    dref = torch.einsum("nk,bnthw->bkthw", w.double(), gy.double())
+    dx = X.new_act(B, K, T, H, W, "cuda")
+    X.pw_conv(rows(gy), w.cuda(), dx, B, N, K, g, w_sn=1, w_sk=K, tc=True)
+    assert relerr(dx, dref) <= 3e-6
+
+
+def test_tc_prologues_epilogues_accumulate(X):
+    B, K, N, T, H, W = 2, 54, 24, 2, 12, 11
+    x, x2 = synth_tensor((B, K, T, H, W), 11), synth_tensor((B, K, T, H, W), 12)
+    w = synth_tensor((N, K), 13, 0.2)
+    ta, tb, tcc = synth_tensor((B, K), 14), synth_tensor((B, K), 15), synth_tensor((B, K), 16)
+    aux = synth_tensor((B, N, T, H, W), 17)
+    ea, eb = synth_tensor((B, N), 18), synth_tensor((B, N), 19)
+    bias = synth_tensor((N,), 20)
+    v = lambda t: t.double().view(B, -1, 1, 1, 1)
+    conv = lambda z: torch.einsum("nk,bkthw->bnthw", w.double(), z.double())
+    g = X.geom(T, H, W)
+    cu = lambda t: t.cuda()
+    sw = lambda z: z * torch.sigmoid(z)
+    xd, x2d, auxd = x.double(), x2.double(), aux.double()
+    cases = {X.PRO_AFFINE: v(ta) * xd + v(tb), X.PRO_AFFINE_RELU: F.relu(v(ta) * xd + v(tb)),
+             X.PRO_AFFINE_SWISH: sw(v(ta) * xd + v(tb)), X.PRO_AFFINE2: v(ta) * xd + v(tb) * x2d + v(tcc)}
+    for mode, xin in cases.items():
+        y = X.new_act(B, N, T, H, W, "cuda")
+        X.pw_conv(rows(x), cu(w), y, B, K, N, g, x2=rows(x2), pro=mode, pro_tabs=(cu(ta), cu(tb), cu(tcc)), tc=True)
+        assert relerr(y, conv(xin)) <= 5e-6, f"pro {mode}"
+    base = conv(x)
+    pre = v(ea) * auxd + v(eb)
+    sg = torch.sigmoid(pre)
+    bb = bias.double().view(1, -1, 1, 1, 1)
+    epis = {X.EPI_RELU: F.relu(base + bb), X.EPI_DRELU: base * (pre > 0), X.EPI_DSWISH: base * (sg * (1 + pre * (1 - sg))),
+            X.EPI_ADD_AUX: base + auxd, X.EPI_SIGMOID: torch.sigmoid(base + bb), X.EPI_NONE: base + bb}
+    for mode, ref in epis.items():
+        y = X.new_act(B, N, T, H, W, "cuda")
+        stats = torch.zeros(B, N, 2, device="cuda", dtype=torch.float64)
+        use_bias = mode in (X.EPI_RELU, X.EPI_SIGMOID, X.EPI_NONE)
+        has_aux = mode in (X.EPI_DRELU, X.EPI_DSWISH, X.EPI_ADD_AUX)
+        X.pw_conv(rows(x), cu(w), y, B, K, N, g, bias=cu(bias) if use_bias else None, epi=mode, aux=rows(aux) if has_aux else None,
+                  epi_tabs=(cu(ea), cu(eb)), stats=stats, stats_mode=X.STATS_SUM_AUX if has_aux else X.STATS_SUM_SQ, tc=True)
+        assert relerr(y, ref) <= 5e-6, f"epi {mode}"
+        second = (ref * auxd) if has_aux else ref ** 2
+        assert relerr(stats[..., 1], second.sum(dim=(2, 3, 4))) <= 2e-5, f"epi {mode} stats"
+    y = rows(aux).clone()
+    X.pw_conv(rows(x), cu(w), y, B, K, N, g, accumulate=1, tc=True)
+    assert relerr(y, base + auxd) <= 5e-6, "accumulate"
+
+
+def test_tc_large_rows_layer1_shape(X):
+    """The bench's dominant launch shape at reduced T: 24 -> 54 channels, 112x112, many row tiles per sample."""
+    B, K, N, T, H, W = 2, 24, 54, 3, 112, 112
+    x = synth_tensor((B, K, T, H, W), 5)
+    w = synth_tensor((N, K), 6, 0.2)
+    g = X.geom(T, H, W)
+    y1, y2 = X.new_act(B, N, T, H, W, "cuda"), X.new_act(B, N, T, H, W, "cuda")
+    s1 = torch.zeros(B, N, 2, device="cuda", dtype=torch.float64)
+    s2 = torch.zeros_like(s1)
+    X.pw_conv(rows(x), w.cuda(), y1, B, K, N, g, stats=s1, stats_mode=X.STATS_SUM_SQ, tc=True)
+    X.pw_conv(rows(x), w.cuda(), y2, B, K, N, g, stats=s2, stats_mode=X.STATS_SUM_SQ, tc=False)
+    assert (y1 - y2).abs().max().item() <= 2e-5 * y2.abs().max().item()
+    assert ((s1 - s2).abs() / s2.abs().clamp_min(1.0)).max().item() <= 1e-6
