@@ -338,7 +338,7 @@ temporal_gather_bwd_x_kernel(const V* __restrict__ gout, const int* __restrict__
 template <typename V>
 __global__ void __launch_bounds__(256)
 temporal_gather_bwd_z_kernel(const V* __restrict__ gout, const V* __restrict__ x, const int* __restrict__ i0,
-                             float* __restrict__ dcoord, long long opb, int T, int K, long long inner_v,
+                             double* __restrict__ dcoord, long long opb, int T, int K, long long inner_v,
                              long long chunk_v, float scale) {
     long long o = blockIdx.y;
     int k = blockIdx.z;
@@ -350,21 +350,22 @@ temporal_gather_bwd_z_kernel(const V* __restrict__ gout, const V* __restrict__ x
     const V* x1 = x + (o * (long long)T + (v1 ? a + 1 : 0)) * inner_v;
     long long lo = (long long)blockIdx.x * chunk_v;
     long long hi = lo + chunk_v < inner_v ? lo + chunk_v : inner_v;
-    float acc = 0.f;
+    // the terms gout*(x1-x0) have mixed signs and largely cancel: accumulate in double (the kernel is HBM-bound)
+    double acc = 0.0;
     for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         V g = VecOps<V>::ld(gs + i);
         V p0 = v0 ? VecOps<V>::ld(x0 + i) : VecOps<V>::zero();
         V p1 = v1 ? VecOps<V>::ld(x1 + i) : VecOps<V>::zero();
-        acc += VecOps<V>::dotdiff(g, p1, p0);
+        acc += (double)VecOps<V>::dotdiff(g, p1, p0);
     }
-    __shared__ float red[8];
-    acc = warp_sum(acc);
+    __shared__ double red[8];
+    acc = warp_sum_d(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) atomicAdd(dcoord + b * K + k, v * scale);
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        v = warp_sum_d(v);
+        if (threadIdx.x == 0) atomicAdd(dcoord + b * K + k, v * (double)scale);
     }
 }
 
@@ -493,7 +494,7 @@ int cf_temporal_gather_bwd_x(const float* gout, const int32_t* i0, const float* 
     return CF_OK;
 }
 
-int cf_temporal_gather_bwd_coord(const float* gout, const float* x, const int32_t* i0, float* dcoord_accum,
+int cf_temporal_gather_bwd_coord(const float* gout, const float* x, const int32_t* i0, double* dcoord_accum,
                                  int64_t outer, int64_t outer_per_b, int T, int K, int64_t inner, float scale,
                                  cudaStream_t stream) {
     CF_CHECK_ARG(gout && x && i0 && dcoord_accum, "null pointer");

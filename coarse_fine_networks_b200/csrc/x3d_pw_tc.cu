@@ -433,10 +433,14 @@ static size_t tc_smem_bytes(const TcTiling& t, int K) {
 
 template <int AV, int EV>
 static int launch_tc(const cf_pw_args* a, const TcTiling& t, int R, uint32_t tmem_cols, size_t smem, cudaStream_t stream) {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(pw_tc_kernel<AV, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        done = true;
+    static size_t cur_max = 48 * 1024;       // opt in to more dynamic shared memory as larger problems show up
+    if (smem > cur_max) {
+        cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<AV, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            cf_set_error("cf_pw_conv_tc: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+            return CF_ERR_CUDA;
+        }
+        cur_max = smem;
     }
     int tps = cf_cdiv(R, TC_BM);
     dim3 grid((unsigned)(tps * a->B), (unsigned)t.ntiles);
@@ -452,7 +456,7 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a->wpack_bytes >= (int64_t)cf_pw_tc_ws_bytes(K, N), "weight-pack workspace too small");
     CF_CHECK_ARG((((uintptr_t)a->wpack) & 127) == 0, "weight-pack workspace must be 128-byte aligned");
     size_t smem = tc_smem_bytes(t, K);
-    CF_CHECK_ARG(smem <= 227 * 1024, "K too large for the tensor-core path");
+    CF_CHECK_ARG(smem <= 225 * 1024, "K too large for the tensor-core path");
     CF_CHECK_ARG((long long)cf_cdiv(R, TC_BM) * a->B < (1LL << 31), "too many row tiles");
     {
         long long total = (long long)t.ntiles * t.nchunks * t.NTp * 8;
@@ -470,6 +474,7 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     CF_TC_CASE(4, 4) CF_TC_CASE(4, 2) CF_TC_CASE(4, 1) CF_TC_CASE(2, 4) CF_TC_CASE(2, 2) CF_TC_CASE(2, 1) CF_TC_CASE(1, 4)
     CF_TC_CASE(1, 2) CF_TC_CASE(1, 1) rc = CF_ERR_ARG;
 #undef CF_TC_CASE
+    if (rc != CF_OK) return rc;
     CF_COUNT_LAUNCH(2);
     CF_CHECK_LAUNCH();
     return rc;

@@ -108,9 +108,10 @@ class TemporalSample(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             _, dx = _gather_bwd_x(gout, i0, w1, ctx.meta, xd)
         if ctx.needs_input_grad[1]:
-            dcoord = torch.zeros(i0.shape, device=gout.device, dtype=torch.float32)
+            dcoord = torch.zeros(i0.shape, device=gout.device, dtype=torch.float64)
             call("cf_temporal_gather_bwd_coord", ptr(gout), ptr(xd), ptr(i0), ptr(dcoord), outer, opb, T, K, inner,
                  float(T - 1), stream_ptr())
+            dcoord = dcoord.float()
         return dx, dcoord
 
 

@@ -76,8 +76,9 @@ int cf_temporal_gather_bwd_x(const float* gout, const int32_t* i0, const float* 
                              size_t ws_bytes, int64_t outer, int64_t outer_per_b, int T, int K, int64_t inner,
                              cudaStream_t stream);
 /* dcoord_accum[b,k] += scale * sum_{o in b,i} gout[o,k,i] (x[o,i0+1,i] - x[o,i0,i]);
- * scale = T-1 turns d/dz into d/dcdf. */
-int cf_temporal_gather_bwd_coord(const float* gout, const float* x, const int32_t* i0, float* dcoord_accum,
+ * scale = T-1 turns d/dz into d/dcdf.  The terms cancel heavily, so the sum is carried in fp64
+ * (dcoord_accum is a zero-filled double [B,K] buffer; the caller rounds it to fp32 once). */
+int cf_temporal_gather_bwd_coord(const float* gout, const float* x, const int32_t* i0, double* dcoord_accum,
                                  int64_t outer, int64_t outer_per_b, int T, int K, int64_t inner, float scale,
                                  cudaStream_t stream);
 
