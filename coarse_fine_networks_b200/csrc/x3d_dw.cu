@@ -319,6 +319,248 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const cf_dw_args a, int c
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// 3x3x3 / pad 1 / temporal stride 1 specialisations (every Bottleneck conv2, x3d_fine.py:89-97): the window
+// geometry is compile time (no runtime div / mod per tap) and each thread produces TW = 4 consecutive
+// positions along W so that one row of loaded inputs serves all of them.
+// ---------------------------------------------------------------------------------------
+#define DW3_TW 4
+
+// data gradient: dx[ti,hi,wi] = sum_taps pro(d[t,h,w]) * w[tap], t = ti+1-dt, h = (hi+1-dh)/ST, w = (wi+1-dw)/ST
+template <int V, int ST>
+__global__ void __launch_bounds__(256) dw_dgrad3_kernel(const cf_dw_args a) {
+    extern __shared__ __align__(16) float sm[];
+    const cf_geom& g = a.g;
+    const int C = a.C;
+    float* ws = sm;                 // [27][C]
+    float* sst = sm + 27 * C;       // [2][C]
+    const int tid = threadIdx.x, b = blockIdx.y;
+    for (int i = tid; i < 27 * C; i += 256) {
+        int tap = i / C, c = i - tap * C;
+        ws[i] = a.w[(size_t)c * 27 + tap];
+    }
+    const bool do_stats = a.stats_mode != CF_STATS_NONE;
+    if (do_stats) for (int i = tid; i < 2 * C; i += 256) sst[i] = 0.f;
+    __syncthreads();
+    constexpr int TW = DW3_TW;
+    constexpr int SPAN = (ST == 1) ? TW + 2 : TW / 2 + 1;
+    const int CV = C / V, WG = (g.Wi + TW - 1) / TW;
+    const long long task = (long long)blockIdx.x * 256 + tid;
+    const long long ntask = (long long)g.Ti * g.Hi * WG * CV;
+    if (task < ntask) {
+        const int cv = (int)(task % CV);
+        long long q = task / CV;
+        const int wg = (int)(q % WG); q /= WG;
+        const int hi = (int)(q % g.Hi);
+        const int ti = (int)(q / g.Hi);
+        const int c0 = cv * V;
+        const int wi0 = wg * TW;
+        const int wbase = (ST == 1) ? wi0 - 1 : wi0 / 2;
+        const bool aff2 = a.pro_mode == CF_PRO_AFFINE2;
+        Vec<V> pa, pb, pc;
+#pragma unroll
+        for (int i = 0; i < V; ++i) { pa.v[i] = 1.f; pb.v[i] = 0.f; pc.v[i] = 0.f; }
+        if (a.pro_mode != CF_PRO_NONE) {
+            pa = vload_s<V>(a.pro_a + (size_t)b * C + c0);
+            if (a.pro_b) pb = vload_s<V>(a.pro_b + (size_t)b * C + c0);
+            if (a.pro_c) pc = vload_s<V>(a.pro_c + (size_t)b * C + c0);
+        }
+        Vec<V> acc[TW];
+#pragma unroll
+        for (int u = 0; u < TW; ++u)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[u].v[i] = 0.f;
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+            const int t = ti + 1 - dt;
+            if ((unsigned)t >= (unsigned)g.T) continue;
+#pragma unroll
+            for (int dh = 0; dh < 3; ++dh) {
+                const int hn = hi + 1 - dh;
+                if (hn < 0 || (ST == 2 && (hn & 1))) continue;
+                const int h = hn / ST;
+                if (h >= g.H) continue;
+                const long long rowoff = ((((long long)b * g.T + t) * g.H + h) * g.W) * C + c0;
+                Vec<V> in[SPAN];
+#pragma unroll
+                for (int j = 0; j < SPAN; ++j) {
+                    const int w = wbase + j;
+                    if ((unsigned)w < (unsigned)g.W) {
+                        Vec<V> dv = vload<V>(a.x + rowoff + (long long)w * C);
+                        if (aff2) {
+                            Vec<V> d2 = vload<V>(a.x2 + rowoff + (long long)w * C);
+#pragma unroll
+                            for (int i = 0; i < V; ++i) in[j].v[i] = fmaf(pa.v[i], dv.v[i], fmaf(pb.v[i], d2.v[i], pc.v[i]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < V; ++i) in[j].v[i] = dw_pro(a.pro_mode, dv.v[i], 0.f, pa.v[i], pb.v[i], pc.v[i]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < V; ++i) in[j].v[i] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int dw = 0; dw < 3; ++dw) {
+                    const Vec<V> wv = vload_s<V>(ws + (size_t)((dt * 3 + dh) * 3 + dw) * C + c0);
+#pragma unroll
+                    for (int u = 0; u < TW; ++u) {
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const int wn = u + 1 - dw;                 // relative to wi0 (a multiple of 4)
+                        if (ST == 2 && (wn & 1)) continue;
+                        const int j = (ST == 1) ? wn + 1 : wn / 2;
+                        if (j < 0 || j >= SPAN) continue;
+#pragma unroll
+                        for (int i = 0; i < V; ++i) acc[u].v[i] = fmaf(in[j].v[i], wv.v[i], acc[u].v[i]);
+                    }
+                }
+            }
+        }
+        Vec<V> ea, eb, s1, s2;
+#pragma unroll
+        for (int i = 0; i < V; ++i) { ea.v[i] = 1.f; eb.v[i] = 0.f; s1.v[i] = 0.f; s2.v[i] = 0.f; }
+        if (a.epi_mode == CF_EPI_DRELU) { ea = vload_s<V>(a.epi_a + (size_t)b * C + c0); eb = vload_s<V>(a.epi_b + (size_t)b * C + c0); }
+        const long long orow = ((((long long)b * g.Ti + ti) * g.Hi + hi) * g.Wi) * C + c0;
+#pragma unroll
+        for (int u = 0; u < TW; ++u) {
+            const int wi = wi0 + u;
+            if (wi >= g.Wi) continue;
+            const long long ooff = orow + (long long)wi * C;
+            Vec<V> auxv;
+#pragma unroll
+            for (int i = 0; i < V; ++i) auxv.v[i] = 0.f;
+            if (a.epi_mode == CF_EPI_DRELU || a.stats_mode == CF_STATS_SUM_AUX) auxv = vload<V>(a.aux + ooff);
+            if (a.epi_mode == CF_EPI_DRELU) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc[u].v[i] = (fmaf(ea.v[i], auxv.v[i], eb.v[i]) > 0.f) ? acc[u].v[i] : 0.f;
+            }
+            vstore<V>(a.y + ooff, acc[u]);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                s1.v[i] += acc[u].v[i];
+                s2.v[i] += a.stats_mode == CF_STATS_SUM_AUX ? acc[u].v[i] * auxv.v[i] : acc[u].v[i] * acc[u].v[i];
+            }
+        }
+        if (do_stats) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { atomicAdd(sst + c0 + i, s1.v[i]); atomicAdd(sst + C + c0 + i, s2.v[i]); }
+        }
+    }
+    if (do_stats) {
+        __syncthreads();
+        for (int i = tid; i < C; i += 256) {
+            double* st = a.stats + ((size_t)b * C + i) * 2;
+            atomicAdd(st, (double)sst[i]);
+            atomicAdd(st + 1, (double)sst[C + i]);
+        }
+    }
+}
+
+// weight gradient: dw[c,tap] += sum_pos pro2(d[pos,c], y2[pos,c]) * act(x[pos_in(tap),c]); each loop iteration takes
+// TWG = 2 neighbouring output positions along W so the 3 input rows are loaded once for both
+template <int V, int ST>
+__global__ void __launch_bounds__(256) dw_wgrad3_kernel(const cf_dw_args a, int chunk) {
+    extern __shared__ __align__(16) float sm[];     // [27][C]
+    const cf_geom& g = a.g;
+    const int C = a.C;
+    const int tid = threadIdx.x, b = blockIdx.y;
+    for (int i = tid; i < 27 * C; i += 256) sm[i] = 0.f;
+    __syncthreads();
+    constexpr int TWG = 2;
+    constexpr int SPAN = (TWG - 1) * ST + 3;
+    const int CV = C / V, PY = 256 / CV;
+    const int cv = tid % CV, lane = tid / CV;
+    const int WG = (g.W + TWG - 1) / TWG;
+    const long long NG = (long long)g.T * g.H * WG;          // position groups per sample
+    const long long p0 = (long long)blockIdx.x * chunk;
+    const long long p1 = p0 + chunk < NG ? p0 + chunk : NG;
+    if (lane < PY) {
+        const int c0 = cv * V;
+        const bool aff2 = a.pro_mode == CF_PRO_AFFINE2;
+        const bool act = a.epi_a != nullptr;
+        Vec<V> da, db, dc, xa, xb;
+#pragma unroll
+        for (int i = 0; i < V; ++i) { da.v[i] = 1.f; db.v[i] = 0.f; dc.v[i] = 0.f; xa.v[i] = 1.f; xb.v[i] = 0.f; }
+        if (a.pro_mode != CF_PRO_NONE) {
+            da = vload_s<V>(a.pro_a + (size_t)b * C + c0);
+            if (a.pro_b) db = vload_s<V>(a.pro_b + (size_t)b * C + c0);
+            if (a.pro_c) dc = vload_s<V>(a.pro_c + (size_t)b * C + c0);
+        }
+        if (act) { xa = vload_s<V>(a.epi_a + (size_t)b * C + c0); xb = vload_s<V>(a.epi_b + (size_t)b * C + c0); }
+        Vec<V> acc[27];
+#pragma unroll
+        for (int tp = 0; tp < 27; ++tp)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[tp].v[i] = 0.f;
+        for (long long p = p0 + lane; p < p1; p += PY) {
+            const int wgi = (int)(p % WG);
+            const long long q = p / WG;
+            const int h = (int)(q % g.H);
+            const int t = (int)(q / g.H);
+            const int w0 = wgi * TWG;
+            Vec<V> d[TWG];
+            const long long drow = ((((long long)b * g.T + t) * g.H + h) * g.W) * C + c0;
+#pragma unroll
+            for (int u = 0; u < TWG; ++u) {
+                if (w0 + u < g.W) {
+                    d[u] = vload<V>(a.x + drow + (long long)(w0 + u) * C);
+                    if (aff2) {
+                        Vec<V> d2 = vload<V>(a.x2 + drow + (long long)(w0 + u) * C);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) d[u].v[i] = fmaf(da.v[i], d[u].v[i], fmaf(db.v[i], d2.v[i], dc.v[i]));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) d[u].v[i] = 0.f;
+                }
+            }
+            const int wib = w0 * ST - 1;
+#pragma unroll
+            for (int dt = 0; dt < 3; ++dt) {
+                const int ti = t - 1 + dt;
+                if ((unsigned)ti >= (unsigned)g.Ti) continue;
+#pragma unroll
+                for (int dh = 0; dh < 3; ++dh) {
+                    const int hi = h * ST - 1 + dh;
+                    if ((unsigned)hi >= (unsigned)g.Hi) continue;
+                    const long long xrow = ((((long long)b * g.Ti + ti) * g.Hi + hi) * g.Wi) * C + c0;
+                    Vec<V> xin[SPAN];
+#pragma unroll
+                    for (int j = 0; j < SPAN; ++j) {
+                        const int wi = wib + j;
+                        if ((unsigned)wi < (unsigned)g.Wi) {
+                            Vec<V> xv = vload<V>(a.aux + xrow + (long long)wi * C);
+#pragma unroll
+                            for (int i = 0; i < V; ++i) xin[j].v[i] = act ? fmaxf(fmaf(xa.v[i], xv.v[i], xb.v[i]), 0.f) : xv.v[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < V; ++i) xin[j].v[i] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+                        for (int u = 0; u < TWG; ++u)
+#pragma unroll
+                            for (int i = 0; i < V; ++i)
+                                acc[(dt * 3 + dh) * 3 + dw].v[i] = fmaf(d[u].v[i], xin[u * ST + dw].v[i], acc[(dt * 3 + dh) * 3 + dw].v[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int tp = 0; tp < 27; ++tp)
+#pragma unroll
+            for (int i = 0; i < V; ++i) atomicAdd(sm + tp * C + c0 + i, acc[tp].v[i]);
+    }
+    __syncthreads();
+    for (int i = tid; i < 27 * C; i += 256) {
+        int tp = i / C, c = i - tp * C;
+        atomicAdd(a.y + (size_t)c * 27 + tp, sm[i]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 extern "C" size_t cf_sizeof_dw_args(void) { return sizeof(cf_dw_args); }
 
@@ -390,6 +632,43 @@ static int launch_dw_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     return CF_OK;
 }
 
+static bool is_333(const cf_geom& g) {
+    return g.kt == 3 && g.kh == 3 && g.kw == 3 && g.pt == 1 && g.ph == 1 && g.pw == 1 && g.st == 1 && g.sh == g.sw &&
+           (g.sh == 1 || g.sh == 2);
+}
+
+template <int V, int ST>
+static int launch_dw_dgrad3(const cf_dw_args* a, cudaStream_t stream) {
+    const cf_geom& g = a->g;
+    size_t smem = (size_t)(27 + 2) * a->C * sizeof(float);
+    long long ntask = (long long)g.Ti * g.Hi * ((g.Wi + DW3_TW - 1) / DW3_TW) * (a->C / V);
+    dim3 grid((unsigned)cf_cdiv64(ntask, 256), (unsigned)a->B);
+    static bool done = false;
+    if (!done) { set_smem(dw_dgrad3_kernel<V, ST>); done = true; }
+    dw_dgrad3_kernel<V, ST><<<grid, 256, smem, stream>>>(*a);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}
+
+template <int V, int ST>
+static int launch_dw_wgrad3(const cf_dw_args* a, cudaStream_t stream) {
+    const cf_geom& g = a->g;
+    size_t smem = (size_t)27 * a->C * sizeof(float);
+    long long NG = (long long)g.T * g.H * ((g.W + 1) / 2);
+    int PY = 256 / (a->C / V);
+    long long want_ctas = cf_cdiv64(148 * 4, a->B);
+    long long chunk = cf_cdiv64(NG, want_ctas);
+    if (chunk < 4LL * PY) chunk = 4LL * PY;
+    dim3 grid((unsigned)cf_cdiv64(NG, chunk), (unsigned)a->B);
+    static bool done = false;
+    if (!done) { set_smem(dw_wgrad3_kernel<V, ST>); done = true; }
+    dw_wgrad3_kernel<V, ST><<<grid, 256, smem, stream>>>(*a, (int)chunk);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}
+
 static int dw_common_checks(const cf_dw_args* a) {
     CF_CHECK_ARG(a && a->x && a->w && a->y, "null pointer");
     CF_CHECK_ARG(a->B > 0 && a->C > 0 && a->B <= 65535, "bad shape");
@@ -418,6 +697,12 @@ extern "C" int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     int v = pick_vec(a->C, a->x, a->y);
     if (a->x2 && (((uintptr_t)a->x2) & 15)) v = v > 2 ? 2 : v;
     if (a->aux && (((uintptr_t)a->aux) & 15)) v = v > 2 ? 2 : v;
+    if (is_333(a->g)) {
+        const bool s2 = a->g.sh == 2;
+        if (v == 4) return s2 ? launch_dw_dgrad3<4, 2>(a, stream) : launch_dw_dgrad3<4, 1>(a, stream);
+        if (v == 2) return s2 ? launch_dw_dgrad3<2, 2>(a, stream) : launch_dw_dgrad3<2, 1>(a, stream);
+        return s2 ? launch_dw_dgrad3<1, 2>(a, stream) : launch_dw_dgrad3<1, 1>(a, stream);
+    }
     if (v == 4) return launch_dw_dgrad<4>(a, stream);
     if (v == 2) return launch_dw_dgrad<2>(a, stream);
     return launch_dw_dgrad<1>(a, stream);
@@ -431,6 +716,12 @@ extern "C" int cf_dw_conv_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     int taps = a->g.kt * a->g.kh * a->g.kw;
     int v = pick_vec(a->C, a->x, a->aux);
     if (a->C / v > 256) { cf_set_error("cf_dw_conv_wgrad: C/vec > 256"); return CF_ERR_ARG; }
+    if (is_333(a->g)) {
+        const bool s2 = a->g.sh == 2;
+        if (v == 4) return s2 ? launch_dw_wgrad3<4, 2>(a, stream) : launch_dw_wgrad3<4, 1>(a, stream);
+        if (v == 2) return s2 ? launch_dw_wgrad3<2, 2>(a, stream) : launch_dw_wgrad3<2, 1>(a, stream);
+        return s2 ? launch_dw_wgrad3<1, 2>(a, stream) : launch_dw_wgrad3<1, 1>(a, stream);
+    }
     if (taps == 27) {
         if (v == 4) return launch_dw_wgrad<4, 27>(a, stream);
         if (v == 2) return launch_dw_wgrad<2, 27>(a, stream);

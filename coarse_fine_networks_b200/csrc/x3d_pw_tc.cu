@@ -10,7 +10,7 @@
 //
 // Precision: the reference is fp32 and the parity bar is 1e-3 on train-mode logits, which single-pass
 // TF32 misses (3e-3, SURVEY 8(a) finding 2).  Every operand is split on the fly into hi = tf32(x) and
-// lo = x - hi and three kind::tf32 MMAs (lo*hi + hi*lo + hi*hi) accumulate in fp32 in TMEM ("3xTF32"):
+// lo = tf32(x - hi) (round to nearest) and three kind::tf32 MMAs (lo*hi + hi*lo + hi*hi) accumulate in fp32 in TMEM ("3xTF32"):
 // ~2^-21 relative error, and the extra tensor work hides under the HBM time of these skinny GEMMs.
 //
 // One CTA = 128 rows of ONE sample x one tile of <= 128 output channels; K is walked in chunks of 32
@@ -110,7 +110,17 @@ __device__ __host__ __forceinline__ uint32_t sw128_off(int row, int q) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((q ^ (row & 7)) << 4));
 }
 
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// round-to-nearest TF32 (cvt.rna): with truncation the dropped lo*lo term and the hardware's truncation of lo are
+// one-signed and the error grows linearly in K (1.7e-5 at K = 2048); rounded, the residuals are symmetric.
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
+    hi = tf32_rn(v);
+    lo = tf32_rn(v - hi);
+}
 
 __device__ __forceinline__ float tc_swish(float v) { return v * cf_sigmoid(v); }
 __device__ __forceinline__ float tc_dswish(float v) {
@@ -146,8 +156,7 @@ __global__ void pw_tc_pack_kernel(const float* __restrict__ w, long long w_sn, l
     for (int e = 0; e < 4; ++e) {
         int k = c * TC_KC + q * 4 + e;
         float v = (nl < NT && n < N && k < K) ? __ldg(w + (long long)n * w_sn + (long long)k * w_sk) : 0.f;
-        hi[e] = tf32_hi(v);
-        lo[e] = v - hi[e];
+        tf32_split(v, hi[e], lo[e]);
     }
     char* blk = (char*)pack + ((long long)(j * nchunks + c) * 2 * NTp * 128);
     uint32_t off = sw128_off(nl, q);
@@ -301,8 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const cf_pw_args a, c
             for (int e = 0; e < 4; ++e) {
                 float t = v[p][e];
                 if (pro != CF_PRO_NONE) t = (row < rows_valid && k + e < K) ? tc_pro(pro, t, pro == CF_PRO_AFFINE2 ? v2[p][e] : 0.f, pa[e], pb[e], pc[e]) : 0.f;
-                hi[e] = tf32_hi(t);
-                lo[e] = t - hi[e];
+                tf32_split(t, hi[e], lo[e]);
             }
             const uint32_t off = sw128_off(row, q);
             *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);

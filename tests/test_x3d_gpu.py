@@ -61,7 +61,7 @@ def test_pw_conv_plain_and_stats(X, K, N):
     g = synth_tensor((B, N, T, H, W), 3)
     dx = X.new_act(B, K, T, H, W, "cuda")
     X.pw_conv(rows(g), w.cuda(), dx, B, N, K, X.geom(T, H, W), w_sn=1, w_sk=K)
-    close(dx, torch.einsum("nk,bnthw->bkthw", w, g), rtol=1e-5, atol=1e-5, what="dgrad")
+    close(dx, torch.einsum("nk,bnthw->bkthw", w, g), rtol=2e-5, atol=1e-5, what="dgrad")
     # weight gradient
     dw = torch.zeros(N, K, device="cuda")
     db = torch.zeros(N, device="cuda")
