@@ -323,21 +323,16 @@ def test_coarse_net_eval_mode_all_grads_vs_fp64(mods):
     out = m([x.cuda(), {k: v.cuda() for k, v in feat.items()}, mask.cuda(), 0, meta.cuda()])
     relmax(out, o64.float(), 1e-3, "eval logits vs fp64")
     (out * gout.cuda()).sum().backward()
-    n_checked, n_good, gs, g64s = 0, 0, [], []
+    coss = []
     for k, p in m.named_parameters():
         g64 = p64[k].grad
         if g64 is None or float(g64.abs().max()) == 0.0:
             continue
-        n_checked += 1
         g = p.grad.detach().cpu().double()
-        cos = float((g * g64).sum() / (g.norm() * g64.norm()).clamp_min(1e-300))
-        n_good += cos >= 0.99
-        gs.append(g.flatten() / g64.norm().clamp_min(1e-300))           # per-tensor normalisation: every tensor counts alike
-        g64s.append(g64.flatten() / g64.norm().clamp_min(1e-300))
-    G, G64 = torch.cat(gs), torch.cat(g64s)
-    total_cos = float((G * G64).sum() / (G.norm() * G64.norm()))
-    assert n_checked > 380, n_checked
-    assert total_cos >= 0.999 and n_good >= 0.98 * n_checked, (total_cos, n_good, n_checked)
+        coss.append(float((g * g64).sum() / (g.norm() * g64.norm()).clamp_min(1e-300)))
+    coss.sort()
+    assert len(coss) > 380, len(coss)
+    assert coss[len(coss) // 2] >= 0.9999 and coss[len(coss) // 50] >= 0.99, (coss[:5], coss[len(coss) // 2])
 
 
 def test_coarse_net_int_meta_and_shipped_ckpt_keys(mods):
