@@ -25,102 +25,11 @@
 #include "cf_common.cuh"
 #include "../../include/cfnet_b200.h"
 
-#define TC_BM 128
-#define TC_KC 32
 #define TC_THREADS 256
 #define TC_NT_MAX 128
 #define TC_A_STAGE_BYTES (2 * TC_BM * TC_KC * 4)      /* hi + lo */
 
-// ---------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(0x989680u)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
-    uint32_t u[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
-// bits [0,14), leading byte offset (unused for swizzled K-major, 1) in [16,30), stride byte offset = 1024 B
-// (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// byte offset of (row, 16-byte chunk q) inside a [rows][32 floats] K-major SWIZZLE_128B tile
-__device__ __host__ __forceinline__ uint32_t sw128_off(int row, int q) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((q ^ (row & 7)) << 4));
-}
-
-// round-to-nearest TF32 (cvt.rna): with truncation the dropped lo*lo term and the hardware's truncation of lo are
-// one-signed and the error grows linearly in K (1.7e-5 at K = 2048); rounded, the residuals are symmetric.
-__device__ __forceinline__ float tf32_rn(float v) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    return __uint_as_float(u);
-}
-__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
-    hi = tf32_rn(v);
-    lo = tf32_rn(v - hi);
-}
+#include "tc_ptx.cuh"
 
 __device__ __forceinline__ float tc_swish(float v) { return v * cf_sigmoid(v); }
 __device__ __forceinline__ float tc_dswish(float v) {
@@ -429,10 +338,17 @@ static TcTiling tc_tiling(int K, int N) {
     return t;
 }
 
-extern "C" size_t cf_pw_tc_ws_bytes(int K, int N) {
+static size_t tc_v1_ws_bytes(int K, int N) {
     if (K <= 0 || N <= 0) return 0;
     TcTiling t = tc_tiling(K, N);
     return (size_t)t.ntiles * t.nchunks * 2 * t.NTp * 128;
+}
+
+// host launcher of the weight packer, shared with the persistent kernel (x3d_pw_tc2.cu)
+void cf_pw_tc_pack_launch(const float* w, long long w_sn, long long w_sk, float* pack, int K, int N, int NT, int NTp, int ntiles,
+                          int nchunks, cudaStream_t stream) {
+    long long total = (long long)ntiles * nchunks * NTp * 8;
+    pw_tc_pack_kernel<<<(unsigned)cf_cdiv64(total, 256), 256, 0, stream>>>(w, w_sn, w_sk, pack, K, N, NT, NTp, ntiles, nchunks);
 }
 
 static size_t tc_smem_bytes(const TcTiling& t, int K) {
@@ -456,12 +372,12 @@ static int launch_tc(const cf_pw_args* a, const TcTiling& t, int R, uint32_t tme
     return CF_OK;
 }
 
-// called by cf_pw_conv (x3d_pw.cu) for dense problems when the caller supplied a weight-pack workspace
-int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
+// the first tensor-core kernel (one tile per CTA), kept behind CFNET_PW_TC_V1=1 for A/B measurements
+int cf_pw_conv_tc_v1(const cf_pw_args* a, cudaStream_t stream) {
     const int K = a->K, N = a->N;
     const int R = a->g.T * a->g.H * a->g.W;
     TcTiling t = tc_tiling(K, N);
-    CF_CHECK_ARG(a->wpack_bytes >= (int64_t)cf_pw_tc_ws_bytes(K, N), "weight-pack workspace too small");
+    CF_CHECK_ARG(a->wpack_bytes >= (int64_t)tc_v1_ws_bytes(K, N), "weight-pack workspace too small");
     CF_CHECK_ARG((((uintptr_t)a->wpack) & 127) == 0, "weight-pack workspace must be 128-byte aligned");
     size_t smem = tc_smem_bytes(t, K);
     CF_CHECK_ARG(smem <= 225 * 1024, "K too large for the tensor-core path");
