@@ -105,21 +105,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (an error the host sees), never as a hung GPU.
-// Each try_wait may suspend up to ~10 ms; 400 rounds = seconds, far beyond any legitimate wait of these kernels.
+// Plain try_wait polls (the suspend-time-hint form woke up only every ~200 cycles); after a short burst the warp backs
+// off with nanosleep so that waiting roles do not take issue slots from working ones.  ~2^22 backed-off polls = seconds.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    for (int spin = 0; spin < 400; ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, P1;\n\t"
-            "}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(0x989680u)
-            : "memory");
-        if (ok) return;
+#pragma unroll 1
+    for (int spin = 0; spin < 16; ++spin)
+        if (mbar_try(addr, parity)) return;
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        __nanosleep(40);
+        if (mbar_try(addr, parity)) return;
     }
     __trap();
 }

@@ -7,13 +7,14 @@
 // 3xTF32 arithmetic as the one-tile-per-CTA kernel in x3d_pw_tc.cu (which measured 16-21 % of HBM peak: one
 // CTA did load -> MMA -> epilogue strictly in sequence with 12 KB of loads in flight per SM).  Here:
 //
-//   * one CTA per SM walks the (row tile, channel tile) list; 16 warps in two roles that only meet at mbarriers:
+//   * one CTA per SM walks the (row tile, channel tile) list; 20 warps in three roles that only meet at mbarriers (register budgets
+//     rebalanced per role with setmaxnreg: 120 / 32 / 104):
 //       warps 0-7   producers: global loads of the next 3 (1 with a second input) activation chunks are in
 //                   flight in registers while the current one gets its BatchNorm/ReLU/Swish/BN-backward
 //                   prologue, the hi/lo TF32 split and the SWIZZLE_128B store into a ring of A stages;
-//                   the warp that completes a stage has one lane issue its tcgen05.mma's (3 per 8 k) into one of two
-//                   TMEM accumulators and commit the stage-free / accumulator-full barriers;
-//       warps 8-15  epilogue: two groups of four warps (one per TMEM lane quadrant) take alternate 32-column
+//       warp  8     MMA issuer: the warp walks the stages convergently, one elected lane issues the tcgen05.mma's
+//                   (3 per 8 k) into one of two TMEM accumulators and commits stage-free / accumulator-full barriers;
+//       warps 12-19 epilogue: two groups of four warps (one per TMEM lane quadrant) take alternate 32-column
 //                   slabs: tcgen05.ld -> padded shared slab -> coalesced row-major stores with bias /
 //                   activation derivative / residual add and the BatchNorm statistics;
 //     so the loads of tile i+1, the MMAs of tile i and the stores of tile i-1 overlap;
@@ -31,7 +32,14 @@
 #define P2_EPI_WARPS 8
 #define P2_PROD_THREADS (P2_PROD_WARPS * 32)
 #define P2_EPI_THREADS (P2_EPI_WARPS * 32)
-#define P2_THREADS ((P2_PROD_WARPS + P2_EPI_WARPS) * 32)
+#define P2_MMA_WARP P2_PROD_WARPS
+#define P2_EPI_WARP0 (P2_PROD_WARPS + 4)          /* roles are warpgroup (4-warp) aligned for setmaxnreg */
+#define P2_THREADS ((P2_PROD_WARPS + 4 + P2_EPI_WARPS) * 32)
+// register budgets after setmaxnreg: registers only move WITHIN the CTA's launch allocation (640 threads x 96 = 61440),
+// an .inc beyond it waits forever: 256 x 120 + 128 x 32 + 256 x 104 = 61440
+#define P2_REGS_PROD 120
+#define P2_REGS_MMA 32
+#define P2_REGS_EPI 104
 #define P2_A_STAGE (2 * TC_BM * TC_KC * 4) /* hi + lo: 32 KB */
 #define P2_CS_LD 36
 #define P2_CS_FLOATS (TC_BM * P2_CS_LD)
@@ -40,15 +48,25 @@
 #define P2_NT_MAX 224
 #define P2_SMEM_MAX (222 * 1024) /* dynamic; + ~4.2 KB static stays under the 227 KB per-CTA limit */
 
+// cycle counters of CTA 0 (CFNET_PW_TC_TIMING=1; read back with cf_pw_tc_debug_read): where each role's time goes
+__device__ long long p2_dbg[32];
+#define P2_T0() (p.timing ? clock64() : 0)
+#define P2_ACC(slot, t0) do { if (p.timing) { long long t1__ = clock64(); tacc[slot] += t1__ - (t0); (t0) = t1__; } } while (0)
+
 struct P2Params {
-    int B, R, tps, ntiles, NT, NTp, nchunks, nstages, resident, acc_stride, KP, g_j, g_rt;
+    int B, R, tps, ntiles, NT, NTp, nchunks, nstages, resident, acc_stride, KP, g_j, g_rt, timing, dbg_1x;
     uint32_t tmem_cols, b_chunk_bytes, stage_bytes;
     long long total_tiles;
 };
 
-// sigmoid from ex2.approx / rcp.approx (2^-22 relative: at the 3xTF32 level, far inside the 1e-3 parity bar); the
-// IEEE expf + division cost 4x more issue slots and made the Swish producers instruction-bound
-__device__ __forceinline__ float p2_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid from ex2.approx / rcp.approx (2^-22 relative: at the 3xTF32 level, far inside the 1e-3 parity bar): 5 issue
+// slots (2 of them MUFU) instead of ~16 for expf + IEEE division, which made the Swish producers instruction-bound
+__device__ __forceinline__ float p2_sigmoid(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
 __device__ __forceinline__ float p2_swish(float v) { return v * p2_sigmoid(v); }
 __device__ __forceinline__ float p2_dswish(float v) {
     float s = p2_sigmoid(v);
@@ -135,16 +153,18 @@ __device__ __forceinline__ void p2_load_item(const cf_pw_args& a, const P2Params
     const int K = a.K;
     const int k = it.c * TC_KC + q * 4;
     const int rows_valid = min(TC_BM, p.R - it.r0);
-    const size_t base = ((size_t)it.b * p.R + it.r0) * K;
+    const size_t off = ((size_t)it.b * p.R + it.r0 + rr) * K + k;
+    const float* xp = a.x + off;
+    const float* x2p = X2 ? a.x2 + off : nullptr;
+    const size_t step = (size_t)32 * K;
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp) {
-        const int row = pp * 32 + rr;
-        const bool rv = row < rows_valid;
+    for (int pp = 0; pp < 4; ++pp, xp += step, x2p += X2 ? step : 0) {
+        const bool rv = pp * 32 + rr < rows_valid;
 #pragma unroll
         for (int e = 0; e < 4; e += AV) {
             if (rv && k + e < K) {
-                P2Vec<AV>::ld(a.x + base + (size_t)row * K + k + e, &v[pp][e]);
-                if (X2) P2Vec<AV>::ld(a.x2 + base + (size_t)row * K + k + e, &v2[X2 ? pp : 0][e]);
+                P2Vec<AV>::ld(xp + e, &v[pp][e]);
+                if (X2) P2Vec<AV>::ld(x2p + e, &v2[X2 ? pp : 0][e]);
             } else {
 #pragma unroll
                 for (int u = 0; u < AV; ++u) {
@@ -157,9 +177,8 @@ __device__ __forceinline__ void p2_load_item(const cf_pw_args& a, const P2Params
 }
 
 template <int AV, int PRO>
-__device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params& p, uint8_t* stages, uint8_t* wres, float* tab,
-                                            uint64_t* full, uint64_t* empty, uint64_t* tfull, uint64_t* tempty, uint64_t* wres_bar,
-                                            uint32_t* fill_cnt, uint32_t tmem, const float* __restrict__ pack, int tid) {
+__device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params& p, uint8_t* stages, float* tab, uint64_t* full,
+                                            uint64_t* empty, const float* __restrict__ pack, int tid) {
     constexpr bool X2 = PRO == CF_PRO_AFFINE2;
     constexpr int NSET = X2 ? 2 : 4;
     const int lane = tid & 31;
@@ -178,7 +197,10 @@ __device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params&
     }
     int cur_b = -1;
     int s = 0;
-    uint32_t ph = 0, tcount = 0;
+    uint32_t ph = 0;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tt = P2_T0();
+    const long long tstart = tt;
     while (pr.valid) {
 #pragma unroll
         for (int u = 0; u < NSET; ++u) {
@@ -199,7 +221,9 @@ __device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params&
                 named_bar_sync(1, P2_PROD_THREADS);
                 cur_b = pr.b;
             }
+            P2_ACC(0, tt);                                   // 0: loads issued + tables
             mbar_wait_b(&empty[s], ph ^ 1u);
+            P2_ACC(1, tt);                                   // 1: wait for a free stage
             uint8_t* stage = stages + (size_t)s * p.stage_bytes;
             if (!p.resident && tid == 0) {
                 mbar_expect_tx(&full[s], p.b_chunk_bytes);
@@ -239,124 +263,198 @@ __device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params&
                 *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
+            P2_ACC(2, tt);                                   // 2: prologue + split + stores
             fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) {
-                // The producer warp that completes a stage issues its MMAs (no dedicated MMA warp: 16 warps keep the
-                // 128-register budget).  Stages complete in item order because every warp finishes item i -- including
-                // the MMA issue when it was the last one in -- before it touches item i+1.
-                __threadfence_block();
-                const uint32_t old = atomicAdd(&fill_cnt[s], 1u);
-                if (old == P2_PROD_WARPS - 1) {
-                    __threadfence_block();
-                    fill_cnt[s] = 0;                                     // nobody counts on this stage again before empty[s] fires
-                    const int acc = (int)(tcount & 1u);
-                    if (pr.c == 0) mbar_wait_b(&tempty[acc], ((tcount >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator
-                    if (p.resident) mbar_wait_b(wres_bar, 0u);
-                    else mbar_wait_b(&full[s], ph);                      // this chunk's weight block landed
-                    tc_fence_after();
-                    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7, 10),
-                    // both K-major (bits 15,16 = 0), N >> 3 @ bit 17, M >> 4 @ bit 24
-                    const uint32_t idesc =
-                        (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NTp >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-                    const uint32_t d_tmem = tmem + (uint32_t)(acc * p.acc_stride);
-                    const uint32_t a_hi_s = smem_u32(stage), a_lo_s = a_hi_s + TC_BM * TC_KC * 4;
-                    const uint32_t b_hi_s = p.resident ? smem_u32(wres + (size_t)pr.c * p.b_chunk_bytes) : a_hi_s + P2_A_STAGE;
-                    const uint32_t b_lo_s = b_hi_s + (uint32_t)p.NTp * 128u;
-                    const int nk8 = min(4, (a.K - pr.c * TC_KC + 7) >> 3);
-                    for (int k8 = 0; k8 < nk8; ++k8) {
-                        const uint32_t ko = (uint32_t)k8 * 32u;          // 8 tf32 = 32 bytes along K inside the swizzle row
-                        umma_tf32(d_tmem, make_desc_sw128(a_lo_s + ko), make_desc_sw128(b_hi_s + ko), idesc, (uint32_t)((pr.c | k8) != 0));
-                        umma_tf32(d_tmem, make_desc_sw128(a_hi_s + ko), make_desc_sw128(b_lo_s + ko), idesc, 1u);
-                        umma_tf32(d_tmem, make_desc_sw128(a_hi_s + ko), make_desc_sw128(b_hi_s + ko), idesc, 1u);
-                    }
-                    umma_commit(&empty[s]);                              // stage reusable once these MMAs retire
-                    if (pr.c == p.nchunks - 1) umma_commit(&tfull[acc]); // accumulator complete
-                }
-            }
-            __syncwarp();
+            P2_ACC(3, tt);                                   // 3: proxy fence + warp sync
+            if (lane == 0) mbar_arrive(&full[s]);
+            P2_ACC(4, tt);                                   // 4: arrive
             if (++s == p.nstages) { s = 0; ph ^= 1u; }
-            if (pr.c == p.nchunks - 1) ++tcount;
             p2_advance(pr, p);
         }
+    }
+    if (p.timing && blockIdx.x == 0 && tid == 0) {
+        for (int i = 0; i < 5; ++i) p2_dbg[i] = tacc[i];
+        p2_dbg[7] = clock64() - tstart;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// MMA issuer: one warp runs the loop convergently (descriptor arithmetic stays warp-uniform), one elected lane issues.
+// Issuing from a divergent `if (lane == 0)` inside a producer warp measured ~70 cycles per tcgen05.mma (per-lane
+// descriptor math moved to uniform registers one MMA at a time) and made that warp the pipeline's slowest stage.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool p2_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void p2_mma_warp(const cf_pw_args& a, const P2Params& p, uint8_t* stages, uint8_t* wres, uint64_t* full,
+                                            uint64_t* empty, uint64_t* tfull, uint64_t* tempty, uint64_t* wres_bar, uint32_t tmem) {
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7, 10),
+    // both K-major (bits 15,16 = 0), N >> 3 @ bit 17, M >> 4 @ bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NTp >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint64_t lo_off = (uint64_t)((TC_BM * TC_KC * 4) >> 4);          // A lo tile follows A hi (descriptor address units: 16 B)
+    const uint64_t blo_off = (uint64_t)(((uint32_t)p.NTp * 128u) >> 4);    // B lo tile follows B hi
+    const uint64_t stages_desc = make_desc_sw128(smem_u32(stages));
+    const uint64_t wres_desc = make_desc_sw128(smem_u32(wres));
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tt = P2_T0();
+    const long long tstart = tt;
+    if (p.resident) mbar_wait_b(wres_bar, 0u);
+    int s = 0;
+    uint32_t ph = 0, tcount = 0;
+    P2Item it;
+    for (p2_first(it, p); it.valid; p2_next_tile(it, p), ++tcount) {
+        const int acc = (int)(tcount & 1u);
+        P2_ACC(0, tt);
+        mbar_wait_b(&tempty[acc], ((tcount >> 1) & 1u) ^ 1u);             // the epilogue drained this accumulator
+        P2_ACC(1, tt);                                                     // 1: wait for the accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)(acc * p.acc_stride);
+        for (int c = 0; c < p.nchunks; ++c) {
+            mbar_wait_b(&full[s], ph);                                     // producers (and the weight block) filled this stage
+            P2_ACC(2, tt);                                                 // 2: wait for a full stage
+            tc_fence_after();
+            const uint64_t a_hi = stages_desc + (uint64_t)(((uint32_t)s * p.stage_bytes) >> 4);
+            const uint64_t a_lo = a_hi + lo_off;
+            const uint64_t b_hi = p.resident ? wres_desc + (uint64_t)(((uint32_t)c * p.b_chunk_bytes) >> 4) : a_hi + (uint64_t)(P2_A_STAGE >> 4);
+            const uint64_t b_lo = b_hi + blo_off;
+            const int nk8 = min(4, (a.K - c * TC_KC + 7) >> 3);
+            if (p2_elect_one()) {
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8) {
+                    if (k8 < nk8) {
+                        const uint64_t ko = (uint64_t)(k8 * 2);            // 8 tf32 = 32 bytes along K inside the swizzle row
+                        if (!p.dbg_1x) {
+                            umma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, (uint32_t)((c | k8) != 0));
+                            umma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                        } else {                                           // debug: single-pass TF32 (wrong results, timing only)
+                            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, (uint32_t)((c | k8) != 0));
+                        }
+                    }
+                }
+                umma_commit(&empty[s]);                                    // stage reusable once these MMAs retire
+                if (c == p.nchunks - 1) umma_commit(&tfull[acc]);          // accumulator complete
+            }
+            __syncwarp();
+            P2_ACC(3, tt);                                                 // 3: issue + commits
+            if (++s == p.nstages) { s = 0; ph ^= 1u; }
+        }
+    }
+    if (p.timing && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+        for (int i = 0; i < 4; ++i) p2_dbg[16 + i] = tacc[i];
+        p2_dbg[20] = clock64() - tstart;
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // epilogue: one 32-column slab, shared tile -> global (coalesced along N)
 // ---------------------------------------------------------------------------------------
-template <int EV, int EPI>
-__device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const float* __restrict__ Cs, float* red, int b, int r0,
-                                              int rows_valid, int R, int n0, int col0, int nvalid, int gt) {
+#define P2_SCR_FLOATS (16 * 32 * 2)          /* per group: [rows per pass <= 16][32 columns][2 statistics] */
+
+// packed fp32x2 arithmetic (sm_100 FADD2 / FFMA2): halves the issue slots of the bias add and the statistics
+__device__ __forceinline__ void p2_add2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void p2_fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(c0), "+f"(c1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// FULL: all 128 rows of the tile are valid (every tile but the last one of a sample): no per-pass row checks
+template <int EV, int EPI, int SMODE, bool FULL>
+__device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const float* __restrict__ cp, float* __restrict__ dp,
+                                              const float* __restrict__ ap, size_t gstep, int rs, int rows_valid, const float* bi,
+                                              const float* ea, const float* eb, bool has_bias, float* s1, float* s2) {
+    constexpr int CPR = 32 / EV, RPP = 128 / CPR, NPASS = TC_BM / RPP;
+    constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX;
+    constexpr bool NEED_AUX = EPI_AUX || SMODE == CF_STATS_SUM_AUX;
+    float ax[NEED_AUX ? NPASS : 1][EV];
+    if (NEED_AUX) {
+#pragma unroll
+        for (int i = 0; i < NPASS; ++i, ap += gstep) {
+            if (FULL || rs + i * RPP < rows_valid) P2Vec<EV>::ld(ap, ax[NEED_AUX ? i : 0]);
+            else {
+#pragma unroll
+                for (int e = 0; e < EV; ++e) ax[NEED_AUX ? i : 0][e] = 0.f;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPASS; ++i, dp += gstep, cp += RPP * P2_CS_LD) {
+        if (!FULL && rs + i * RPP >= rows_valid) break;
+        float vv[EV];
+        P2Vec<EV>::ldrw(cp, vv);
+        if (has_bias) {
+#pragma unroll
+            for (int e = 0; e < EV; e += 2) p2_add2(vv[e], vv[e + 1], bi[e], bi[e + 1]);
+        }
+        const float* axe = ax[NEED_AUX ? i : 0];
+#pragma unroll
+        for (int e = 0; e < EV; ++e) {
+            float t = vv[e];
+            if (EPI == CF_EPI_RELU) t = fmaxf(t, 0.f);
+            else if (EPI == CF_EPI_DRELU) t = (fmaf(ea[e], axe[e], eb[e]) > 0.f) ? t : 0.f;
+            else if (EPI == CF_EPI_DSWISH) t *= p2_dswish(fmaf(ea[e], axe[e], eb[e]));
+            else if (EPI == CF_EPI_ADD_AUX) t += axe[e];
+            else if (EPI == CF_EPI_SIGMOID) t = p2_sigmoid(t);
+            vv[e] = t;
+        }
+        if (SMODE != CF_STATS_NONE) {
+#pragma unroll
+            for (int e = 0; e < EV; e += 2) {
+                p2_add2(s1[e], s1[e + 1], vv[e], vv[e + 1]);
+                if (SMODE == CF_STATS_SUM_AUX) p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], axe[e], axe[e + 1]);
+                else p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], vv[e], vv[e + 1]);
+            }
+        }
+        P2Vec<EV>::st(dp, vv);
+    }
+}
+
+template <int EV, int EPI, int SMODE>
+__device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const float* __restrict__ Cs, float* __restrict__ scr, int b,
+                                              int r0, int rows_valid, int R, int n0, int col0, int nvalid, int gt) {
     constexpr int CPR = 32 / EV;             // column groups per row
     constexpr int RPP = 128 / CPR;           // rows per pass
-    constexpr int NPASS = TC_BM / RPP;
     const int N = a.N;
     const int cg = gt % CPR, rs = gt / CPR;
     const int nl = col0 + cg * EV;           // column within the channel tile
-    if (nl >= nvalid) return;
-    const int n = n0 + nl;
-    const int smode = a.stats_mode;
-    constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX;
-    const bool need_aux = EPI_AUX || smode == CF_STATS_SUM_AUX;
-    float bi[EV], ea[EV], eb[EV], s1[EV], s2[EV];
+    const bool active = nl < nvalid;         // nvalid and nl are multiples of EV: a column group is all-valid or all-padding
+    float s1[EV], s2[EV];
 #pragma unroll
-    for (int e = 0; e < EV; ++e) {
-        const bool nv = nl + e < nvalid;
-        bi[e] = (nv && a.bias) ? a.bias[n + e] : 0.f;
-        ea[e] = (nv && a.epi_a) ? a.epi_a[(size_t)b * N + n + e] : 1.f;
-        eb[e] = (nv && a.epi_b) ? a.epi_b[(size_t)b * N + n + e] : 0.f;
-        s1[e] = 0.f;
-        s2[e] = 0.f;
-    }
-    const size_t gbase = ((size_t)b * R + r0) * N + n;
-    float ax[NPASS][EV];
-    if (need_aux) {
-#pragma unroll
-        for (int i = 0; i < NPASS; ++i) {
-            const int r = rs + i * RPP;
-            if (r < rows_valid) P2Vec<EV>::ld(a.aux + gbase + (size_t)r * N, ax[i]);
-            else {
-#pragma unroll
-                for (int e = 0; e < EV; ++e) ax[i][e] = 0.f;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NPASS; ++i) {
-        const int r = rs + i * RPP;
-        if (r >= rows_valid) break;
-        float vv[EV];
-        P2Vec<EV>::ldrw(Cs + r * P2_CS_LD + cg * EV, vv);
+    for (int e = 0; e < EV; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+    if (active) {
+        const int n = n0 + nl;
+        float bi[EV], ea[EV], eb[EV];
 #pragma unroll
         for (int e = 0; e < EV; ++e) {
-            float t = vv[e] + bi[e];
-            const float axe = need_aux ? ax[i][e] : 0.f;
-            if (EPI == CF_EPI_RELU) t = fmaxf(t, 0.f);
-            else if (EPI == CF_EPI_DRELU) t = (fmaf(ea[e], axe, eb[e]) > 0.f) ? t : 0.f;
-            else if (EPI == CF_EPI_DSWISH) t *= p2_dswish(fmaf(ea[e], axe, eb[e]));
-            else if (EPI == CF_EPI_ADD_AUX) t += axe;
-            else if (EPI == CF_EPI_SIGMOID) t = p2_sigmoid(t);
-            vv[e] = t;
-            s1[e] += t;
-            s2[e] += (smode == CF_STATS_SUM_AUX) ? t * axe : t * t;
+            bi[e] = a.bias ? a.bias[n + e] : 0.f;
+            ea[e] = (EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH) ? a.epi_a[(size_t)b * N + n + e] : 1.f;
+            eb[e] = (EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH) ? a.epi_b[(size_t)b * N + n + e] : 0.f;
         }
-        float* dst = a.y + gbase + (size_t)r * N;
-        if (a.accumulate) {
-            float old[EV];
-            P2Vec<EV>::ldrw(dst, old);
-#pragma unroll
-            for (int e = 0; e < EV; ++e) vv[e] += old[e];
-        }
-        P2Vec<EV>::st(dst, vv);
+        const size_t g0 = ((size_t)b * R + r0 + rs) * N + n;
+        const size_t gstep = (size_t)RPP * N;
+        const float* cp = Cs + rs * P2_CS_LD + cg * EV;
+        const float* ap = a.aux ? a.aux + g0 : nullptr;
+        if (rows_valid == TC_BM)
+            p2_store_rows<EV, EPI, SMODE, true>(a, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
+        else
+            p2_store_rows<EV, EPI, SMODE, false>(a, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
     }
-    if (smode != CF_STATS_NONE) {
+    if (SMODE != CF_STATS_NONE) {            // partial column sums of this thread's rows; reduced after the group barrier
 #pragma unroll
-        for (int e = 0; e < EV; ++e)
-            if (nl + e < nvalid) {
-                atomicAdd(red + n + e, s1[e]);
-                atomicAdd(red + P2_RED_N + n + e, s2[e]);
-            }
+        for (int e = 0; e < EV; ++e) {
+            scr[(rs * 32 + cg * EV + e) * 2] = s1[e];
+            scr[(rs * 32 + cg * EV + e) * 2 + 1] = s2[e];
+        }
     }
 }
 
@@ -372,23 +470,27 @@ __device__ __forceinline__ void p2_flush_stats(const cf_pw_args& a, float* red, 
     named_bar_sync(4, P2_EPI_THREADS);
 }
 
-template <int EV, int EPI>
-__device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params& p, float* Cs_all, float* red, uint64_t* tfull,
-                                            uint64_t* tempty, uint32_t tmem, int warp, int lane) {
-    const int ew = warp - P2_PROD_WARPS;
+template <int EV, int EPI, int SMODE>
+__device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params& p, float* Cs_all, float* scr_all, float* red,
+                                            uint64_t* tfull, uint64_t* tempty, uint32_t tmem, int warp, int lane) {
+    constexpr int RPP = 128 / (32 / EV);
+    const int ew = warp - P2_EPI_WARP0;
     const int grp = ew >> 2;
     const int qd = warp & 3;                                 // TMEM lane quadrant this warp may read
     const int gt = (ew & 3) * 32 + lane;                     // thread index within the group (phase 2)
     const int et = ew * 32 + lane;
     float* Cs = Cs_all + grp * P2_CS_FLOATS;
+    float* scr = scr_all + grp * P2_SCR_FLOATS;
     const int row_own = qd * 32 + lane;
     const int nslabs = (p.NTp + 31) >> 5;
-    const bool do_stats = a.stats_mode != CF_STATS_NONE;
     int cur_b = -1;
     uint32_t tcount = 0;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tt = P2_T0();
+    const long long tstart = tt;
     P2Item it;
     for (p2_first(it, p); it.valid; p2_next_tile(it, p), ++tcount) {
-        if (do_stats && it.b != cur_b) {
+        if (SMODE != CF_STATS_NONE && it.b != cur_b) {
             if (cur_b >= 0) p2_flush_stats(a, red, cur_b, et);
             cur_b = it.b;
         }
@@ -397,7 +499,9 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
         const int rows_valid = min(TC_BM, p.R - it.r0);
         const int n0 = it.j * p.NT;
         const int nvalid = min(p.NT, a.N - n0);
+        P2_ACC(0, tt);                                       // 0: tile bookkeeping (+ statistics flush)
         mbar_wait_b(&tfull[acc], aph);
+        P2_ACC(1, tt);                                       // 1: wait for the accumulator
         tc_fence_after();
         const uint32_t tbase = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * p.acc_stride);
         for (int slab = grp; slab < nslabs; slab += 2) {
@@ -408,13 +512,34 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
             }
-            named_bar_sync(2 + grp, 128);                    // the previous slab's readers are done with Cs
+            P2_ACC(2, tt);                                   // 2: tcgen05.ld + release
+            named_bar_sync(2 + grp, 128);                    // the previous slab's readers are done with Cs and scr
+            P2_ACC(3, tt);                                   // 3: group barriers
             float* dst = Cs + row_own * P2_CS_LD;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(r32[4 * i], r32[4 * i + 1], r32[4 * i + 2], r32[4 * i + 3]);
+            P2_ACC(4, tt);                                   // 4: accumulator rows -> shared slab
             named_bar_sync(2 + grp, 128);
-            p2_store_slab<EV, EPI>(a, Cs, red, it.b, it.r0, rows_valid, p.R, n0, slab * 32, nvalid, gt);
+            P2_ACC(3, tt);
+            p2_store_slab<EV, EPI, SMODE>(a, Cs, scr, it.b, it.r0, rows_valid, p.R, n0, slab * 32, nvalid, gt);
+            P2_ACC(5, tt);                                   // 5: slab -> global (+ aux, activation, statistics partials)
+            if (SMODE != CF_STATS_NONE) {
+                // column sums over the rows-per-pass partials: one owner thread per (column, statistic) -- a slab belongs
+                // to exactly one group, so the per-CTA table needs no atomics (shared fp32 atomics are CAS loops)
+                named_bar_sync(2 + grp, 128);
+                P2_ACC(3, tt);
+                if (gt < 64) {
+                    const int col = gt >> 1, st = gt & 1;
+                    if (slab * 32 + col < nvalid) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int r = 0; r < RPP; ++r) sum += scr[(r * 32 + col) * 2 + st];
+                        red[st * P2_RED_N + n0 + slab * 32 + col] += sum;
+                    }
+                }
+                P2_ACC(6, tt);                               // 6: statistics reduction
+            }
         }
         if (grp >= nslabs) {                                 // a group without slabs still releases the accumulator
             tc_fence_before();
@@ -422,7 +547,11 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
     }
-    if (do_stats && cur_b >= 0) p2_flush_stats(a, red, cur_b, et);
+    if (SMODE != CF_STATS_NONE && cur_b >= 0) p2_flush_stats(a, red, cur_b, et);
+    if (p.timing && blockIdx.x == 0 && et == 0) {
+        for (int i = 0; i < 7; ++i) p2_dbg[8 + i] = tacc[i];
+        p2_dbg[15] = clock64() - tstart;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -437,14 +566,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
     __shared__ __align__(8) uint64_t tempty[2];
     __shared__ __align__(8) uint64_t wres_bar;
     __shared__ uint32_t tmem_addr_s;
-    __shared__ uint32_t fill_cnt[P2_MAX_STAGES];
     __shared__ float red[2 * P2_RED_N];
 
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B tiles: 1024-B aligned
     uint8_t* stages = base;
     uint8_t* wres = stages + (size_t)p.nstages * p.stage_bytes;
     float* Cs = reinterpret_cast<float*>(wres + (p.resident ? (size_t)p.nchunks * p.b_chunk_bytes : 0));
-    float* tab = Cs + 2 * P2_CS_FLOATS;
+    float* scr = Cs + 2 * P2_CS_FLOATS;
+    float* tab = scr + 2 * P2_SCR_FLOATS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -454,8 +583,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
     }
     if (tid == 0) {
         for (int s = 0; s < p.nstages; ++s) {
-            mbar_init(&full[s], 1);                          // streamed weight block (expect_tx arrival)
-            fill_cnt[s] = 0;
+            mbar_init(&full[s], P2_PROD_WARPS + (p.resident ? 0 : 1));   // + the streamed weight block's expect_tx arrival
             mbar_init(&empty[s], 1);
         }
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
@@ -470,8 +598,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
     const uint32_t tmem = tmem_addr_s;
 
     if (warp < P2_PROD_WARPS) {
-        // ================= producers (+ MMA issue by the warp that completes a stage) =================
-#define P2_PARGS a, p, stages, wres, tab, full, empty, tfull, tempty, &wres_bar, fill_cnt, tmem, pack, tid
+        // ================= producers =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_REGS_PROD));
+#define P2_PARGS a, p, stages, tab, full, empty, pack, tid
         if (p.resident && tid == 0) {
             mbar_expect_tx(&wres_bar, (uint32_t)p.nchunks * p.b_chunk_bytes);
             for (int c = 0; c < p.nchunks; ++c)
@@ -485,22 +614,36 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
         case CF_PRO_AFFINE2: p2_producer<AV_, CF_PRO_AFFINE2>(P2_PARGS); break;  \
         default: p2_producer<AV_, CF_PRO_NONE>(P2_PARGS); break;                 \
     }
-        if (av == 4) { P2_PROD(4) } else if (av == 2) { P2_PROD(2) } else { P2_PROD(1) }
+        if (av == 4) { P2_PROD(4) } else { P2_PROD(2) }
 #undef P2_PROD
 #undef P2_PARGS
+    } else if (warp < P2_EPI_WARP0) {
+        // ================= MMA issuer (first warp of its warpgroup; the other three only give up their registers) =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_REGS_MMA));
+        if (warp == P2_MMA_WARP) p2_mma_warp(a, p, stages, wres, full, empty, tfull, tempty, &wres_bar, tmem);
     } else {
         // ================= epilogue =================
-#define P2_EPI(EV_)                                                                                                    \
-    switch (a.epi_mode) {                                                                                              \
-        case CF_EPI_RELU: p2_epilogue<EV_, CF_EPI_RELU>(a, p, Cs, red, tfull, tempty, tmem, warp, lane); break;        \
-        case CF_EPI_DRELU: p2_epilogue<EV_, CF_EPI_DRELU>(a, p, Cs, red, tfull, tempty, tmem, warp, lane); break;      \
-        case CF_EPI_DSWISH: p2_epilogue<EV_, CF_EPI_DSWISH>(a, p, Cs, red, tfull, tempty, tmem, warp, lane); break;    \
-        case CF_EPI_ADD_AUX: p2_epilogue<EV_, CF_EPI_ADD_AUX>(a, p, Cs, red, tfull, tempty, tmem, warp, lane); break;  \
-        case CF_EPI_SIGMOID: p2_epilogue<EV_, CF_EPI_SIGMOID>(a, p, Cs, red, tfull, tempty, tmem, warp, lane); break;  \
-        default: p2_epilogue<EV_, CF_EPI_NONE>(a, p, Cs, red, tfull, tempty, tmem, warp, lane); break;                 \
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_REGS_EPI));
+#define P2_EARGS a, p, Cs, scr, red, tfull, tempty, tmem, warp, lane
+#define P2_EPI_S(EV_, EPI_)                                                                  \
+    switch (a.stats_mode) {                                                                  \
+        case CF_STATS_SUM_SQ: p2_epilogue<EV_, EPI_, CF_STATS_SUM_SQ>(P2_EARGS); break;      \
+        case CF_STATS_SUM_AUX: p2_epilogue<EV_, EPI_, CF_STATS_SUM_AUX>(P2_EARGS); break;    \
+        default: p2_epilogue<EV_, EPI_, CF_STATS_NONE>(P2_EARGS); break;                     \
     }
-        if (ev == 4) { P2_EPI(4) } else if (ev == 2) { P2_EPI(2) } else { P2_EPI(1) }
+#define P2_EPI(EV_)                                                      \
+    switch (a.epi_mode) {                                                \
+        case CF_EPI_RELU: P2_EPI_S(EV_, CF_EPI_RELU) break;              \
+        case CF_EPI_DRELU: P2_EPI_S(EV_, CF_EPI_DRELU) break;            \
+        case CF_EPI_DSWISH: P2_EPI_S(EV_, CF_EPI_DSWISH) break;          \
+        case CF_EPI_ADD_AUX: P2_EPI_S(EV_, CF_EPI_ADD_AUX) break;        \
+        case CF_EPI_SIGMOID: P2_EPI_S(EV_, CF_EPI_SIGMOID) break;        \
+        default: P2_EPI_S(EV_, CF_EPI_NONE) break;                       \
+    }
+        if (ev == 4) { P2_EPI(4) } else { P2_EPI(2) }
 #undef P2_EPI
+#undef P2_EPI_S
+#undef P2_EARGS
     }
     tc_fence_before();
     __syncthreads();
@@ -559,6 +702,23 @@ static int p2_sm_count() {
     return n;
 }
 
+static int p2_timing() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CFNET_PW_TC_TIMING");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
+// debug: cycle counters of CTA 0 of the last persistent launch run with CFNET_PW_TC_TIMING=1 (16 values; see P2_ACC slots)
+extern "C" int cf_pw_tc_debug_read(long long* out16) {
+    long long zero[32] = {0};
+    if (cudaMemcpyFromSymbol(out16, p2_dbg, 24 * sizeof(long long)) != cudaSuccess) return CF_ERR_CUDA;
+    cudaMemcpyToSymbol(p2_dbg, zero, sizeof(zero));
+    return CF_OK;
+}
+
 static bool p2_use_v1() {
     static int v = -1;
     if (v < 0) {
@@ -581,7 +741,13 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(p.total_tiles < (1LL << 31), "too many tiles");
     CF_CHECK_ARG(a->wpack_bytes >= (int64_t)cf_pw_tc_ws_bytes(K, N), "weight-pack workspace too small");
     CF_CHECK_ARG((((uintptr_t)a->wpack) & 127) == 0, "weight-pack workspace must be 128-byte aligned");
-    if (a->stats_mode != CF_STATS_NONE && N > P2_RED_N) return cf_pw_conv_tc_v1(a, stream);   // per-CTA statistics table holds 512 channels
+    // rare shapes stay on the one-tile-per-CTA kernel: odd channel counts (the 157-class head), in-place accumulation
+    // (only the scattered CUDA-core path of the strided convs uses it), statistics over more than 512 channels
+    uintptr_t xa = (uintptr_t)a->x | (uintptr_t)(a->x2 ? a->x2 : a->x);
+    int av = ((K & 3) == 0 && (xa & 15) == 0) ? 4 : (((K & 1) == 0 && (xa & 7) == 0) ? 2 : 1);
+    uintptr_t ya = (uintptr_t)a->y | (uintptr_t)(a->aux ? a->aux : a->y);
+    int ev = ((N & 3) == 0 && (ya & 15) == 0) ? 4 : (((N & 1) == 0 && (ya & 7) == 0) ? 2 : 1);
+    if (av == 1 || ev == 1 || a->accumulate || (a->stats_mode != CF_STATS_NONE && N > P2_RED_N)) return cf_pw_conv_tc_v1(a, stream);
     // shared-memory plan: weights resident next to >= 3 A stages, else streamed with each stage; if even two stages
     // of the widest channel tile do not fit (very long K: big prologue tables), narrow the channel tile
     size_t smem = 0;
@@ -592,7 +758,7 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
             p2_tiling(K, N, p, nt_try[ti]);
             p.total_tiles = (long long)a->B * p.tps * p.ntiles;
         }
-        const size_t fixed = 1024 + 2 * (size_t)P2_CS_FLOATS * 4 + 3 * (size_t)p.KP * 4;
+        const size_t fixed = 1024 + 2 * (size_t)(P2_CS_FLOATS + P2_SCR_FLOATS) * 4 + 3 * (size_t)p.KP * 4;
         if (fixed + 2 * (size_t)P2_A_STAGE >= P2_SMEM_MAX) break;
         const size_t avail = P2_SMEM_MAX - fixed;
         const size_t wres_bytes = (size_t)p.nchunks * p.b_chunk_bytes;
@@ -620,10 +786,6 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < 2 * p.acc_stride) p.tmem_cols <<= 1;
     cf_pw_tc_pack_launch(a->w, a->w_sn, a->w_sk, a->wpack, K, N, p.NT, p.NTp, p.ntiles, p.nchunks, stream);
-    uintptr_t xa = (uintptr_t)a->x | (uintptr_t)(a->x2 ? a->x2 : a->x);
-    int av = ((K & 3) == 0 && (xa & 15) == 0) ? 4 : (((K & 1) == 0 && (xa & 7) == 0) ? 2 : 1);
-    uintptr_t ya = (uintptr_t)a->y | (uintptr_t)(a->aux ? a->aux : a->y);
-    int ev = ((N & 3) == 0 && (ya & 15) == 0) ? 4 : (((N & 1) == 0 && (ya & 7) == 0) ? 2 : 1);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
@@ -634,6 +796,12 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
         attr_done = true;
     }
     long long grid = p.total_tiles < p2_sm_count() ? p.total_tiles : p2_sm_count();
+    p.timing = p2_timing();
+    {
+        static int one = -1;
+        if (one < 0) { const char* e = getenv("CFNET_PW_TC_1X"); one = (e && e[0] == '1') ? 1 : 0; }
+        p.dbg_1x = one;
+    }
     p.g_j = (int)(grid % p.ntiles);
     p.g_rt = (int)(grid / p.ntiles);
     pw_tc2_kernel<<<(unsigned)grid, P2_THREADS, smem, stream>>>(*a, a->wpack, p, av, ev);

@@ -162,6 +162,8 @@ typedef struct {
 int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream);
 /* bytes of the packed (hi/lo split, swizzled) weight workspace of the tensor-core path */
 size_t cf_pw_tc_ws_bytes(int K, int N);
+/* debug: per-role cycle counters of CTA 0 of the last tensor-core launch made with CFNET_PW_TC_TIMING=1 (24 values) */
+int cf_pw_tc_debug_read(long long* out16);
 
 /* weight gradient:
  *   dw[n*K + k] += sum_{b,r} pro_dy(dy[b,r,n], dy2[b,r,n]) * pro_x(x[b, gather(r,k)]);

@@ -79,5 +79,17 @@ for name, K, N, T, H, W, pro, epi, smode in CASES:
     ms = timeit(fn)
     rows = B * T * H * W
     byt = rows * 4 * (K * (2 if x2 is not None else 1) + N * (2 if aux is not None else 1))
+    if os.environ.get("CFNET_PW_TC_TIMING") == "1":
+        import ctypes
+        from coarse_fine_networks_b200 import _lib
+        buf = (ctypes.c_longlong * 24)()
+        _lib.lib.cf_pw_tc_debug_read(buf)          # discard the accumulated launches, then time exactly one
+        fn()
+        torch.cuda.synchronize()
+        _lib.lib.cf_pw_tc_debug_read(buf)
+        v = list(buf)
+        print("   producer thread 0  [loads, wait-stage, transform+store, fence, arrive] =", v[0:5], "total", v[7])
+        print("   mma warp           [bookkeeping, wait-acc, wait-stage, issue+commit] =", v[16:20], "total", v[20])
+        print("   epilogue thread 0  [bookkeeping, wait-acc, tmem-ld, barriers, sts, store-slab, stats-reduce] =", v[8:15], "total", v[15])
     print(f"{name:38s} rows {rows:9d}  {ms*1e3:9.1f} us  {byt/ms/1e6:8.1f} GB/s  {100*byt/ms/1e6/peak:5.1f}% of measured HBM peak")
     del x, x2, y, aux
