@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const cf_pw_wgrad_args a,
 }
 
 // ---------------------------------------------------------------------------------------
-int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream);      // x3d_pw_tc.cu
+int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream);      // x3d_pw_tc2.cu
+int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream);   // x3d_pw_wgrad_tc.cu (-1: not eligible)
 
 extern "C" size_t cf_sizeof_pw_args(void) { return sizeof(cf_pw_args); }
 size_t cf_sizeof_pw_wgrad_args(void) { return sizeof(cf_pw_wgrad_args); }
@@ -390,6 +391,10 @@ extern "C" int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a->x_mode == CF_PRO_NONE || a->x_a, "x tables missing");
     int taps = a->g.kt * a->g.kh * a->g.kw;
     CF_CHECK_ARG(!a->gather_in || a->K % taps == 0, "K must be channels*taps");
+    {
+        int rc = cf_pw_wgrad_tc(a, stream);                 // dense problems: tensor cores
+        if (rc >= 0) return rc;
+    }
     int R = a->g.T * a->g.H * a->g.W;
     int nt = cf_cdiv(a->N, WG_T), kt = cf_cdiv(a->K, WG_T);
     int want = cf_cdiv(148 * 3, nt * kt * a->B);

@@ -1,0 +1,391 @@
+// Weight gradient of the pointwise convs on the tcgen05 tensor cores (sm_100a), persistent and warp-specialised.
+//
+//   dw[n,k] += sum_{b,r} pro_dy(dy[b,r,n], dy2[b,r,n]) * pro_x(x[b,r,k])          (x3d_fine.py:100-105 backward)
+//
+// The reduction runs over ROWS (millions of them) and the result is a tiny [N,K] matrix: a tall-skinny "transposed"
+// GEMM.  The CUDA-core kernel it replaces (pw_wgrad_kernel, x3d_pw.cu) took 28 % of the training step.  Here both
+// operands are MN-major for the tensor core: a block of RB rows of dy (resp. x) is stored as [row][32 channels] =
+// 128-byte rows (32-byte-unit swizzle) and read by tcgen05.mma as A = dy^T
+// (M = dy channels, K = rows) and B = x (N = x channels), 8 rows per instruction, 3xTF32 (hi/lo split, fp32
+// accumulation in TMEM).  One CTA per SM walks a contiguous range of row blocks and keeps its [N,K] partial in TMEM
+// for the whole launch; at the end the partials are added to dw with fp32 atomics (148 x N x K per launch).
+//
+//   warps 0-15  producers: batches of 4 (tensor, 32-channel chunk) units per thread: loads issued first, then the
+//               BatchNorm-backward / Swish prologue, the hi/lo split and the swizzled stores into a ring of stages;
+//   warp  16    MMA issuer (convergent loop, one elected lane issues); commits stage-free barriers;
+//   all warps   final TMEM -> global atomics.
+// Problems whose [N,K] partial exceeds the 512 TMEM columns are split over blockIdx.y (dy channel tiles or x channel
+// halves).  Strided / windowed inputs, bias gradients, odd channel counts and N or K > 512 stay on the CUDA-core kernel.
+#include "cf_common.cuh"
+#include "../../include/cfnet_b200.h"
+#include "tc_ptx.cuh"
+#include <stdlib.h>
+
+#define WG_PROD_WARPS 16
+#define WG_PROD_THREADS (WG_PROD_WARPS * 32)
+#define WG_THREADS (WG_PROD_THREADS + 32)
+#define WG_MAX_STAGES 4
+#define WG_UB 4                                  /* units per batch (loads in flight per thread) */
+#define WG_SMEM_MAX (220 * 1024)
+
+struct WgParams {
+    int B, R, N, K;                              // N = dy channels, K = x channels
+    int RB, rbps, nstages;                       // rows per stage, row blocks per sample
+    int nchA, nchA_pad, nchB;                    // real / padded dy chunks and x chunks of ONE CTA
+    int mt_per, npad_per;                        // dy channel tiles (128) and padded x channels of one CTA
+    int msplit, nsplit;                          // blockIdx.y = ms * nsplit + ns
+    int items_per_cta;
+    long long total_items;
+    uint32_t chunk_bytes, stage_bytes, tmem_cols;
+    int av_dy, av_x;
+};
+
+// MN-major descriptor.  32-bit (tf32) MN-major operands only exist in the SWIZZLE_128B_BASE32B layout (layout type 1;
+// cute::UMMA::Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over [4 rows][128 B]): rows of 32 channels are 128 B apart, the
+// four 32-byte units of a row are XORed with (row & 3), the pattern repeats every 4 rows (512 B).  LBO = stride between
+// 32-channel blocks, SBO = stride between 4-row groups.
+__device__ __forceinline__ uint64_t wg_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+           (1ull << 61);
+}
+// byte offset of (row, 16-byte chunk q8) inside a [rows][32 floats] chunk in that layout
+__device__ __forceinline__ uint32_t wg_sw_off(int row, int q8) {
+    return (uint32_t)(row * 128 + ((((q8 >> 1) ^ (row & 3)) << 5) | ((q8 & 1) << 4)));
+}
+__device__ __forceinline__ bool wg_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ float wg_sigmoid(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+__device__ __forceinline__ float wg_pro(int mode, float x, float x2, float a, float b, float c) {
+    switch (mode) {
+        case CF_PRO_AFFINE: return fmaf(a, x, b);
+        case CF_PRO_AFFINE_RELU: return fmaxf(fmaf(a, x, b), 0.f);
+        case CF_PRO_AFFINE_SWISH: { float z = fmaf(a, x, b); return z * wg_sigmoid(z); }
+        case CF_PRO_AFFINE2: return fmaf(a, x, fmaf(b, x2, c));
+        default: return x;
+    }
+}
+// 4 floats at p (channel c .. c+3 of a row with C channels), zero beyond C; AV = 4 or 2
+__device__ __forceinline__ void wg_ld4(const float* p, int c, int C, int av, float* v) {
+    if (av == 4) {
+        if (c < C) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(p));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+            v[0] = v[1] = v[2] = v[3] = 0.f;
+        }
+    } else {
+        if (c < C) {
+            float2 t = __ldg(reinterpret_cast<const float2*>(p));
+            v[0] = t.x; v[1] = t.y;
+        } else {
+            v[0] = v[1] = 0.f;
+        }
+        if (c + 2 < C) {
+            float2 t = __ldg(reinterpret_cast<const float2*>(p + 2));
+            v[2] = t.x; v[3] = t.y;
+        } else {
+            v[2] = v[3] = 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_wgrad_args a, const WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full[WG_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty[WG_MAX_STAGES];
+    __shared__ __align__(8) uint64_t done_bar;
+    __shared__ uint32_t tmem_addr_s;
+
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stages = base;
+    float* tabA = reinterpret_cast<float*>(stages + (size_t)p.nstages * p.stage_bytes);      // [3][nchA*32]
+    float* tabB = tabA + 3 * p.nchA * 32;                                                      // [2][nchB*32]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ms = blockIdx.y / p.nsplit, ns = blockIdx.y - ms * p.nsplit;
+    const int n_base = ms * p.mt_per * 128;                  // first dy channel of this CTA
+    const int k_base = ns * p.npad_per;                      // first x channel of this CTA
+    const long long item0 = (long long)blockIdx.x * p.items_per_cta;
+    const long long item1 = min(item0 + p.items_per_cta, p.total_items);
+
+    if (warp == WG_PROD_WARPS) {
+        tmem_alloc(&tmem_addr_s, p.tmem_cols);
+        tmem_relinquish();
+    }
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(&full[s], WG_PROD_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&done_bar, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_addr_s;
+    const uint32_t a_lo_off = (uint32_t)p.nchA_pad * p.chunk_bytes;              // A lo region follows A hi
+    const uint32_t b_hi_off = 2u * a_lo_off;
+    const uint32_t b_lo_off = b_hi_off + (uint32_t)p.nchB * p.chunk_bytes;
+
+    if (warp < WG_PROD_WARPS) {
+        // ================= producers =================
+        const int TPC = p.RB * 8;                            // threads per chunk
+        const int groups = WG_PROD_THREADS / TPC;
+        const int grp = tid / TPC, lt = tid - grp * TPC;
+        const int row = lt >> 3, q8 = lt & 7;
+        const uint32_t soff = wg_sw_off(row, q8);
+        const int nunits = p.nchA + p.nchB;
+        const int N = p.N, K = p.K;
+        int s = 0, cur_b = -1;
+        uint32_t ph = 0;
+        for (long long item = item0; item < item1; ++item) {
+            const int b = (int)(item / p.rbps);
+            const int r0 = (int)(item - (long long)b * p.rbps) * p.RB;
+            const int rows_valid = min(p.RB, p.R - r0);
+            if (b != cur_b) {                                // per-sample prologue tables (zero beyond the real channels)
+                named_bar_sync(1, WG_PROD_THREADS);
+                for (int t = tid; t < p.nchA * 32; t += WG_PROD_THREADS) {
+                    const int n = n_base + t;
+                    const bool v = n < N && a.dy_mode != CF_PRO_NONE;
+                    tabA[t] = v ? a.dy_a[(size_t)b * N + n] : 0.f;
+                    tabA[p.nchA * 32 + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
+                    tabA[2 * p.nchA * 32 + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
+                }
+                for (int t = tid; t < p.nchB * 32; t += WG_PROD_THREADS) {
+                    const int k = k_base + t;
+                    const bool v = k < K && a.x_mode != CF_PRO_NONE;
+                    tabB[t] = v ? a.x_a[(size_t)b * K + k] : 0.f;
+                    tabB[p.nchB * 32 + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
+                }
+                named_bar_sync(1, WG_PROD_THREADS);
+                cur_b = b;
+            }
+            mbar_wait_b(&empty[s], ph ^ 1u);
+            uint8_t* stage = stages + (size_t)s * p.stage_bytes;
+            const bool rv = row < rows_valid;
+            const size_t grow = (size_t)b * p.R + r0 + row;
+            const float* dyr = a.dy + grow * N;
+            const float* dy2r = a.dy2 ? a.dy2 + grow * N : nullptr;
+            const float* xr = a.x + grow * K;
+            for (int u0 = grp; u0 < nunits; u0 += groups * WG_UB) {
+                float v[WG_UB][4], v2[WG_UB][4];
+#pragma unroll
+                for (int i = 0; i < WG_UB; ++i) {            // all loads of the batch first
+                    const int u = u0 + i * groups;
+                    if (u < nunits && rv) {
+                        if (u < p.nchA) {
+                            const int c = n_base + u * 32 + q8 * 4;
+                            wg_ld4(dyr + c, c, N, p.av_dy, v[i]);
+                            if (a.dy_mode == CF_PRO_AFFINE2) wg_ld4(dy2r + c, c, N, p.av_dy, v2[i]);
+                        } else {
+                            const int c = k_base + (u - p.nchA) * 32 + q8 * 4;
+                            wg_ld4(xr + c, c, K, p.av_x, v[i]);
+                        }
+                    } else {
+                        v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+                        v2[i][0] = v2[i][1] = v2[i][2] = v2[i][3] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < WG_UB; ++i) {
+                    const int u = u0 + i * groups;
+                    if (u >= nunits) break;
+                    float hi[4], lo[4];
+                    uint8_t* dst;
+                    if (u < p.nchA) {
+                        const int tl = u * 32 + q8 * 4;
+                        const float4 ta = *reinterpret_cast<const float4*>(tabA + tl);
+                        const float4 tb = *reinterpret_cast<const float4*>(tabA + p.nchA * 32 + tl);
+                        const float4 tc = *reinterpret_cast<const float4*>(tabA + 2 * p.nchA * 32 + tl);
+                        const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w}, pc[4] = {tc.x, tc.y, tc.z, tc.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t = v[i][e];
+                            if (a.dy_mode != CF_PRO_NONE) t = rv ? wg_pro(a.dy_mode, t, v2[i][e], pa[e], pb[e], pc[e]) : 0.f;
+                            tf32_split(t, hi[e], lo[e]);
+                        }
+                        dst = stage + (uint32_t)u * p.chunk_bytes + soff;
+                        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(dst + a_lo_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    } else {
+                        const int j = u - p.nchA;
+                        const int tl = j * 32 + q8 * 4;
+                        const float4 ta = *reinterpret_cast<const float4*>(tabB + tl);
+                        const float4 tb = *reinterpret_cast<const float4*>(tabB + p.nchB * 32 + tl);
+                        const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t = v[i][e];
+                            if (a.x_mode != CF_PRO_NONE) t = rv ? wg_pro(a.x_mode, t, 0.f, pa[e], pb[e], 0.f) : 0.f;
+                            tf32_split(t, hi[e], lo[e]);
+                        }
+                        dst = stage + b_hi_off + (uint32_t)j * p.chunk_bytes + soff;
+                        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(dst + (b_lo_off - b_hi_off)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (++s == p.nstages) { s = 0; ph ^= 1u; }
+        }
+    } else {
+        // ================= MMA issuer =================
+        // instruction descriptor: D = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7, 10), A and B MN-major (bits 15, 16),
+        // N >> 3 @ bit 17, M >> 4 @ bit 24
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.npad_per >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+        const uint32_t stages_s = smem_u32(stages);
+        const int ksteps = p.RB >> 3;
+        int s = 0;
+        uint32_t ph = 0;
+        bool first = true;
+        for (long long item = item0; item < item1; ++item) {
+            mbar_wait_b(&full[s], ph);
+            tc_fence_after();
+            const uint32_t st = stages_s + (uint32_t)s * p.stage_bytes;
+            const uint64_t a_hi = wg_desc_mn(st, p.chunk_bytes, 512u);
+            const uint64_t a_lo = wg_desc_mn(st + a_lo_off, p.chunk_bytes, 512u);
+            const uint64_t b_hi = wg_desc_mn(st + b_hi_off, p.chunk_bytes, 512u);
+            const uint64_t b_lo = wg_desc_mn(st + b_lo_off, p.chunk_bytes, 512u);
+            if (wg_elect_one()) {
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t ko = (uint64_t)(ks * (1024 >> 4));                  // next group of 8 rows
+                    for (int mt = 0; mt < p.mt_per; ++mt) {
+                        const uint64_t mo = (uint64_t)(((uint32_t)mt * 4u * p.chunk_bytes) >> 4) + ko;   // 128 dy channels = 4 chunks
+                        const uint32_t d = tmem + (uint32_t)(mt * p.npad_per);
+                        umma_tf32(d, a_lo + mo, b_hi + ko, idesc, (uint32_t)(!(first && ks == 0)));
+                        umma_tf32(d, a_hi + mo, b_lo + ko, idesc, 1u);
+                        umma_tf32(d, a_hi + mo, b_hi + ko, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty[s]);
+                if (item == item1 - 1) umma_commit(&done_bar);
+            }
+            __syncwarp();
+            first = false;
+            if (++s == p.nstages) { s = 0; ph ^= 1u; }
+        }
+    }
+
+    // ================= all warps: TMEM partial -> dw (fp32 atomics) =================
+    __syncthreads();
+    if (item1 > item0) {
+        mbar_wait_b(&done_bar, 0u);
+        tc_fence_after();
+        const int qd = warp & 3;                             // TMEM lane quadrant of this warp
+        const int nslab = p.npad_per >> 5;
+        const int njobs = p.mt_per * nslab;                  // (channel tile, 32-column slab) jobs, spread over warps / 4
+        for (int job = warp >> 2; warp < WG_PROD_WARPS && job < njobs; job += WG_PROD_WARPS / 4) {
+            const int mt = job / nslab, sl = job - mt * nslab;
+            const int n = n_base + mt * 128 + qd * 32 + lane;
+            float r32[32];
+            tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mt * p.npad_per + sl * 32), r32);
+            if (n < p.N && n < n_base + p.mt_per * 128) {
+                float* dst = a.dw + (size_t)n * p.K + k_base + sl * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (k_base + sl * 32 + i < p.K && sl * 32 + i < p.npad_per) atomicAdd(dst + i, r32[i]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WG_PROD_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem, p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+static int wg_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// returns CF_OK when launched, -1 when the problem is not eligible (the caller runs the CUDA-core kernel)
+int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char* e = getenv("CFNET_PW_WGRAD_SIMT");
+        disabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (disabled) return -1;
+    const int N = a->N, K = a->K;
+    if (a->gather_in || a->dbias || (N & 1) || (K & 1) || N > 512 || K > 512) return -1;
+    if (a->dy_mode != CF_PRO_NONE && a->dy_mode != CF_PRO_AFFINE2) return -1;
+    const long long R = (long long)a->g.T * a->g.H * a->g.W;
+    if (R * a->B < 4096) return -1;                          // tiny problems: launch overhead dominates, keep the simple kernel
+    WgParams p;
+    p.B = a->B; p.R = (int)R; p.N = N; p.K = K;
+    uintptr_t da = (uintptr_t)a->dy | (uintptr_t)(a->dy2 ? a->dy2 : a->dy);
+    p.av_dy = ((N & 3) == 0 && (da & 15) == 0) ? 4 : 2;
+    p.av_x = ((K & 3) == 0 && (((uintptr_t)a->x) & 15) == 0) ? 4 : 2;
+    if ((da & 7) || (((uintptr_t)a->x) & 7)) return -1;
+    // split so that the partial fits 512 TMEM columns and one MMA covers <= 256 x channels
+    const int mtiles = (N + 127) / 128;
+    const int kpad = (K + 31) / 32 * 32;
+    p.nsplit = kpad > 256 ? 2 : 1;
+    p.npad_per = ((kpad / 32 + p.nsplit - 1) / p.nsplit) * 32;
+    p.msplit = 1;
+    while (((mtiles + p.msplit - 1) / p.msplit) * p.npad_per > 512) ++p.msplit;
+    p.mt_per = (mtiles + p.msplit - 1) / p.msplit;
+    p.nchB = p.npad_per / 32;
+    p.nchA_pad = 4 * p.mt_per;
+    {
+        int nreal = (N + 31) / 32;                           // real 32-channel chunks of dy; a CTA loads at most its own tiles'
+        p.nchA = nreal < p.nchA_pad ? nreal : p.nchA_pad;
+        if (p.msplit > 1) p.nchA = p.nchA_pad;               // (padded channels of the last tile load as zeros)
+    }
+    p.tmem_cols = 32;
+    while ((int)p.tmem_cols < p.mt_per * p.npad_per) p.tmem_cols <<= 1;
+    const size_t tab_bytes = (size_t)(3 * p.nchA + 2 * p.nchB) * 32 * 4;
+    p.RB = 32;
+    for (;;) {
+        p.chunk_bytes = (uint32_t)p.RB * 128u;
+        p.stage_bytes = (uint32_t)(2 * (p.nchA_pad + p.nchB)) * p.chunk_bytes;
+        p.nstages = (int)((WG_SMEM_MAX - 1024 - tab_bytes) / p.stage_bytes);
+        if (p.nstages >= 2 || p.RB == 16) break;
+        p.RB = 16;
+    }
+    if (p.nstages < 2) return -1;
+    if (p.nstages > WG_MAX_STAGES) p.nstages = WG_MAX_STAGES;
+    p.rbps = (int)((R + p.RB - 1) / p.RB);
+    p.total_items = (long long)a->B * p.rbps;
+    int gx = wg_sm_count() / (p.msplit * p.nsplit);
+    if (gx < 1) gx = 1;
+    if (gx > p.total_items) gx = (int)p.total_items;
+    p.items_per_cta = (int)((p.total_items + gx - 1) / gx);
+    gx = (int)((p.total_items + p.items_per_cta - 1) / p.items_per_cta);
+    const size_t smem = 1024 + (size_t)p.nstages * p.stage_bytes + tab_bytes;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX);
+        if (e != cudaSuccess) {
+            cf_set_error("cf_pw_wgrad_tc: cannot opt in to %d B of shared memory: %s", WG_SMEM_MAX, cudaGetErrorString(e));
+            return CF_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    dim3 grid((unsigned)gx, (unsigned)(p.msplit * p.nsplit));
+    pw_wgrad_tc_kernel<<<grid, WG_THREADS, smem, stream>>>(*a, p);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}

@@ -108,3 +108,35 @@ def test_tc_large_rows_layer1_shape(X):
     n = T * H * W
     scale = (s2[..., 1] * n).sqrt().unsqueeze(-1)          # sqrt(n * sum y^2) >= sum |y|: the scale of the summands
     assert ((s1 - s2).abs() / torch.stack([scale[..., 0], s2[..., 1]], -1)).max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("K,N", [(24, 54), (54, 24), (48, 108), (108, 48), (96, 216), (216, 96), (192, 432), (432, 192),
+                                 (360, 24), (34, 130), (8, 16)])
+def test_tc_wgrad_vs_fp64(X, K, N):
+    """Tensor-core weight gradient (MN-major operands, partial kept in TMEM) against fp64, all prologue modes,
+    ragged row blocks (R = 4 * 29 * 19 = 2204 rows per sample is not a multiple of 16 or 32), TMEM splits
+    (432 x 192 and 192 x 432 exceed 512 columns)."""
+    B, T, H, W = 3, 4, 29, 19
+    dy, dy2 = synth_tensor((B, N, T, H, W), 21), synth_tensor((B, N, T, H, W), 22)
+    x = synth_tensor((B, K, T, H, W), 23)
+    da, db, dc = synth_tensor((B, N), 24), synth_tensor((B, N), 25), synth_tensor((B, N), 26)
+    ta, tb = synth_tensor((B, K), 27), synth_tensor((B, K), 28)
+    v = lambda t: t.double().view(B, -1, 1, 1, 1)
+    g = X.geom(T, H, W)
+    cu = lambda t: t.cuda()
+    # plain
+    dw = torch.zeros(N, K, device="cuda")
+    X.pw_wgrad(rows(dy), rows(x), dw, B, K, N, g)
+    ref = torch.einsum("bnthw,bkthw->nk", dy.double(), x.double())
+    assert relerr(dw, ref) <= 1e-5, "plain"
+    # accumulation into a non-zero buffer (+=)
+    X.pw_wgrad(rows(dy), rows(x), dw, B, K, N, g)
+    assert relerr(dw, 2 * ref) <= 1e-5, "accumulate"
+    # BatchNorm-backward map on dy, Swish / ReLU prologue on x
+    dyy = v(da) * dy.double() + v(db) * dy2.double() + v(dc)
+    z = v(ta) * x.double() + v(tb)
+    for mode, xx in ((X.PRO_AFFINE_SWISH, z * torch.sigmoid(z)), (X.PRO_AFFINE_RELU, F.relu(z)), (X.PRO_NONE, x.double())):
+        dw = torch.zeros(N, K, device="cuda")
+        X.pw_wgrad(rows(dy), rows(x), dw, B, K, N, g, dy2=rows(dy2), dy_mode=X.PRO_AFFINE2, dy_tabs=(cu(da), cu(db), cu(dc)),
+                   x_mode=mode, x_tabs=(cu(ta), cu(tb)))
+        assert relerr(dw, torch.einsum("bnthw,bkthw->nk", dyy, xx)) <= 1e-5, f"x_mode {mode}"

@@ -93,3 +93,30 @@ for name, K, N, T, H, W, pro, epi, smode in CASES:
         print("   epilogue thread 0  [bookkeeping, wait-acc, tmem-ld, barriers, sts, store-slab, stats-reduce] =", v[8:15], "total", v[15])
     print(f"{name:38s} rows {rows:9d}  {ms*1e3:9.1f} us  {byt/ms/1e6:8.1f} GB/s  {100*byt/ms/1e6/peak:5.1f}% of measured HBM peak")
     del x, x2, y, aux
+
+# ---- weight gradients (dy [rows,N], x [rows,K] -> dw [N,K]); bytes = read dy, dy2, x
+WCASES = [
+    ("l1 conv1 wgrad dy54 x24", 24, 54, 256, 56, 56, X.PRO_NONE),
+    ("l1 conv3 wgrad dy24 x54 swish", 54, 24, 256, 56, 56, X.PRO_AFFINE_SWISH),
+    ("l2 conv3 wgrad dy48 x108 swish", 108, 48, 256, 28, 28, X.PRO_AFFINE_SWISH),
+    ("l3 conv1 wgrad dy216 x96", 96, 216, 256, 14, 14, X.PRO_NONE),
+    ("l3 conv3 wgrad dy96 x216 swish", 216, 96, 256, 14, 14, X.PRO_AFFINE_SWISH),
+    ("l4 conv3 wgrad dy192 x432 swish", 432, 192, 256, 7, 7, X.PRO_AFFINE_SWISH),
+]
+print("weight gradient:", "CUDA-core kernel" if os.environ.get("CFNET_PW_WGRAD_SIMT") == "1" else "tensor-core kernel")
+for name, K, N, T, H, W, xmode in WCASES:
+    if only and only not in name:
+        continue
+    dy = torch.randn(B, N, T, H, W, device=dev).contiguous(memory_format=CL3)
+    dy2 = torch.randn_like(dy)
+    x = torch.randn(B, K, T, H, W, device=dev).contiguous(memory_format=CL3)
+    dtabs = tuple(torch.randn(B, N, device=dev) for _ in range(3))
+    xtabs = (torch.randn(B, K, device=dev), torch.randn(B, K, device=dev)) if xmode != X.PRO_NONE else (None, None)
+    dw = torch.zeros(N, K, device=dev)
+    g = X.geom(T, H, W)
+    fn = lambda: X.pw_wgrad(dy, x, dw, B, K, N, g, dy2=dy2, dy_mode=X.PRO_AFFINE2, dy_tabs=dtabs, x_mode=xmode, x_tabs=xtabs)
+    ms = timeit(fn)
+    rows = B * T * H * W
+    byt = rows * 4 * (2 * N + K)
+    print(f"{name:38s} rows {rows:9d}  {ms*1e3:9.1f} us  {byt/ms/1e6:8.1f} GB/s  {100*byt/ms/1e6/peak:5.1f}% of measured HBM peak")
+    del dy, dy2, x
