@@ -25,7 +25,7 @@
 #define WG_PROD_THREADS (WG_PROD_WARPS * 32)
 #define WG_THREADS (WG_PROD_THREADS + 32)
 #define WG_MAX_STAGES 4
-#define WG_UB 4                                  /* units per batch (loads in flight per thread) */
+#define WG_UB 2                                  /* units per batch; two batches (this one and the next) are in registers */
 #define WG_SMEM_MAX (220 * 1024)
 
 struct WgParams {
@@ -63,14 +63,13 @@ __device__ __forceinline__ float wg_sigmoid(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return r;
 }
-__device__ __forceinline__ float wg_pro(int mode, float x, float x2, float a, float b, float c) {
-    switch (mode) {
-        case CF_PRO_AFFINE: return fmaf(a, x, b);
-        case CF_PRO_AFFINE_RELU: return fmaxf(fmaf(a, x, b), 0.f);
-        case CF_PRO_AFFINE_SWISH: { float z = fmaf(a, x, b); return z * wg_sigmoid(z); }
-        case CF_PRO_AFFINE2: return fmaf(a, x, fmaf(b, x2, c));
-        default: return x;
-    }
+template <int MODE>
+__device__ __forceinline__ float wg_pro(float x, float x2, float a, float b, float c) {
+    if (MODE == CF_PRO_AFFINE) return fmaf(a, x, b);
+    if (MODE == CF_PRO_AFFINE_RELU) return fmaxf(fmaf(a, x, b), 0.f);
+    if (MODE == CF_PRO_AFFINE_SWISH) { float z = fmaf(a, x, b); return z * wg_sigmoid(z); }
+    if (MODE == CF_PRO_AFFINE2) return fmaf(a, x, fmaf(b, x2, c));
+    return x;
 }
 // 4 floats at p (channel c .. c+3 of a row with C channels), zero beyond C; AV = 4 or 2
 __device__ __forceinline__ void wg_ld4(const float* p, int c, int C, int av, float* v) {
@@ -97,6 +96,7 @@ __device__ __forceinline__ void wg_ld4(const float* p, int c, int C, int av, flo
     }
 }
 
+template <int DYM, int XM>
 __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_wgrad_args a, const WgParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full[WG_MAX_STAGES];
@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
 
     if (warp < WG_PROD_WARPS) {
         // ================= producers =================
+        // A thread's work is a sequence of batches (item, u0): up to WG_UB (tensor, chunk) units of one row block.  The
+        // loads of batch i+1 -- usually the next row block -- are issued before batch i is transformed and stored, so a
+        // full memory latency is never exposed per stage (it was: 2400 cycles per 32-row stage in the first version).
         const int TPC = p.RB * 8;                            // threads per chunk
         const int groups = WG_PROD_THREADS / TPC;
         const int grp = tid / TPC, lt = tid - grp * TPC;
@@ -145,24 +148,102 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
         const uint32_t soff = wg_sw_off(row, q8);
         const int nunits = p.nchA + p.nchB;
         const int N = p.N, K = p.K;
+        const int ustep = groups * WG_UB;
+        constexpr bool aff2 = DYM == CF_PRO_AFFINE2;
+        float vA[WG_UB][4], wA[WG_UB][4], vB[WG_UB][4], wB[WG_UB][4];
+
+        // (b, rb) of a row block advance incrementally: no divisions in the per-stage path
+        auto load_batch = [&](int b, int rb, int u0, float (&v)[WG_UB][4], float (&v2)[WG_UB][4]) {
+            const int r0 = rb * p.RB;
+            const bool rv = row < min(p.RB, p.R - r0);
+            const size_t grow = (size_t)b * p.R + r0 + row;
+            const float* dyp = a.dy + grow * N + n_base + q8 * 4;
+            const float* dy2p = aff2 ? a.dy2 + grow * N + n_base + q8 * 4 : nullptr;
+            const float* xp = a.x + grow * K + k_base + q8 * 4;
+#pragma unroll
+            for (int i = 0; i < WG_UB; ++i) {
+                const int u = u0 + i * groups;
+                if (u < nunits && rv) {
+                    if (u < p.nchA) {
+                        const int c = n_base + u * 32 + q8 * 4;
+                        wg_ld4(dyp + u * 32, c, N, p.av_dy, v[i]);
+                        if (aff2) wg_ld4(dy2p + u * 32, c, N, p.av_dy, v2[i]);
+                    } else {
+                        const int c = k_base + (u - p.nchA) * 32 + q8 * 4;
+                        wg_ld4(xp + (u - p.nchA) * 32, c, K, p.av_x, v[i]);
+                    }
+                } else {
+                    v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+                    v2[i][0] = v2[i][1] = v2[i][2] = v2[i][3] = 0.f;
+                }
+            }
+        };
+        auto store_batch = [&](uint8_t* stage, int u0, bool rv, const float (&v)[WG_UB][4], const float (&v2)[WG_UB][4]) {
+#pragma unroll
+            for (int i = 0; i < WG_UB; ++i) {
+                const int u = u0 + i * groups;
+                if (u >= nunits) break;
+                float hi[4], lo[4];
+                if (u < p.nchA) {
+                    const int tl = u * 32 + q8 * 4;
+                    const float4 ta = *reinterpret_cast<const float4*>(tabA + tl);
+                    const float4 tb = *reinterpret_cast<const float4*>(tabA + p.nchA * 32 + tl);
+                    const float4 tc = *reinterpret_cast<const float4*>(tabA + 2 * p.nchA * 32 + tl);
+                    const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w}, pc[4] = {tc.x, tc.y, tc.z, tc.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t = v[i][e];
+                        if (DYM != CF_PRO_NONE) t = rv ? wg_pro<DYM>(t, v2[i][e], pa[e], pb[e], pc[e]) : 0.f;
+                        tf32_split(t, hi[e], lo[e]);
+                    }
+                    uint8_t* dst = stage + (uint32_t)u * p.chunk_bytes + soff;
+                    *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(dst + a_lo_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                } else {
+                    const int j = u - p.nchA;
+                    const int tl = j * 32 + q8 * 4;
+                    const float4 ta = *reinterpret_cast<const float4*>(tabB + tl);
+                    const float4 tb = *reinterpret_cast<const float4*>(tabB + p.nchB * 32 + tl);
+                    const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t = v[i][e];
+                        if (XM != CF_PRO_NONE) t = rv ? wg_pro<XM>(t, 0.f, pa[e], pb[e], 0.f) : 0.f;
+                        tf32_split(t, hi[e], lo[e]);
+                    }
+                    uint8_t* dst = stage + b_hi_off + (uint32_t)j * p.chunk_bytes + soff;
+                    *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(dst + (b_lo_off - b_hi_off)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        };
+
         int s = 0, cur_b = -1;
         uint32_t ph = 0;
-        for (long long item = item0; item < item1; ++item) {
-            const int b = (int)(item / p.rbps);
-            const int r0 = (int)(item - (long long)b * p.rbps) * p.RB;
-            const int rows_valid = min(p.RB, p.R - r0);
+        int b = (int)(item0 / p.rbps);
+        int rb = (int)(item0 - (long long)b * p.rbps);
+        long long item = item0;
+        if (item0 < item1 && grp < nunits) load_batch(b, rb, grp, vA, wA);
+
+        // One row block.  Its batches alternate between the two register sets starting with (cv, cw); which set a batch
+        // uses is fixed in the code (a run-time "current set" flag made the compiler copy registers right after the
+        // loads, i.e. wait for them: no prefetch at all -- 34 % of all stall samples sat on those moves).
+        auto item_body = [&](float (&cv)[WG_UB][4], float (&cw)[WG_UB][4], float (&nv)[WG_UB][4], float (&nw)[WG_UB][4]) {
+            const bool rv = row < min(p.RB, p.R - rb * p.RB);
+            int nb = b, nrb = rb + 1;                        // the next row block
+            if (nrb == p.rbps) { nrb = 0; ++nb; }
             if (b != cur_b) {                                // per-sample prologue tables (zero beyond the real channels)
                 named_bar_sync(1, WG_PROD_THREADS);
                 for (int t = tid; t < p.nchA * 32; t += WG_PROD_THREADS) {
                     const int n = n_base + t;
-                    const bool v = n < N && a.dy_mode != CF_PRO_NONE;
+                    const bool v = n < N && DYM != CF_PRO_NONE;
                     tabA[t] = v ? a.dy_a[(size_t)b * N + n] : 0.f;
                     tabA[p.nchA * 32 + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
                     tabA[2 * p.nchA * 32 + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
                 }
                 for (int t = tid; t < p.nchB * 32; t += WG_PROD_THREADS) {
                     const int k = k_base + t;
-                    const bool v = k < K && a.x_mode != CF_PRO_NONE;
+                    const bool v = k < K && XM != CF_PRO_NONE;
                     tabB[t] = v ? a.x_a[(size_t)b * K + k] : 0.f;
                     tabB[p.nchB * 32 + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
                 }
@@ -171,73 +252,41 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
             }
             mbar_wait_b(&empty[s], ph ^ 1u);
             uint8_t* stage = stages + (size_t)s * p.stage_bytes;
-            const bool rv = row < rows_valid;
-            const size_t grow = (size_t)b * p.R + r0 + row;
-            const float* dyr = a.dy + grow * N;
-            const float* dy2r = a.dy2 ? a.dy2 + grow * N : nullptr;
-            const float* xr = a.x + grow * K;
-            for (int u0 = grp; u0 < nunits; u0 += groups * WG_UB) {
-                float v[WG_UB][4], v2[WG_UB][4];
-#pragma unroll
-                for (int i = 0; i < WG_UB; ++i) {            // all loads of the batch first
-                    const int u = u0 + i * groups;
-                    if (u < nunits && rv) {
-                        if (u < p.nchA) {
-                            const int c = n_base + u * 32 + q8 * 4;
-                            wg_ld4(dyr + c, c, N, p.av_dy, v[i]);
-                            if (a.dy_mode == CF_PRO_AFFINE2) wg_ld4(dy2r + c, c, N, p.av_dy, v2[i]);
-                        } else {
-                            const int c = k_base + (u - p.nchA) * 32 + q8 * 4;
-                            wg_ld4(xr + c, c, K, p.av_x, v[i]);
-                        }
-                    } else {
-                        v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
-                        v2[i][0] = v2[i][1] = v2[i][2] = v2[i][3] = 0.f;
-                    }
+            const bool more_items = item + 1 < item1;
+            for (int u0 = grp; u0 < nunits;) {
+                {
+                    const int nu0 = u0 + ustep;
+                    if (nu0 < nunits) load_batch(b, rb, nu0, nv, nw);
+                    else if (more_items) load_batch(nb, nrb, grp, nv, nw);
+                    store_batch(stage, u0, rv, cv, cw);
+                    u0 = nu0;
                 }
-#pragma unroll
-                for (int i = 0; i < WG_UB; ++i) {
-                    const int u = u0 + i * groups;
-                    if (u >= nunits) break;
-                    float hi[4], lo[4];
-                    uint8_t* dst;
-                    if (u < p.nchA) {
-                        const int tl = u * 32 + q8 * 4;
-                        const float4 ta = *reinterpret_cast<const float4*>(tabA + tl);
-                        const float4 tb = *reinterpret_cast<const float4*>(tabA + p.nchA * 32 + tl);
-                        const float4 tc = *reinterpret_cast<const float4*>(tabA + 2 * p.nchA * 32 + tl);
-                        const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w}, pc[4] = {tc.x, tc.y, tc.z, tc.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float t = v[i][e];
-                            if (a.dy_mode != CF_PRO_NONE) t = rv ? wg_pro(a.dy_mode, t, v2[i][e], pa[e], pb[e], pc[e]) : 0.f;
-                            tf32_split(t, hi[e], lo[e]);
-                        }
-                        dst = stage + (uint32_t)u * p.chunk_bytes + soff;
-                        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4*>(dst + a_lo_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    } else {
-                        const int j = u - p.nchA;
-                        const int tl = j * 32 + q8 * 4;
-                        const float4 ta = *reinterpret_cast<const float4*>(tabB + tl);
-                        const float4 tb = *reinterpret_cast<const float4*>(tabB + p.nchB * 32 + tl);
-                        const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float t = v[i][e];
-                            if (a.x_mode != CF_PRO_NONE) t = rv ? wg_pro(a.x_mode, t, 0.f, pa[e], pb[e], 0.f) : 0.f;
-                            tf32_split(t, hi[e], lo[e]);
-                        }
-                        dst = stage + b_hi_off + (uint32_t)j * p.chunk_bytes + soff;
-                        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4*>(dst + (b_lo_off - b_hi_off)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    }
+                if (u0 >= nunits) break;
+                {
+                    const int nu0 = u0 + ustep;
+                    if (nu0 < nunits) load_batch(b, rb, nu0, cv, cw);
+                    else if (more_items) load_batch(nb, nrb, grp, cv, cw);
+                    store_batch(stage, u0, rv, nv, nw);
+                    u0 = nu0;
                 }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
             if (++s == p.nstages) { s = 0; ph ^= 1u; }
+            b = nb;
+            rb = nrb;
+            ++item;
+        };
+        const int nbatches = grp < nunits ? (nunits - grp + ustep - 1) / ustep : 0;
+        if (nbatches & 1) {                                  // odd: consecutive row blocks start on alternating sets
+            while (item + 1 < item1) {
+                item_body(vA, wA, vB, wB);
+                item_body(vB, wB, vA, wA);
+            }
+            if (item < item1) item_body(vA, wA, vB, wB);
+        } else {
+            while (item < item1) item_body(vA, wA, vB, wB);
         }
     } else {
         // ================= MMA issuer =================
@@ -330,6 +379,7 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     const int N = a->N, K = a->K;
     if (a->gather_in || a->dbias || (N & 1) || (K & 1) || N > 512 || K > 512) return -1;
     if (a->dy_mode != CF_PRO_NONE && a->dy_mode != CF_PRO_AFFINE2) return -1;
+    if (a->x_mode == CF_PRO_AFFINE2) return -1;
     const long long R = (long long)a->g.T * a->g.H * a->g.W;
     if (R * a->B < 4096) return -1;                          // tiny problems: launch overhead dominates, keep the simple kernel
     WgParams p;
@@ -356,13 +406,13 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.mt_per * p.npad_per) p.tmem_cols <<= 1;
     const size_t tab_bytes = (size_t)(3 * p.nchA + 2 * p.nchB) * 32 * 4;
-    p.RB = 32;
+    p.RB = 64;                                               // rows per stage: as many as leave >= 2 stages (per-stage overhead amortised)
     for (;;) {
         p.chunk_bytes = (uint32_t)p.RB * 128u;
         p.stage_bytes = (uint32_t)(2 * (p.nchA_pad + p.nchB)) * p.chunk_bytes;
         p.nstages = (int)((WG_SMEM_MAX - 1024 - tab_bytes) / p.stage_bytes);
         if (p.nstages >= 2 || p.RB == 16) break;
-        p.RB = 16;
+        p.RB >>= 1;
     }
     if (p.nstages < 2) return -1;
     if (p.nstages > WG_MAX_STAGES) p.nstages = WG_MAX_STAGES;
@@ -374,17 +424,31 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     p.items_per_cta = (int)((p.total_items + gx - 1) / gx);
     gx = (int)((p.total_items + p.items_per_cta - 1) / p.items_per_cta);
     const size_t smem = 1024 + (size_t)p.nstages * p.stage_bytes + tab_bytes;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX);
-        if (e != cudaSuccess) {
-            cf_set_error("cf_pw_wgrad_tc: cannot opt in to %d B of shared memory: %s", WG_SMEM_MAX, cudaGetErrorString(e));
-            return CF_ERR_CUDA;
-        }
-        attr_done = true;
-    }
     dim3 grid((unsigned)gx, (unsigned)(p.msplit * p.nsplit));
-    pw_wgrad_tc_kernel<<<grid, WG_THREADS, smem, stream>>>(*a, p);
+    cudaError_t e = cudaSuccess;
+#define WG_LAUNCH(DYM_, XM_)                                                                                                  \
+    do {                                                                                                                      \
+        static bool attr_done = false;                                                                                        \
+        if (!attr_done) {                                                                                                     \
+            e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<DYM_, XM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX); \
+            attr_done = e == cudaSuccess;                                                                                     \
+        }                                                                                                                     \
+        if (e == cudaSuccess) pw_wgrad_tc_kernel<DYM_, XM_><<<grid, WG_THREADS, smem, stream>>>(*a, p);                       \
+    } while (0)
+#define WG_LAUNCH_X(DYM_)                                                              \
+    switch (a->x_mode) {                                                               \
+        case CF_PRO_NONE: WG_LAUNCH(DYM_, CF_PRO_NONE); break;                         \
+        case CF_PRO_AFFINE: WG_LAUNCH(DYM_, CF_PRO_AFFINE); break;                     \
+        case CF_PRO_AFFINE_RELU: WG_LAUNCH(DYM_, CF_PRO_AFFINE_RELU); break;           \
+        default: WG_LAUNCH(DYM_, CF_PRO_AFFINE_SWISH); break;                          \
+    }
+    if (a->dy_mode == CF_PRO_AFFINE2) { WG_LAUNCH_X(CF_PRO_AFFINE2) } else { WG_LAUNCH_X(CF_PRO_NONE) }
+#undef WG_LAUNCH_X
+#undef WG_LAUNCH
+    if (e != cudaSuccess) {
+        cf_set_error("cf_pw_wgrad_tc: cannot opt in to %d B of shared memory: %s", WG_SMEM_MAX, cudaGetErrorString(e));
+        return CF_ERR_CUDA;
+    }
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
