@@ -679,10 +679,14 @@ static int dw_common_checks(const cf_dw_args* a) {
     return CF_OK;
 }
 
+int cf_dw3_try(int mode, const cf_dw_args* a, cudaStream_t stream);   // x3d_dw3.cu: plane-marching 3x3x3 stride-1 kernels (-1: not eligible)
+
 extern "C" int cf_dw_conv_fwd(const cf_dw_args* a, cudaStream_t stream) {
     int rc = dw_common_checks(a);
     if (rc) return rc;
     CF_CHECK_ARG(a->pro_mode != CF_PRO_AFFINE2, "forward takes NONE/AFFINE/AFFINE_RELU");
+    rc = cf_dw3_try(0, a, stream);
+    if (rc >= 0) return rc;
     int v = pick_vec(a->C, a->x, a->y);
     if (v == 4) return launch_dw_fwd<4>(a, stream);
     if (v == 2) return launch_dw_fwd<2>(a, stream);
@@ -694,6 +698,8 @@ extern "C" int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     if (rc) return rc;
     CF_CHECK_ARG(a->epi_mode == CF_EPI_NONE || (a->epi_mode == CF_EPI_DRELU && a->aux && a->epi_a && a->epi_b), "bad epilogue");
     CF_CHECK_ARG(a->stats_mode != CF_STATS_SUM_AUX || a->aux, "aux missing");
+    rc = cf_dw3_try(1, a, stream);
+    if (rc >= 0) return rc;
     int v = pick_vec(a->C, a->x, a->y);
     if (a->x2 && (((uintptr_t)a->x2) & 15)) v = v > 2 ? 2 : v;
     if (a->aux && (((uintptr_t)a->aux) & 15)) v = v > 2 ? 2 : v;
@@ -713,6 +719,8 @@ extern "C" int cf_dw_conv_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     if (rc) return rc;
     CF_CHECK_ARG(a->aux, "aux (the forward input) missing");
     CF_CHECK_ARG(a->C <= 1024, "C too large");
+    rc = cf_dw3_try(2, a, stream);
+    if (rc >= 0) return rc;
     int taps = a->g.kt * a->g.kh * a->g.kw;
     int v = pick_vec(a->C, a->x, a->aux);
     if (a->C / v > 256) { cf_set_error("cf_dw_conv_wgrad: C/vec > 256"); return CF_ERR_ARG; }

@@ -188,9 +188,12 @@ def test_dense_conv_through_tap_gather(X):
     close(db, gy.sum(dim=(0, 2, 3, 4)), rtol=1e-5, atol=1e-4, what="3x3x3 dbias")
 
 
-@pytest.mark.parametrize("C,stride", [(54, 1), (54, 2), (108, 2), (24, 1), (7, 2)])
-def test_depthwise_fwd_bwd(X, C, stride):
-    B, T, H, W = 2, 4, 9, 10
+@pytest.mark.parametrize("C,stride,T,H,W", [(54, 1, 4, 9, 10), (54, 2, 4, 9, 10), (108, 2, 4, 9, 10), (24, 1, 4, 9, 10), (7, 2, 4, 9, 10),
+                                            # plane-marching kernels (x3d_dw3.cu): tiles of 8 x 14 / 8 x 7, several T segments, ragged H
+                                            (54, 1, 9, 11, 28), (108, 1, 7, 14, 14), (216, 1, 13, 7, 7), (54, 1, 1, 56, 56),
+                                            (54, 1, 5, 8, 42)])
+def test_depthwise_fwd_bwd(X, C, stride, T, H, W):
+    B = 2
     x = synth_tensor((B, C, T, H, W), 51)
     w = synth_tensor((C, 1, 3, 3, 3), 52, 0.3)
     ta, tb = synth_tensor((B, C), 53), synth_tensor((B, C), 54)
