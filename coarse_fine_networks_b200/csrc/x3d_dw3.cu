@@ -29,7 +29,9 @@ enum { D3_FWD = 0, D3_DGRAD = 1, D3_WGRAD = 2 };
 
 struct D3Params {
     int B, C, T, H, W;
-    int htiles, wtiles, slabs, tseg, ntseg;
+    int htiles, wtiles, slabs;
+    long long total_steps;            // columns * T, a column = (sample, h tile, w tile, channel slab)
+    int steps_per_cta;
 };
 
 __device__ __forceinline__ void d3_cp_async8(void* smem, const void* gmem) {
@@ -60,16 +62,24 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
     const int patch = tid / D3_LANES, lane = tid - patch * D3_LANES;
     const int pr = patch / NPW, pc = patch - pr * NPW;
     const int oh0 = pr * 2, ow0 = pc * D3_PW;                      // patch origin inside the tile
-    int bx = blockIdx.x;
-    const int seg = bx % p.ntseg; bx /= p.ntseg;
-    const int slab = bx % p.slabs; bx /= p.slabs;
-    const int tw_i = bx % p.wtiles;
-    const int th_i = bx / p.wtiles;
-    const int b = blockIdx.y;
     const int C = p.C, T = p.T, H = p.H, W = p.W;
+    // This CTA's share of the flattened (column, t) sequence: contiguous, equal for all CTAs (no wave quantisation: the
+    // grid is one CTA per SM); a share may span several columns, each piece restarts the ring (2 halo planes).
+    const long long step0 = (long long)blockIdx.x * p.steps_per_cta;
+    const long long step1 = min(step0 + p.steps_per_cta, p.total_steps);
+    for (long long step = step0; step < step1;) {
+    const int col = (int)(step / T);
+    const int t0 = (int)(step - (long long)col * T);
+    const int t1 = (int)min((long long)T, t0 + (step1 - step));
+    step += t1 - t0;
+    int bx = col;
+    const int slab = bx % p.slabs; bx /= p.slabs;
+    const int tw_i = bx % p.wtiles; bx /= p.wtiles;
+    const int th_i = bx % p.htiles;
+    const int b = bx / p.htiles;
     const int h0 = th_i * D3_TH, w0 = tw_i * TW;
     const int cs0 = slab * D3_CS, c0 = cs0 + lane * 2;
-    const int t0 = seg * p.tseg, t1 = min(T, t0 + p.tseg);
+    __syncthreads();                                               // the previous piece's reductions are done with the ring
 
     // ---- per-CTA constants: prologue / epilogue tables of this sample and slab, weights of the slab
     //   ring tensor:  FWD: a.x with (pro_a, pro_b);  DGRAD: a.x (+ a.x2) with (pro_a, pro_b, pro_c);
@@ -111,39 +121,46 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
     const float* src1 = two_src ? a.x2 : nullptr;
     const int ring_mode = MODE == D3_WGRAD ? (a.epi_a ? CF_PRO_AFFINE_RELU : CF_PRO_NONE) : a.pro_mode;
 
-    // ---- plane movement: this thread owns positions patch + k * NPATCH of every plane, at its own channel pair
+    // ---- plane movement: this thread owns positions patch + k * NPATCH of every plane, at its own channel pair.  Which
+    // of them lie inside the image, and their element offsets inside a frame, do not depend on t: computed once per piece.
+    uint32_t vmask = 0;
+    int goff[KPT];
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+        const int pos = patch + k * NPATCH;
+        const int hh = pos / HW, ww = pos - hh * HW;
+        const int h = h0 - 1 + hh, w = w0 - 1 + ww;
+        const bool v = pos < NPOS && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+        goff[k] = v ? (h * W + w) * C + c0 : 0;
+        vmask |= v ? (1u << k) : 0u;
+    }
+    const int soff0 = patch * D3_CS + lane * 2;                   // staging / ring offset of position k: soff0 + k * NPATCH * 54
+    const size_t frame = (size_t)H * W * C;
     auto plane_issue = [&](int t) {                               // global -> staging (cp.async, 8 bytes per position)
         if (t < 0 || t >= T) return;
-        const size_t pbase = ((size_t)b * T + t) * H;
+        const float* f0 = src0 + ((size_t)b * T + t) * frame;
+        const float* f1 = src1 ? src1 + ((size_t)b * T + t) * frame : nullptr;
 #pragma unroll
         for (int k = 0; k < KPT; ++k) {
-            const int pos = patch + k * NPATCH;
-            if (pos >= NPOS) break;
-            const int hh = pos / HW, ww = pos - hh * HW;
-            const int h = h0 - 1 + hh, w = w0 - 1 + ww;
-            if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) {
-                const size_t g = ((pbase + h) * W + w) * C + c0;
-                d3_cp_async8(stg0 + pos * D3_CS + lane * 2, src0 + g);
-                if (MODE == D3_DGRAD && src1) d3_cp_async8(stg1 + pos * D3_CS + lane * 2, src1 + g);
+            if (vmask & (1u << k)) {
+                d3_cp_async8(stg0 + soff0 + k * (NPATCH * D3_CS), f0 + goff[k]);
+                if (MODE == D3_DGRAD && f1) d3_cp_async8(stg1 + soff0 + k * (NPATCH * D3_CS), f1 + goff[k]);
             }
         }
     };
     auto plane_land = [&](int t, float* dst) {                    // staging -> ring slot with the prologue; zero outside
-        const bool tv = t >= 0 && t < T;
+        const uint32_t m = (t >= 0 && t < T) ? vmask : 0u;
 #pragma unroll
         for (int k = 0; k < KPT; ++k) {
-            const int pos = patch + k * NPATCH;
-            if (pos >= NPOS) break;
-            const int hh = pos / HW, ww = pos - hh * HW;
-            const int h = h0 - 1 + hh, w = w0 - 1 + ww;
+            if (patch + k * NPATCH >= NPOS) break;
             float2 v = make_float2(0.f, 0.f);
-            if (tv && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) {
-                const float2 x = *reinterpret_cast<const float2*>(stg0 + pos * D3_CS + lane * 2);
+            if (m & (1u << k)) {
+                const float2 x = *reinterpret_cast<const float2*>(stg0 + soff0 + k * (NPATCH * D3_CS));
                 if (ring_mode == CF_PRO_AFFINE_RELU) {
                     v.x = fmaxf(fmaf(ra.x, x.x, rb.x), 0.f);
                     v.y = fmaxf(fmaf(ra.y, x.y, rb.y), 0.f);
                 } else if (ring_mode == CF_PRO_AFFINE2) {
-                    const float2 x2 = *reinterpret_cast<const float2*>(stg1 + pos * D3_CS + lane * 2);
+                    const float2 x2 = *reinterpret_cast<const float2*>(stg1 + soff0 + k * (NPATCH * D3_CS));
                     v.x = fmaf(ra.x, x.x, fmaf(rb.x, x2.x, rc.x));
                     v.y = fmaf(ra.y, x.y, fmaf(rb.y, x2.y, rc.y));
                 } else if (ring_mode == CF_PRO_AFFINE) {
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
                     v = x;
                 }
             }
-            *reinterpret_cast<float2*>(dst + pos * D3_CS + lane * 2) = v;
+            *reinterpret_cast<float2*>(dst + soff0 + k * (NPATCH * D3_CS)) = v;
         }
     };
     auto slot = [&](int t) { return ring + ((t - t0 + 1) % 3) * PLANE; };     // plane t0-1 -> slot 0
@@ -164,6 +181,23 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
     for (int i = 0; i < 27; ++i)
         wreg[i] = MODE == D3_WGRAD ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(ws + i * D3_CS + lane * 2);
     float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+    // WGRAD: raw output-gradient values (and the second BatchNorm-backward operand) of the NEXT frame's patch, loaded one
+    // step ahead so that their latency hides behind the current frame's FMAs
+    float2 dn[MODE == D3_WGRAD ? 2 : 1][MODE == D3_WGRAD ? D3_PW : 1], dn2[MODE == D3_WGRAD ? 2 : 1][MODE == D3_WGRAD ? D3_PW : 1];
+    auto d_prefetch = [&](int t) {
+        if (MODE != D3_WGRAD) return;
+        const size_t ob = (((size_t)b * T + t) * H + h0 + oh0) * W + w0 + ow0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < D3_PW; ++j) {
+                const bool v = t < T && h0 + oh0 + r < H;
+                const size_t g = (ob + (size_t)r * W + j) * C + c0;
+                dn[MODE == D3_WGRAD ? r : 0][MODE == D3_WGRAD ? j : 0] = v ? __ldg(reinterpret_cast<const float2*>(a.x + g)) : make_float2(0.f, 0.f);
+                if (a.pro_mode == CF_PRO_AFFINE2)
+                    dn2[MODE == D3_WGRAD ? r : 0][MODE == D3_WGRAD ? j : 0] = v ? __ldg(reinterpret_cast<const float2*>(a.x2 + g)) : make_float2(0.f, 0.f);
+            }
+    };
     const float* pbase_thr = ring + (oh0 * HW + ow0) * D3_CS + lane * 2;     // patch origin (haloed coordinates) in slot 0
 
     // ---- prologue: planes t0-1 and t0 synchronously, t0+1 in flight
@@ -174,6 +208,7 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
     d3_cp_async_wait_all();
     plane_land(t0, slot(t0));
     plane_issue(t0 + 1);
+    d_prefetch(t0);
 
     for (int t = t0; t < t1; ++t) {
         d3_cp_async_wait_all();
@@ -243,6 +278,12 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
             }
         } else {
             // weight gradient: d' at the patch positions (BatchNorm-backward map of the output gradient)
+            float2 dcur[2][D3_PW], dcur2[2][D3_PW];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int j = 0; j < D3_PW; ++j) { dcur[r][j] = dn[MODE == D3_WGRAD ? r : 0][MODE == D3_WGRAD ? j : 0]; dcur2[r][j] = dn2[MODE == D3_WGRAD ? r : 0][MODE == D3_WGRAD ? j : 0]; }
+            if (t + 1 < t1) d_prefetch(t + 1);
             const float* pl0 = pbase_thr + (sl0 % 3) * PLANE;
             const float* pl1 = pbase_thr + ((sl0 + 1) % 3) * PLANE;
             const float* pl2 = pbase_thr + ((sl0 + 2) % 3) * PLANE;
@@ -252,10 +293,9 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
                 float2 d[D3_PW];
 #pragma unroll
                 for (int j = 0; j < D3_PW; ++j) {
-                    const size_t g = (orow_base + (size_t)r * W + j) * C + c0;
-                    float2 v = __ldg(reinterpret_cast<const float2*>(a.x + g));
+                    float2 v = dcur[r][j];
                     if (a.pro_mode == CF_PRO_AFFINE2) {
-                        const float2 v2 = __ldg(reinterpret_cast<const float2*>(a.x2 + g));
+                        const float2 v2 = dcur2[r][j];
                         v.x = fmaf(ea.x, v.x, fmaf(eb.x, v2.x, rc.x));
                         v.y = fmaf(ea.y, v.y, fmaf(eb.y, v2.y, rc.y));
                     } else if (a.pro_mode != CF_PRO_NONE) {
@@ -315,6 +355,7 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
             atomicAdd(a.stats + ((size_t)b * C + cs0 + c) * 2 + which, (double)s);
         }
     }
+    }   // pieces
 }
 
 // ---------------------------------------------------------------------------------------
@@ -330,7 +371,7 @@ static int d3_launch(const cf_dw_args* a, const D3Params& p, cudaStream_t stream
         if (e != cudaSuccess) { cf_set_error("dw3: cannot opt in to shared memory: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
         done = true;
     }
-    dim3 grid((unsigned)(p.htiles * p.wtiles * p.slabs * p.ntseg), (unsigned)p.B);
+    dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
     dw3_kernel<MODE, NPW><<<grid, D3_LANES * 4 * NPW, smem, stream>>>(*a, p);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
@@ -358,17 +399,23 @@ int cf_dw3_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (mode == D3_DGRAD && a->stats_mode == CF_STATS_SUM_SQ) return -1;
     D3Params p;
     p.B = a->B; p.C = a->C; p.T = g.T; p.H = g.H; p.W = g.W;
-    const int npw = g.W == 7 ? 1 : 2;
+    static int force_npw = -1;                                     // CFNET_DW3_NPW=1|2: tile width experiment
+    if (force_npw < 0) { const char* e = getenv("CFNET_DW3_NPW"); force_npw = e ? atoi(e) : 0; }
+    const int npw = (g.W == 7 || force_npw == 1) ? 1 : 2;
     p.htiles = (g.H + D3_TH - 1) / D3_TH;
     p.wtiles = g.W / (D3_PW * npw);
     p.slabs = a->C / D3_CS;
-    const long long base = (long long)p.B * p.htiles * p.wtiles * p.slabs;
-    long long want = (3LL * 148 + base - 1) / base;              // T segments for about three waves of CTAs
-    if (want < 1) want = 1;
-    int tseg = (int)((g.T + want - 1) / want);
-    if (tseg < 6) tseg = g.T < 6 ? g.T : 6;                      // two halo planes per segment: keep their share below 1/4
-    p.tseg = tseg;
-    p.ntseg = (g.T + tseg - 1) / tseg;
+    const long long cols = (long long)p.B * p.htiles * p.wtiles * p.slabs;
+    p.total_steps = cols * g.T;
+    int nsm = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+    const int cta_per_sm = npw == 1 ? 2 : 1;                       // 78-97 KB of shared memory per CTA at the narrow tile
+    nsm *= cta_per_sm;
+    long long spc = (p.total_steps + nsm - 1) / nsm;
+    if (spc < 4) spc = 4;                                        // two halo planes per piece: keep their share bounded
+    p.steps_per_cta = (int)spc;
     if (npw == 1) {
         if (mode == D3_FWD) return d3_launch<D3_FWD, 1>(a, p, stream);
         if (mode == D3_DGRAD) return d3_launch<D3_DGRAD, 1>(a, p, stream);
