@@ -680,12 +680,15 @@ static int dw_common_checks(const cf_dw_args* a) {
 }
 
 int cf_dw3_try(int mode, const cf_dw_args* a, cudaStream_t stream);   // x3d_dw3.cu: plane-marching 3x3x3 stride-1 kernels (-1: not eligible)
+int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream); // x3d_dw3s2.cu: spatial stride 2, forward (0) and weight gradient (2)
 
 extern "C" int cf_dw_conv_fwd(const cf_dw_args* a, cudaStream_t stream) {
     int rc = dw_common_checks(a);
     if (rc) return rc;
     CF_CHECK_ARG(a->pro_mode != CF_PRO_AFFINE2, "forward takes NONE/AFFINE/AFFINE_RELU");
     rc = cf_dw3_try(0, a, stream);
+    if (rc >= 0) return rc;
+    rc = cf_dw3s2_try(0, a, stream);
     if (rc >= 0) return rc;
     int v = pick_vec(a->C, a->x, a->y);
     if (v == 4) return launch_dw_fwd<4>(a, stream);
@@ -720,6 +723,8 @@ extern "C" int cf_dw_conv_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a->aux, "aux (the forward input) missing");
     CF_CHECK_ARG(a->C <= 1024, "C too large");
     rc = cf_dw3_try(2, a, stream);
+    if (rc >= 0) return rc;
+    rc = cf_dw3s2_try(2, a, stream);
     if (rc >= 0) return rc;
     int taps = a->g.kt * a->g.kh * a->g.kw;
     int v = pick_vec(a->C, a->x, a->aux);

@@ -191,7 +191,9 @@ def test_dense_conv_through_tap_gather(X):
 @pytest.mark.parametrize("C,stride,T,H,W", [(54, 1, 4, 9, 10), (54, 2, 4, 9, 10), (108, 2, 4, 9, 10), (24, 1, 4, 9, 10), (7, 2, 4, 9, 10),
                                             # plane-marching kernels (x3d_dw3.cu): tiles of 8 x 14 / 8 x 7, several T segments, ragged H
                                             (54, 1, 9, 11, 28), (108, 1, 7, 14, 14), (216, 1, 13, 7, 7), (54, 1, 1, 56, 56),
-                                            (54, 1, 5, 8, 42)])
+                                            (54, 1, 5, 8, 42),
+                                            # stride-2 plane-marching kernels (x3d_dw3s2.cu): output tiles 4 x 14 / 4 x 7
+                                            (54, 2, 6, 18, 28), (108, 2, 9, 14, 14), (54, 2, 3, 112, 56), (54, 2, 5, 13, 27)])
 def test_depthwise_fwd_bwd(X, C, stride, T, H, W):
     B = 2
     x = synth_tensor((B, C, T, H, W), 51)
