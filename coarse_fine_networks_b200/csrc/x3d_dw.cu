@@ -703,6 +703,8 @@ extern "C" int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a->stats_mode != CF_STATS_SUM_AUX || a->aux, "aux missing");
     rc = cf_dw3_try(1, a, stream);
     if (rc >= 0) return rc;
+    rc = cf_dw3s2_try(1, a, stream);
+    if (rc >= 0) return rc;
     int v = pick_vec(a->C, a->x, a->y);
     if (a->x2 && (((uintptr_t)a->x2) & 15)) v = v > 2 ? 2 : v;
     if (a->aux && (((uintptr_t)a->aux) & 15)) v = v > 2 ? 2 : v;

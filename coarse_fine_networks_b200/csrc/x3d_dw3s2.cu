@@ -288,6 +288,242 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_kernel(const cf
 }
 
 // ---------------------------------------------------------------------------------------
+// Data gradient of the stride-2 convolution.  The small tensor is the OUTPUT gradient here, so this one is
+// output-centric like x3d_dw3.cu: a ring of three d' planes at output resolution (5 x 15 positions: the 4 x 14 tile
+// plus one row / column towards +h / +w, the only neighbours a transposed stride-2 window reaches) and each thread
+// produces the 2 x 14 INPUT positions under its 1 x 7 output patch.  Which taps reach an input position depends only
+// on its (row, column) parity: 1, 2, 2 or 4 of the 9 spatial taps (27 / 4 per position on average).
+//   dz[ti, 2ho+a, 2wo+b, c] = [a1*y1+b1 > 0] * sum_dt sum_{(dh,ho') in S_a} sum_{(dw,wo') in S_b} d'[ti+1-dt, ho', wo'] w[dt,dh,dw]
+//   S_0 = {(1, o)},  S_1 = {(0, o+1), (2, o)}
+// ---------------------------------------------------------------------------------------
+template <int NPW>
+__global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(const cf_dw_args a, const S2Params p) {
+    constexpr int OTW = S2_PW * NPW, RW = OTW + 1, RH = S2_OTH + 1;
+    constexpr int NPATCH = S2_OTH * NPW, NT = S2_LANES * NPATCH;
+    constexpr int NPOS = RH * RW;
+    constexpr int PLANE = NPOS * S2_CS;
+    constexpr int KPT = (NPOS + NPATCH - 1) / NPATCH;
+    extern __shared__ __align__(16) float sm[];
+    float* ring = sm;                                              // [3][PLANE]
+    float* stg0 = ring + 3 * PLANE;
+    float* stg1 = stg0 + PLANE;
+    float* tabs = stg1 + PLANE;                                    // [5][54]
+    float* ws = tabs + 5 * S2_CS;                                  // [27][54]
+
+    const int tid = threadIdx.x;
+    const int patch = tid / S2_LANES, lane = tid - patch * S2_LANES;
+    const int pr = patch / NPW, pc = patch - pr * NPW;
+    const int C = p.C, T = p.T, Hi = p.Hi, Wi = p.Wi, Ho = p.Ho, Wo = p.Wo;
+    const bool two_src = a.pro_mode == CF_PRO_AFFINE2;
+    const bool drelu = a.epi_mode == CF_EPI_DRELU;
+    const bool need_aux = drelu || a.stats_mode == CF_STATS_SUM_AUX;
+
+    const long long step0 = (long long)blockIdx.x * p.steps_per_cta;
+    const long long step1 = min(step0 + p.steps_per_cta, p.total_steps);
+    for (long long step = step0; step < step1;) {
+        const int col = (int)(step / T);
+        const int t0 = (int)(step - (long long)col * T);
+        const int t1 = (int)min((long long)T, t0 + (step1 - step));
+        step += t1 - t0;
+        int bx = col;
+        const int slab = bx % p.slabs; bx /= p.slabs;
+        const int tw_i = bx % p.wtiles; bx /= p.wtiles;
+        const int th_i = bx % p.htiles;
+        const int b = bx / p.htiles;
+        const int ho0 = th_i * S2_OTH, wo0 = tw_i * OTW;
+        const int cs0 = slab * S2_CS, c0 = cs0 + lane * 2;
+        __syncthreads();
+
+        for (int i = tid; i < S2_CS; i += NT) {
+            const size_t tc = (size_t)b * C + cs0 + i;
+            float ra = 1.f, rb = 0.f, rc = 0.f, ea = 1.f, eb = 0.f;
+            if (a.pro_mode != CF_PRO_NONE) {
+                ra = a.pro_a[tc];
+                rb = a.pro_b ? a.pro_b[tc] : 0.f;
+                rc = a.pro_c ? a.pro_c[tc] : 0.f;
+            }
+            if (drelu) { ea = a.epi_a[tc]; eb = a.epi_b[tc]; }
+            tabs[i] = ra; tabs[S2_CS + i] = rb; tabs[2 * S2_CS + i] = rc; tabs[3 * S2_CS + i] = ea; tabs[4 * S2_CS + i] = eb;
+        }
+        for (int i = tid; i < 27 * S2_CS; i += NT) {
+            const int tap = i / S2_CS, c = i - tap * S2_CS;
+            ws[i] = a.w[(size_t)(cs0 + c) * 27 + tap];
+        }
+        __syncthreads();
+        const float2 ra = *reinterpret_cast<const float2*>(tabs + lane * 2);
+        const float2 rb = *reinterpret_cast<const float2*>(tabs + S2_CS + lane * 2);
+        const float2 rc = *reinterpret_cast<const float2*>(tabs + 2 * S2_CS + lane * 2);
+        const float2 ea = *reinterpret_cast<const float2*>(tabs + 3 * S2_CS + lane * 2);
+        const float2 eb = *reinterpret_cast<const float2*>(tabs + 4 * S2_CS + lane * 2);
+
+        uint32_t vmask = 0;
+        int goff[KPT];
+#pragma unroll
+        for (int k = 0; k < KPT; ++k) {
+            const int pos = patch + k * NPATCH;
+            const int hh = pos / RW, ww = pos - hh * RW;
+            const int h = ho0 + hh, w = wo0 + ww;
+            const bool v = pos < NPOS && h < Ho && w < Wo;
+            goff[k] = v ? (h * Wo + w) * C + c0 : 0;
+            vmask |= v ? (1u << k) : 0u;
+        }
+        const int soff0 = patch * S2_CS + lane * 2;
+        const size_t oframe = (size_t)Ho * Wo * C;
+        auto plane_issue = [&](int t) {
+            if (t < 0 || t >= T) return;
+            const float* f0 = a.x + ((size_t)b * T + t) * oframe;
+            const float* f1 = two_src ? a.x2 + ((size_t)b * T + t) * oframe : nullptr;
+#pragma unroll
+            for (int k = 0; k < KPT; ++k)
+                if (vmask & (1u << k)) {
+                    s2_cp_async8(stg0 + soff0 + k * (NPATCH * S2_CS), f0 + goff[k]);
+                    if (f1) s2_cp_async8(stg1 + soff0 + k * (NPATCH * S2_CS), f1 + goff[k]);
+                }
+        };
+        auto plane_land = [&](int t, float* dst) {
+            const uint32_t m = (t >= 0 && t < T) ? vmask : 0u;
+#pragma unroll
+            for (int k = 0; k < KPT; ++k) {
+                if (patch + k * NPATCH >= NPOS) break;
+                float2 v = make_float2(0.f, 0.f);
+                if (m & (1u << k)) {
+                    const float2 x = *reinterpret_cast<const float2*>(stg0 + soff0 + k * (NPATCH * S2_CS));
+                    if (two_src) {
+                        const float2 x2 = *reinterpret_cast<const float2*>(stg1 + soff0 + k * (NPATCH * S2_CS));
+                        v.x = fmaf(ra.x, x.x, fmaf(rb.x, x2.x, rc.x));
+                        v.y = fmaf(ra.y, x.y, fmaf(rb.y, x2.y, rc.y));
+                    } else if (a.pro_mode != CF_PRO_NONE) {
+                        v.x = fmaf(ra.x, x.x, rb.x);
+                        v.y = fmaf(ra.y, x.y, rb.y);
+                    } else {
+                        v = x;
+                    }
+                }
+                *reinterpret_cast<float2*>(dst + soff0 + k * (NPATCH * S2_CS)) = v;
+            }
+        };
+        auto slot = [&](int t) { return ring + ((t - t0 + 1) % 3) * PLANE; };
+
+        float2 wreg[27];
+#pragma unroll
+        for (int i = 0; i < 27; ++i) wreg[i] = *reinterpret_cast<const float2*>(ws + i * S2_CS + lane * 2);
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+        const int hi_base = 2 * (ho0 + pr), wi_base = 2 * (wo0 + pc * S2_PW);
+        const float* pthr = ring + (pr * RW + pc * S2_PW) * S2_CS + lane * 2;
+
+        plane_issue(t0 - 1);
+        s2_cp_async_wait_all();
+        plane_land(t0 - 1, slot(t0 - 1));
+        plane_issue(t0);
+        s2_cp_async_wait_all();
+        plane_land(t0, slot(t0));
+        plane_issue(t0 + 1);
+
+        for (int ti = t0; ti < t1; ++ti) {
+            s2_cp_async_wait_all();
+            plane_land(ti + 1, slot(ti + 1));
+            __syncthreads();
+            if (ti + 2 <= t1) plane_issue(ti + 2);
+
+            const int sl0 = (ti - t0) % 3;                         // slot of plane ti-1
+            float2 aux[2][2 * S2_PW];
+            if (need_aux) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int j = 0; j < 2 * S2_PW; ++j) {
+                        const bool v = hi_base + r < Hi && wi_base + j < Wi;
+                        aux[r][j] = v ? __ldg(reinterpret_cast<const float2*>(
+                                            a.aux + ((((size_t)b * T + ti) * Hi + hi_base + r) * Wi + wi_base + j) * C + c0))
+                                      : make_float2(0.f, 0.f);
+                    }
+            }
+            float2 acc[2][2 * S2_PW];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int j = 0; j < 2 * S2_PW; ++j) acc[r][j] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int dt = 0; dt < 3; ++dt) {
+                // tap dt reads d' frame ti + 1 - dt: dt = 0 -> ti+1 (slot sl0+2), 1 -> ti (sl0+1), 2 -> ti-1 (sl0)
+                const float* pl = pthr + ((sl0 + 2 - dt) % 3) * PLANE;
+                float2 in0[S2_PW + 1], in1[S2_PW + 1];
+#pragma unroll
+                for (int j = 0; j < S2_PW + 1; ++j) {
+                    in0[j] = *reinterpret_cast<const float2*>(pl + j * S2_CS);
+                    in1[j] = *reinterpret_cast<const float2*>(pl + (RW + j) * S2_CS);
+                }
+                const float2* w = wreg + dt * 9;                   // w[dh * 3 + dw]
+#define S2_FMA(ACC, X, WV) do { ACC.x = fmaf(X.x, WV.x, ACC.x); ACC.y = fmaf(X.y, WV.y, ACC.y); } while (0)
+#pragma unroll
+                for (int j = 0; j < S2_PW; ++j) {
+                    S2_FMA(acc[0][2 * j], in0[j], w[1 * 3 + 1]);                                   // even row, even col
+                    S2_FMA(acc[0][2 * j + 1], in0[j + 1], w[1 * 3 + 0]);                           // even row, odd col
+                    S2_FMA(acc[0][2 * j + 1], in0[j], w[1 * 3 + 2]);
+                    S2_FMA(acc[1][2 * j], in1[j], w[0 * 3 + 1]);                                   // odd row, even col
+                    S2_FMA(acc[1][2 * j], in0[j], w[2 * 3 + 1]);
+                    S2_FMA(acc[1][2 * j + 1], in1[j + 1], w[0 * 3 + 0]);                           // odd row, odd col
+                    S2_FMA(acc[1][2 * j + 1], in1[j], w[0 * 3 + 2]);
+                    S2_FMA(acc[1][2 * j + 1], in0[j + 1], w[2 * 3 + 0]);
+                    S2_FMA(acc[1][2 * j + 1], in0[j], w[2 * 3 + 2]);
+                }
+#undef S2_FMA
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (hi_base + r >= Hi) continue;
+#pragma unroll
+                for (int j = 0; j < 2 * S2_PW; ++j) {
+                    if (wi_base + j >= Wi) continue;
+                    float2 v = acc[r][j];
+                    if (drelu) {
+                        v.x = fmaf(ea.x, aux[r][j].x, eb.x) > 0.f ? v.x : 0.f;
+                        v.y = fmaf(ea.y, aux[r][j].y, eb.y) > 0.f ? v.y : 0.f;
+                    }
+                    *reinterpret_cast<float2*>(a.y + ((((size_t)b * T + ti) * Hi + hi_base + r) * Wi + wi_base + j) * C + c0) = v;
+                    s1.x += v.x; s1.y += v.y;
+                    if (need_aux) { s2.x = fmaf(v.x, aux[r][j].x, s2.x); s2.y = fmaf(v.y, aux[r][j].y, s2.y); }
+                }
+            }
+            __syncthreads();
+        }
+        s2_cp_async_wait_all();
+
+        if (a.stats_mode != CF_STATS_NONE) {
+            float* red = ring;
+            *reinterpret_cast<float2*>(red + patch * 2 * S2_CS + lane * 2) = s1;
+            *reinterpret_cast<float2*>(red + (patch * 2 + 1) * S2_CS + lane * 2) = s2;
+            __syncthreads();
+            for (int i = tid; i < 2 * S2_CS; i += NT) {
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < NPATCH; ++q) s += red[q * 2 * S2_CS + i];
+                const int which = i / S2_CS, c = i - which * S2_CS;
+                atomicAdd(a.stats + ((size_t)b * C + cs0 + c) * 2 + which, (double)s);
+            }
+        }
+    }   // pieces
+}
+
+template <int NPW>
+static int s2_launch_dgrad(const cf_dw_args* a, const S2Params& p, cudaStream_t stream) {
+    constexpr int OTW = S2_PW * NPW;
+    constexpr int PLANE = (S2_OTH + 1) * (OTW + 1) * S2_CS;
+    const size_t smem = (size_t)(5 * PLANE + 5 * S2_CS + 27 * S2_CS) * sizeof(float);
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(dw3s2_dgrad_kernel<NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) { cf_set_error("dw3s2: cannot opt in to shared memory: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
+        done = true;
+    }
+    dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
+    dw3s2_dgrad_kernel<NPW><<<grid, S2_LANES * S2_OTH * NPW, smem, stream>>>(*a, p);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 template <int MODE, int NPW>
 static int s2_launch(const cf_dw_args* a, const S2Params& p, cudaStream_t stream) {
     constexpr int OTW = S2_PW * NPW, IW = 2 * OTW + 1;
@@ -306,7 +542,7 @@ static int s2_launch(const cf_dw_args* a, const S2Params& p, cudaStream_t stream
     return CF_OK;
 }
 
-// mode: 0 forward, 2 weight gradient.  Returns CF_OK when launched, -1 when not eligible.
+// mode: 0 forward, 1 data gradient, 2 weight gradient.  Returns CF_OK when launched, -1 when not eligible.
 int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     static int disabled = -1;
     if (disabled < 0) {
@@ -323,7 +559,8 @@ int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (al & 7) return -1;
     if (mode == S2_FWD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE_RELU)) return -1;
     if (mode == S2_FWD && a->stats_mode == CF_STATS_SUM_AUX) return -1;
-    if (mode == S2_WGRAD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE2)) return -1;
+    if (mode != S2_FWD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE2)) return -1;
+    if (mode == 1 && a->stats_mode == CF_STATS_SUM_SQ) return -1;
     S2Params p;
     p.B = a->B; p.C = a->C; p.T = g.T; p.Hi = g.Hi; p.Wi = g.Wi; p.Ho = g.H; p.Wo = g.W;
     const int npw = g.W == 7 ? 1 : 2;
@@ -340,6 +577,7 @@ int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     long long spc = (p.total_steps + nsm - 1) / nsm;
     if (spc < 4) spc = 4;
     p.steps_per_cta = (int)spc;
+    if (mode == 1) return npw == 1 ? s2_launch_dgrad<1>(a, p, stream) : s2_launch_dgrad<2>(a, p, stream);
     if (npw == 1) return mode == S2_FWD ? s2_launch<S2_FWD, 1>(a, p, stream) : s2_launch<S2_WGRAD, 1>(a, p, stream);
     return mode == S2_FWD ? s2_launch<S2_FWD, 2>(a, p, stream) : s2_launch<S2_WGRAD, 2>(a, p, stream);
 }
