@@ -310,7 +310,8 @@ class TrainWorkload:
         return c
 
     def roofline(self, peaks, flush):
-        """Dominant kernel = the pointwise-conv GEMM (pw_conv_kernel); timed on its largest launch of the
+        """Dominant kernel = the persistent tcgen05 pointwise-conv GEMM (pw_tc2_kernel, 21 % of the step in
+        profiles/r01_launches_coarse_fine_v4.md); timed on its largest launch of the
         step: fine-stream layer1.0.conv1 (24 -> 54 channels at 112x112, all B*Tf frames) with the BatchNorm
         statistics epilogue.  Algorithmic bytes = read x once + write y once (weights 5 KB)."""
         from coarse_fine_networks_b200 import x3d_ops as X
@@ -323,7 +324,7 @@ class TrainWorkload:
         ms = time_kernel(lambda: X.pw_conv(x, w, y, B, K, N, g, stats=stats, stats_mode=X.STATS_SUM_SQ), flush)
         alg = B * T * H * W * (K + N) * 4
         ach = alg / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": "pw_conv_kernel<64,false> (layer1.0.conv1 24->54 @112x112, BN-stat epilogue)",
+        return {"bound": "hbm", "kernel": "pw_tc2_kernel (tcgen05 3xTF32; layer1.0.conv1 24->54 @112x112, all B*Tf frames, BN-stat epilogue)",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                 "peak_basis": peaks["basis"], "algorithmic_bytes": alg, "kernel_ms": ms}
 
