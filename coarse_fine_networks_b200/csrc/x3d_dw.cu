@@ -680,7 +680,8 @@ static int dw_common_checks(const cf_dw_args* a) {
 }
 
 int cf_dw3_try(int mode, const cf_dw_args* a, cudaStream_t stream);   // x3d_dw3.cu: plane-marching 3x3x3 stride-1 kernels (-1: not eligible)
-int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream); // x3d_dw3s2.cu: spatial stride 2, forward (0) and weight gradient (2)
+int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream); // x3d_dw3s2.cu: spatial stride 2
+int cf_dwt5_try(int mode, const cf_dw_args* a, cudaStream_t stream);  // x3d_dwt5.cu: temporal 5x1x1 (stem conv1_t)
 
 extern "C" int cf_dw_conv_fwd(const cf_dw_args* a, cudaStream_t stream) {
     int rc = dw_common_checks(a);
@@ -689,6 +690,8 @@ extern "C" int cf_dw_conv_fwd(const cf_dw_args* a, cudaStream_t stream) {
     rc = cf_dw3_try(0, a, stream);
     if (rc >= 0) return rc;
     rc = cf_dw3s2_try(0, a, stream);
+    if (rc >= 0) return rc;
+    rc = cf_dwt5_try(0, a, stream);
     if (rc >= 0) return rc;
     int v = pick_vec(a->C, a->x, a->y);
     if (v == 4) return launch_dw_fwd<4>(a, stream);
@@ -704,6 +707,8 @@ extern "C" int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     rc = cf_dw3_try(1, a, stream);
     if (rc >= 0) return rc;
     rc = cf_dw3s2_try(1, a, stream);
+    if (rc >= 0) return rc;
+    rc = cf_dwt5_try(1, a, stream);
     if (rc >= 0) return rc;
     int v = pick_vec(a->C, a->x, a->y);
     if (a->x2 && (((uintptr_t)a->x2) & 15)) v = v > 2 ? 2 : v;
@@ -727,6 +732,8 @@ extern "C" int cf_dw_conv_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     rc = cf_dw3_try(2, a, stream);
     if (rc >= 0) return rc;
     rc = cf_dw3s2_try(2, a, stream);
+    if (rc >= 0) return rc;
+    rc = cf_dwt5_try(2, a, stream);
     if (rc >= 0) return rc;
     int taps = a->g.kt * a->g.kh * a->g.kw;
     int v = pick_vec(a->C, a->x, a->aux);

@@ -76,3 +76,23 @@ for name, C, T, H, W, s in CASES:
         ms = timeit(fn)
         print(f"{name:28s} {kind:6s} {ms*1e3:9.1f} us  {byt/ms/1e6:8.1f} GB/s  {100*byt/ms/1e6/peak:5.1f}% of measured HBM peak")
     del y1, y2, dU, out, dz1
+
+# ---- stem temporal 5x1x1 depthwise (conv1_t): 24 channels at 112x112
+if not only or "stem" in only:
+    C, T, H, W = 24, 256, 112, 112
+    g = X.geom(T, H, W, k=(5, 1, 1), p=(2, 0, 0))
+    y0 = torch.randn(B, C, T, H, W, device=dev).contiguous(memory_format=CL3)
+    yt = torch.randn_like(y0)
+    dz = torch.randn_like(y0)
+    out = torch.empty_like(y0)
+    w = torch.randn(C, 5, device=dev) * 0.3
+    tabs = [torch.randn(B, C, device=dev) for _ in range(3)]
+    stats = torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
+    dw = torch.zeros(C, 5, device=dev)
+    n = y0.numel()
+    for kind, fn, byt in [
+        ("fwd", lambda: X.dw_call("cf_dw_conv_fwd", y0, w, out, B, C, g, stats=stats, stats_mode=X.STATS_SUM_SQ), 8 * n),
+        ("dgrad", lambda: X.dw_call("cf_dw_conv_dgrad", dz, w, out, B, C, g, x2=yt, pro=X.PRO_AFFINE2, pro_tabs=tuple(tabs)), 12 * n),
+        ("wgrad", lambda: X.dw_call("cf_dw_conv_wgrad", dz, w, dw, B, C, g, x2=yt, pro=X.PRO_AFFINE2, pro_tabs=tuple(tabs), aux=y0), 12 * n)]:
+        ms = timeit(fn)
+        print(f"{'stem conv1_t 24ch 112x112':28s} {kind:6s} {ms*1e3:9.1f} us  {byt/ms/1e6:8.1f} GB/s  {100*byt/ms/1e6/peak:5.1f}% of measured HBM peak")
