@@ -328,6 +328,8 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const cf_pw_wgrad_args a,
 // ---------------------------------------------------------------------------------------
 int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream);      // x3d_pw_tc2.cu
 int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream);   // x3d_pw_wgrad_tc.cu (-1: not eligible)
+int cf_stem_fwd_try(const cf_pw_args* a, cudaStream_t stream);         // x3d_stem.cu (-1: not the stem conv)
+int cf_stem_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream);
 
 extern "C" size_t cf_sizeof_pw_args(void) { return sizeof(cf_pw_args); }
 size_t cf_sizeof_pw_wgrad_args(void) { return sizeof(cf_pw_wgrad_args); }
@@ -374,6 +376,8 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
     int R = a->g.T * a->g.H * a->g.W;
     if (a->wpack && !a->gather_in && !a->scatter_out) return cf_pw_conv_tc(a, stream);
     if (a->gather_in) {
+        int rcs = cf_stem_fwd_try(a, stream);               // conv1_s: specialised kernel
+        if (rcs >= 0) return rcs;
         if (a->N <= 32) return launch_pw<32, true>(a, R, stream);
         if (a->N <= 64) return launch_pw<64, true>(a, R, stream);
         return launch_pw<128, true>(a, R, stream);
@@ -393,6 +397,8 @@ extern "C" int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(!a->gather_in || a->K % taps == 0, "K must be channels*taps");
     {
         int rc = cf_pw_wgrad_tc(a, stream);                 // dense problems: tensor cores
+        if (rc >= 0) return rc;
+        rc = cf_stem_wgrad_try(a, stream);                  // conv1_s: specialised kernel
         if (rc >= 0) return rc;
     }
     int R = a->g.T * a->g.H * a->g.W;

@@ -164,6 +164,26 @@ def test_dense_conv_through_tap_gather(X):
     dx = torch.zeros(B, 3, T, H, W, device="cuda")
     X.pw_conv(rows(gy), w.cuda(), dx, B, 24, 27, g, w_sn=1, w_sk=27, scatter_out=1)
     close(dx, xr.grad, rtol=1e-5, atol=1e-5, what="conv1_s dgrad")
+    # the specialised stem kernels (x3d_stem.cu) on a temporal WINDOW of a longer clip (the coarse stream reads frames
+    # a..b of the fine stream's clip in place), odd sizes, more than one 64-position tile
+    Tf, a0, Tw, H2, W2 = 7, 2, 4, 23, 17
+    xf = synth_tensor((B, 3, Tf, H2, W2), 44)
+    xw = xf[:, :, a0:a0 + Tw]
+    ref2 = F.conv3d(xw, w, stride=(1, 2, 2), padding=(0, 1, 1))
+    Ho2, Wo2 = ref2.shape[3], ref2.shape[4]
+    xc = xf.cuda()
+    xv = xc[:, :, a0:a0 + Tw]
+    g2 = X.geom(Tw, Ho2, Wo2, Tw, H2, W2, k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1), pos_stride=1, ch_stride=xv.stride(1),
+                sample_stride=xv.stride(0))
+    y2 = X.new_act(B, 24, Tw, Ho2, Wo2, "cuda")
+    X.pw_conv(xv, w.cuda(), y2, B, 27, 24, g2, gather_in=1)
+    close(y2, ref2, rtol=1e-5, atol=1e-5, what="conv1_s window")
+    gy2 = synth_tensor(tuple(ref2.shape), 45)
+    xr2, wr2 = xw.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    F.conv3d(xr2, wr2, stride=(1, 2, 2), padding=(0, 1, 1)).backward(gy2)
+    dw2 = torch.zeros(24, 27, device="cuda")
+    X.pw_wgrad(rows(gy2), xv, dw2, B, 27, 24, g2, gather_in=1)
+    close(dw2, wr2.grad.flatten(1), rtol=1e-5, atol=1e-4, what="conv1_s window wgrad")
     # channels-last 3x3x3 stride (2,2,2) conv, 8 -> 8 channels
     C = 8
     x = synth_tensor((B, C, 6, 9, 9), 44)
