@@ -322,10 +322,16 @@ class TrainWorkload:
         stats = torch.zeros(B, N, 2, device=self.device, dtype=torch.float64)
         g = X.geom(T, H, W)
         ms = time_kernel(lambda: X.pw_conv(x, w, y, B, K, N, g, stats=stats, stats_mode=X.STATS_SUM_SQ), flush)
-        alg = B * T * H * W * (K + N) * 4
+        rows = B * T * H * W
+        alg = rows * (K + N) * 4
         ach = alg / (ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from `ncu --set full` (profiles/r01_full_pw_tc2.md:
+        # 309.5 + 637.5 MB for 3 211 264 rows of the same 24 -> 54 problem = 294.9 B per row against 312 algorithmic:
+        # no re-reads; the difference is output still in L2 when the kernel ends), scaled to this launch's rows
+        traffic = 294.9 * rows
         return {"bound": "hbm", "kernel": "pw_tc2_kernel (tcgen05 3xTF32; layer1.0.conv1 24->54 @112x112, all B*Tf frames, BN-stat epilogue)",
-                "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_basis": "ncu --set full, r01_full_pw_tc2.md, per-row figure x rows of this launch",
                 "peak_basis": peaks["basis"], "algorithmic_bytes": alg, "kernel_ms": ms}
 
     # ---- the reference algorithm on the host CPU (oracle port), one bounded sample per step
