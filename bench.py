@@ -458,6 +458,11 @@ def main():
 
     import torch.distributed as dist
     import __graft_entry__ as ge
+    # libraries (NCCL prints its version banner on stdout) must not get between the driver and the ONE JSON line:
+    # everything written to fd 1 from here on goes to stderr; the line itself is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -544,7 +549,8 @@ def main():
                 "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": cfg,
                 "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
                 "clocks": clocks, "roofline": roof, "gridpool_roofline": gp, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
