@@ -127,7 +127,7 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
         if (mbar_try(addr, parity)) return;
 #pragma unroll 1
     for (int spin = 0; spin < (1 << 22); ++spin) {
-        __nanosleep(40);
+        __nanosleep(128);
         if (mbar_try(addr, parity)) return;
     }
     __trap();

@@ -7,14 +7,14 @@
 // 3xTF32 arithmetic as the one-tile-per-CTA kernel in x3d_pw_tc.cu (which measured 16-21 % of HBM peak: one
 // CTA did load -> MMA -> epilogue strictly in sequence with 12 KB of loads in flight per SM).  Here:
 //
-//   * one CTA per SM walks the (row tile, channel tile) list; 20 warps in three roles that only meet at mbarriers (register budgets
-//     rebalanced per role with setmaxnreg: 120 / 32 / 104):
-//       warps 0-7   producers: global loads of the next 3 (1 with a second input) activation chunks are in
+//   * one CTA per SM walks the (row tile, channel tile) list; 28 warps in three roles that only meet at mbarriers (register budgets
+//     rebalanced per role with setmaxnreg: 72 / 24 / 96):
+//       warps 0-15  producers: global loads of the next 3 (1 with a second input) activation chunks are in
 //                   flight in registers while the current one gets its BatchNorm/ReLU/Swish/BN-backward
 //                   prologue, the hi/lo TF32 split and the SWIZZLE_128B store into a ring of A stages;
-//       warp  8     MMA issuer: the warp walks the stages convergently, one elected lane issues the tcgen05.mma's
+//       warp  16    MMA issuer: the warp walks the stages convergently, one elected lane issues the tcgen05.mma's
 //                   (3 per 8 k) into one of two TMEM accumulators and commits stage-free / accumulator-full barriers;
-//       warps 12-19 epilogue: two groups of four warps (one per TMEM lane quadrant) take alternate 32-column
+//       warps 20-27 epilogue: two groups of four warps (one per TMEM lane quadrant) take alternate 32-column
 //                   slabs: tcgen05.ld -> padded shared slab -> coalesced row-major stores with bias /
 //                   activation derivative / residual add and the BatchNorm statistics;
 //     so the loads of tile i+1, the MMAs of tile i and the stores of tile i-1 overlap;
@@ -28,18 +28,19 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 
-#define P2_PROD_WARPS 8
+#define P2_PROD_WARPS 16
+#define P2_PROD_PASSES (TC_BM / (P2_PROD_WARPS * 4))   /* rows per thread and chunk: 128 rows / (warps x 4 rows per warp) */
 #define P2_EPI_WARPS 8
 #define P2_PROD_THREADS (P2_PROD_WARPS * 32)
 #define P2_EPI_THREADS (P2_EPI_WARPS * 32)
 #define P2_MMA_WARP P2_PROD_WARPS
 #define P2_EPI_WARP0 (P2_PROD_WARPS + 4)          /* roles are warpgroup (4-warp) aligned for setmaxnreg */
 #define P2_THREADS ((P2_PROD_WARPS + 4 + P2_EPI_WARPS) * 32)
-// register budgets after setmaxnreg: registers only move WITHIN the CTA's launch allocation (640 threads x 96 = 61440),
-// an .inc beyond it waits forever: 256 x 120 + 128 x 32 + 256 x 104 = 61440
-#define P2_REGS_PROD 120
-#define P2_REGS_MMA 32
-#define P2_REGS_EPI 104
+// register budgets after setmaxnreg: registers only move WITHIN the CTA's launch allocation (896 threads x 72 = 64512),
+// an .inc beyond it waits forever: 512 x 72 + 128 x 24 + 256 x 96 = 64512
+#define P2_REGS_PROD 72
+#define P2_REGS_MMA 24
+#define P2_REGS_EPI 96
 #define P2_A_STAGE (2 * TC_BM * TC_KC * 4) /* hi + lo: 32 KB */
 #define P2_CS_LD 36
 #define P2_CS_FLOATS (TC_BM * P2_CS_LD)
@@ -50,8 +51,17 @@
 
 // cycle counters of CTA 0 (CFNET_PW_TC_TIMING=1; read back with cf_pw_tc_debug_read): where each role's time goes
 __device__ long long p2_dbg[32];
+// (compiled in only with -DCFNET_P2_TIMING: the 8 counters cost 16 registers per thread, which the 72-register producers
+// do not have)
+#ifdef CFNET_P2_TIMING
 #define P2_T0() (p.timing ? clock64() : 0)
 #define P2_ACC(slot, t0) do { if (p.timing) { long long t1__ = clock64(); tacc[slot] += t1__ - (t0); (t0) = t1__; } } while (0)
+#define P2_TIMING_ON 1
+#else
+#define P2_T0() 0
+#define P2_ACC(slot, t0) do { } while (0)
+#define P2_TIMING_ON 0
+#endif
 
 struct P2Params {
     int B, R, tps, ntiles, NT, NTp, nchunks, nstages, resident, acc_stride, KP, g_j, g_rt, timing, dbg_1x;
@@ -149,17 +159,18 @@ __device__ __forceinline__ void p2_advance(P2Item& it, const P2Params& p) {
 // ---------------------------------------------------------------------------------------
 template <int AV, bool X2>
 __device__ __forceinline__ void p2_load_item(const cf_pw_args& a, const P2Params& p, const P2Item& it, int q, int rr,
-                                             float (&v)[4][4], float (&v2)[X2 ? 4 : 1][4]) {
+                                             float (&v)[P2_PROD_PASSES][4], float (&v2)[X2 ? P2_PROD_PASSES : 1][4]) {
     const int K = a.K;
     const int k = it.c * TC_KC + q * 4;
     const int rows_valid = min(TC_BM, p.R - it.r0);
     const size_t off = ((size_t)it.b * p.R + it.r0 + rr) * K + k;
     const float* xp = a.x + off;
     const float* x2p = X2 ? a.x2 + off : nullptr;
-    const size_t step = (size_t)32 * K;
+    constexpr int RPP = P2_PROD_WARPS * 4;                        // rows per pass
+    const size_t step = (size_t)RPP * K;
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp, xp += step, x2p += X2 ? step : 0) {
-        const bool rv = pp * 32 + rr < rows_valid;
+    for (int pp = 0; pp < P2_PROD_PASSES; ++pp, xp += step, x2p += X2 ? step : 0) {
+        const bool rv = pp * RPP + rr < rows_valid;
 #pragma unroll
         for (int e = 0; e < 4; e += AV) {
             if (rv && k + e < K) {
@@ -180,11 +191,11 @@ template <int AV, int PRO>
 __device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params& p, uint8_t* stages, float* tab, uint64_t* full,
                                             uint64_t* empty, const float* __restrict__ pack, int tid) {
     constexpr bool X2 = PRO == CF_PRO_AFFINE2;
-    constexpr int NSET = X2 ? 2 : 4;
+    constexpr int NSET = X2 ? 2 : 3;                              // register sets of loads in flight (8 / 16 floats each)
     const int lane = tid & 31;
     const int q = tid & 7, rr = tid >> 3;
-    float v[NSET][4][4];
-    float v2[NSET][X2 ? 4 : 1][4];
+    float v[NSET][P2_PROD_PASSES][4];
+    float v2[NSET][X2 ? P2_PROD_PASSES : 1][4];
     P2Item ld, pr;
     p2_first(ld, p);
     pr = ld;
@@ -198,9 +209,11 @@ __device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params&
     int cur_b = -1;
     int s = 0;
     uint32_t ph = 0;
+#ifdef CFNET_P2_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tt = P2_T0();
     const long long tstart = tt;
+#endif
     while (pr.valid) {
 #pragma unroll
         for (int u = 0; u < NSET; ++u) {
@@ -246,8 +259,8 @@ __device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params&
             uint8_t* a_hi = stage;
             uint8_t* a_lo = stage + TC_BM * TC_KC * 4;
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                const int row = pp * 32 + rr;
+            for (int pp = 0; pp < P2_PROD_PASSES; ++pp) {
+                const int row = pp * (P2_PROD_WARPS * 4) + rr;
                 float hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -273,10 +286,12 @@ __device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params&
             p2_advance(pr, p);
         }
     }
+#ifdef CFNET_P2_TIMING
     if (p.timing && blockIdx.x == 0 && tid == 0) {
         for (int i = 0; i < 5; ++i) p2_dbg[i] = tacc[i];
         p2_dbg[7] = clock64() - tstart;
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -299,9 +314,11 @@ __device__ __forceinline__ void p2_mma_warp(const cf_pw_args& a, const P2Params&
     const uint64_t blo_off = (uint64_t)(((uint32_t)p.NTp * 128u) >> 4);    // B lo tile follows B hi
     const uint64_t stages_desc = make_desc_sw128(smem_u32(stages));
     const uint64_t wres_desc = make_desc_sw128(smem_u32(wres));
+#ifdef CFNET_P2_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tt = P2_T0();
     const long long tstart = tt;
+#endif
     if (p.resident) mbar_wait_b(wres_bar, 0u);
     int s = 0;
     uint32_t ph = 0, tcount = 0;
@@ -344,10 +361,12 @@ __device__ __forceinline__ void p2_mma_warp(const cf_pw_args& a, const P2Params&
             if (++s == p.nstages) { s = 0; ph ^= 1u; }
         }
     }
+#ifdef CFNET_P2_TIMING
     if (p.timing && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
         for (int i = 0; i < 4; ++i) p2_dbg[16 + i] = tacc[i];
         p2_dbg[20] = clock64() - tstart;
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -485,9 +504,11 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
     const int nslabs = (p.NTp + 31) >> 5;
     int cur_b = -1;
     uint32_t tcount = 0;
+#ifdef CFNET_P2_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tt = P2_T0();
     const long long tstart = tt;
+#endif
     P2Item it;
     for (p2_first(it, p); it.valid; p2_next_tile(it, p), ++tcount) {
         if (SMODE != CF_STATS_NONE && it.b != cur_b) {
@@ -548,10 +569,12 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
         }
     }
     if (SMODE != CF_STATS_NONE && cur_b >= 0) p2_flush_stats(a, red, cur_b, et);
+#ifdef CFNET_P2_TIMING
     if (p.timing && blockIdx.x == 0 && et == 0) {
         for (int i = 0; i < 7; ++i) p2_dbg[8 + i] = tacc[i];
         p2_dbg[15] = clock64() - tstart;
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -599,7 +622,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
 
     if (warp < P2_PROD_WARPS) {
         // ================= producers =================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_REGS_PROD));
 #define P2_PARGS a, p, stages, tab, full, empty, pack, tid
         if (p.resident && tid == 0) {
             mbar_expect_tx(&wres_bar, (uint32_t)p.nchunks * p.b_chunk_bytes);
