@@ -47,7 +47,7 @@
 #define P2_MAX_STAGES 4
 #define P2_RED_N 512
 #define P2_NT_MAX 224
-#define P2_SMEM_MAX (222 * 1024) /* dynamic; + ~4.2 KB static stays under the 227 KB per-CTA limit */
+#define P2_SMEM_MAX (210 * 1024) /* dynamic; + ~16.5 KB static (statistics table) stays under the 227 KB per-CTA limit */
 
 // cycle counters of CTA 0 (CFNET_PW_TC_TIMING=1; read back with cf_pw_tc_debug_read): where each role's time goes
 __device__ long long p2_dbg[32];
@@ -439,7 +439,7 @@ __device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const float* 
 }
 
 template <int EV, int EPI, int SMODE>
-__device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const float* __restrict__ Cs, float* __restrict__ scr, int b,
+__device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const float* __restrict__ Cs, float* __restrict__ redw, int b,
                                               int r0, int rows_valid, int R, int n0, int col0, int nvalid, int gt) {
     constexpr int CPR = 32 / EV;             // column groups per row
     constexpr int RPP = 128 / CPR;           // rows per pass
@@ -468,11 +468,23 @@ __device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const float* 
         else
             p2_store_rows<EV, EPI, SMODE, false>(a, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
     }
-    if (SMODE != CF_STATS_NONE) {            // partial column sums of this thread's rows; reduced after the group barrier
+    if (SMODE != CF_STATS_NONE) {
+        // column sums: the 32 / CPR row groups of a warp meet by shuffle, then the first CPR lanes add into THIS WARP's
+        // row of the per-CTA table (a slab belongs to one group, a table row to one warp: no atomics, no barrier)
 #pragma unroll
-        for (int e = 0; e < EV; ++e) {
-            scr[(rs * 32 + cg * EV + e) * 2] = s1[e];
-            scr[(rs * 32 + cg * EV + e) * 2 + 1] = s2[e];
+        for (int o = CPR; o < 32; o <<= 1)
+#pragma unroll
+            for (int e = 0; e < EV; ++e) {
+                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+            }
+        if (active && (gt & 31) < CPR) {
+            float* r1 = redw + n0 + nl;
+#pragma unroll
+            for (int e = 0; e < EV; ++e) {
+                r1[e] += s1[e];
+                r1[P2_RED_N + e] += s2[e];
+            }
         }
     }
 }
@@ -480,17 +492,23 @@ __device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const float* 
 __device__ __forceinline__ void p2_flush_stats(const cf_pw_args& a, float* red, int b, int et) {
     named_bar_sync(4, P2_EPI_THREADS);
     for (int i = et; i < a.N; i += P2_EPI_THREADS) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            t1 += red[w * 2 * P2_RED_N + i];
+            t2 += red[w * 2 * P2_RED_N + P2_RED_N + i];
+            red[w * 2 * P2_RED_N + i] = 0.f;
+            red[w * 2 * P2_RED_N + P2_RED_N + i] = 0.f;
+        }
         double* st = a.stats + ((size_t)b * a.N + i) * 2;
-        atomicAdd(st, (double)red[i]);
-        atomicAdd(st + 1, (double)red[P2_RED_N + i]);
-        red[i] = 0.f;
-        red[P2_RED_N + i] = 0.f;
+        atomicAdd(st, (double)t1);
+        atomicAdd(st + 1, (double)t2);
     }
     named_bar_sync(4, P2_EPI_THREADS);
 }
 
 template <int EV, int EPI, int SMODE>
-__device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params& p, float* Cs_all, float* scr_all, float* red,
+__device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params& p, float* Cs_all, float* red,
                                             uint64_t* tfull, uint64_t* tempty, uint32_t tmem, int warp, int lane) {
     constexpr int RPP = 128 / (32 / EV);
     const int ew = warp - P2_EPI_WARP0;
@@ -499,7 +517,7 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
     const int gt = (ew & 3) * 32 + lane;                     // thread index within the group (phase 2)
     const int et = ew * 32 + lane;
     float* Cs = Cs_all + grp * P2_CS_FLOATS;
-    float* scr = scr_all + grp * P2_SCR_FLOATS;
+    float* redw = red + (ew & 3) * 2 * P2_RED_N;                // this warp's row of the statistics table
     const int row_own = qd * 32 + lane;
     const int nslabs = (p.NTp + 31) >> 5;
     int cur_b = -1;
@@ -534,7 +552,7 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
                 if (lane == 0) mbar_arrive(&tempty[acc]);
             }
             P2_ACC(2, tt);                                   // 2: tcgen05.ld + release
-            named_bar_sync(2 + grp, 128);                    // the previous slab's readers are done with Cs and scr
+            named_bar_sync(2 + grp, 128);                    // the previous slab's readers are done with Cs
             P2_ACC(3, tt);                                   // 3: group barriers
             float* dst = Cs + row_own * P2_CS_LD;
 #pragma unroll
@@ -543,24 +561,8 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
             P2_ACC(4, tt);                                   // 4: accumulator rows -> shared slab
             named_bar_sync(2 + grp, 128);
             P2_ACC(3, tt);
-            p2_store_slab<EV, EPI, SMODE>(a, Cs, scr, it.b, it.r0, rows_valid, p.R, n0, slab * 32, nvalid, gt);
+            p2_store_slab<EV, EPI, SMODE>(a, Cs, redw, it.b, it.r0, rows_valid, p.R, n0, slab * 32, nvalid, gt);
             P2_ACC(5, tt);                                   // 5: slab -> global (+ aux, activation, statistics partials)
-            if (SMODE != CF_STATS_NONE) {
-                // column sums over the rows-per-pass partials: one owner thread per (column, statistic) -- a slab belongs
-                // to exactly one group, so the per-CTA table needs no atomics (shared fp32 atomics are CAS loops)
-                named_bar_sync(2 + grp, 128);
-                P2_ACC(3, tt);
-                if (gt < 64) {
-                    const int col = gt >> 1, st = gt & 1;
-                    if (slab * 32 + col < nvalid) {
-                        float sum = 0.f;
-#pragma unroll
-                        for (int r = 0; r < RPP; ++r) sum += scr[(r * 32 + col) * 2 + st];
-                        red[st * P2_RED_N + n0 + slab * 32 + col] += sum;
-                    }
-                }
-                P2_ACC(6, tt);                               // 6: statistics reduction
-            }
         }
         if (grp >= nslabs) {                                 // a group without slabs still releases the accumulator
             tc_fence_before();
@@ -589,14 +591,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
     __shared__ __align__(8) uint64_t tempty[2];
     __shared__ __align__(8) uint64_t wres_bar;
     __shared__ uint32_t tmem_addr_s;
-    __shared__ float red[2 * P2_RED_N];
+    __shared__ float red[4 * 2 * P2_RED_N];                          // [epilogue warp in group][sum, sum2][channel]
 
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B tiles: 1024-B aligned
     uint8_t* stages = base;
     uint8_t* wres = stages + (size_t)p.nstages * p.stage_bytes;
     float* Cs = reinterpret_cast<float*>(wres + (p.resident ? (size_t)p.nchunks * p.b_chunk_bytes : 0));
-    float* scr = Cs + 2 * P2_CS_FLOATS;
-    float* tab = scr + 2 * P2_SCR_FLOATS;
+    float* tab = Cs + 2 * P2_CS_FLOATS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
         mbar_init(&wres_bar, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < 2 * P2_RED_N; i += P2_THREADS) red[i] = 0.f;
+    for (int i = tid; i < 4 * 2 * P2_RED_N; i += P2_THREADS) red[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
     } else {
         // ================= epilogue =================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_REGS_EPI));
-#define P2_EARGS a, p, Cs, scr, red, tfull, tempty, tmem, warp, lane
+#define P2_EARGS a, p, Cs, red, tfull, tempty, tmem, warp, lane
 #define P2_EPI_S(EV_, EPI_)                                                                  \
     switch (a.stats_mode) {                                                                  \
         case CF_STATS_SUM_SQ: p2_epilogue<EV_, EPI_, CF_STATS_SUM_SQ>(P2_EARGS); break;      \
@@ -780,7 +781,7 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
             p2_tiling(K, N, p, nt_try[ti]);
             p.total_tiles = (long long)a->B * p.tps * p.ntiles;
         }
-        const size_t fixed = 1024 + 2 * (size_t)(P2_CS_FLOATS + P2_SCR_FLOATS) * 4 + 3 * (size_t)p.KP * 4;
+        const size_t fixed = 1024 + 2 * (size_t)P2_CS_FLOATS * 4 + 3 * (size_t)p.KP * 4;
         if (fixed + 2 * (size_t)P2_A_STAGE >= P2_SMEM_MAX) break;
         const size_t avail = P2_SMEM_MAX - fixed;
         const size_t wres_bytes = (size_t)p.nchunks * p.b_chunk_bytes;
@@ -802,6 +803,17 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
         }
     }
     CF_CHECK_ARG(planned, "K too large for the tensor-core path");
+    // Keep some L1: the unified L1/shared array is carved in steps (... 164, 196, 228 KB).  Above 196 KB per CTA (dynamic +
+    // 16.5 KB static + 1 KB reserved) no L1 is left and the 8-byte loads / stores of the 54-channel layers (two per
+    // 32-byte sector) go to L2 twice: measured -18 % .. -43 % on the layer-1 shapes.  A ring stage is worth less.
+    {
+        const size_t l1_friendly = 196 * 1024 - 1024 - 17 * 1024;
+        const int min_stages = p.resident ? 3 : 2;
+        while (smem > l1_friendly && p.nstages > min_stages) {
+            --p.nstages;
+            smem -= p.stage_bytes;
+        }
+    }
     CF_CHECK_ARG(a->wpack_bytes >= (int64_t)((size_t)p.ntiles * p.nchunks * p.b_chunk_bytes), "weight-pack workspace too small");
     CF_CHECK_ARG(p.total_tiles < (1LL << 31), "too many tiles");
     p.acc_stride = (p.NTp + 31) / 32 * 32;

@@ -416,6 +416,8 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     }
     if (p.nstages < 2) return -1;
     if (p.nstages > WG_MAX_STAGES) p.nstages = WG_MAX_STAGES;
+    // keep the shared-memory carve-out at <= 196 KB (some L1 left for the 8-byte loads of the 54-channel tensors: see x3d_pw_tc2.cu)
+    while (p.nstages > 2 && 1024 + (size_t)p.nstages * p.stage_bytes + tab_bytes > 193 * 1024) --p.nstages;
     p.rbps = (int)((R + p.RB - 1) / p.RB);
     p.total_items = (long long)a->B * p.rbps;
     int gx = wg_sm_count() / (p.msplit * p.nsplit);
