@@ -375,6 +375,12 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(!a->scatter_out || a->N % taps == 0, "N must be channels*taps");
     int R = a->g.T * a->g.H * a->g.W;
     if (a->wpack && !a->gather_in && !a->scatter_out) return cf_pw_conv_tc(a, stream);
+    if (a->wpack && taps == 1 && a->g.ch_stride == 1 && a->g.pt == 0 && a->g.ph == 0 && a->g.pw == 0 &&
+        (a->gather_in ? (a->g.pos_stride == a->K && a->pro_mode != CF_PRO_AFFINE2)
+                      : (a->g.pos_stride == a->N && a->accumulate && a->stats_mode == CF_STATS_NONE && !a->aux))) {
+        int rct = cf_pw_conv_tc(a, stream);                  // strided 1x1x1 conv (downsample branch): row gather / scatter in the GEMM
+        if (rct >= 0) return rct;
+    }
     if (a->gather_in) {
         int rcs = cf_stem_fwd_try(a, stream);               // conv1_s: specialised kernel
         if (rcs >= 0) return rcs;

@@ -65,6 +65,10 @@ __device__ long long p2_dbg[32];
 
 struct P2Params {
     int B, R, tps, ntiles, NT, NTp, nchunks, nstages, resident, acc_stride, KP, g_j, g_rt, timing, dbg_1x;
+    // strided 1x1x1 convs (the downsample branch, x3d_fine.py:277-288): gmode 1 = the A rows are gathered from a
+    // [Ti,Hi,Wi] volume at (t*st, h*sh, w*sw); gmode 2 = the output rows are scattered to it and accumulated (y +=)
+    int gmode, gH, gW, gHi, gWi, gst, gsh, gsw;
+    long long g_sample_stride;
     uint32_t tmem_cols, b_chunk_bytes, stage_bytes;
     long long total_tiles;
 };
@@ -154,6 +158,13 @@ __device__ __forceinline__ void p2_advance(P2Item& it, const P2Params& p) {
     }
 }
 
+// row of the dense side -> row of the strided volume (within the sample)
+__device__ __forceinline__ long long p2_map_row(const P2Params& p, int r) {
+    const int w = r % p.gW, q = r / p.gW;
+    const int h = q % p.gH, t = q / p.gH;
+    return ((long long)(t * p.gst) * p.gHi + h * p.gsh) * p.gWi + w * p.gsw;
+}
+
 // ---------------------------------------------------------------------------------------
 // producers
 // ---------------------------------------------------------------------------------------
@@ -163,10 +174,27 @@ __device__ __forceinline__ void p2_load_item(const cf_pw_args& a, const P2Params
     const int K = a.K;
     const int k = it.c * TC_KC + q * 4;
     const int rows_valid = min(TC_BM, p.R - it.r0);
+    constexpr int RPP = P2_PROD_WARPS * 4;                        // rows per pass
+    if (p.gmode == 1) {                                           // gathered rows (strided 1x1x1 conv): one row map per pass
+#pragma unroll
+        for (int pp = 0; pp < P2_PROD_PASSES; ++pp) {
+            const int row = pp * RPP + rr;
+            const bool rv = row < rows_valid;
+            const float* xp = a.x + (size_t)it.b * p.g_sample_stride + (rv ? p2_map_row(p, it.r0 + row) : 0) * K + k;
+#pragma unroll
+            for (int e = 0; e < 4; e += AV) {
+                if (rv && k + e < K) P2Vec<AV>::ld(xp + e, &v[pp][e]);
+                else {
+#pragma unroll
+                    for (int u = 0; u < AV; ++u) v[pp][e + u] = 0.f;
+                }
+            }
+        }
+        return;
+    }
     const size_t off = ((size_t)it.b * p.R + it.r0 + rr) * K + k;
     const float* xp = a.x + off;
     const float* x2p = X2 ? a.x2 + off : nullptr;
-    constexpr int RPP = P2_PROD_WARPS * 4;                        // rows per pass
     const size_t step = (size_t)RPP * K;
 #pragma unroll
     for (int pp = 0; pp < P2_PROD_PASSES; ++pp, xp += step, x2p += X2 ? step : 0) {
@@ -389,9 +417,9 @@ __device__ __forceinline__ void p2_fma2(float& c0, float& c1, float a0, float a1
 
 // FULL: all 128 rows of the tile are valid (every tile but the last one of a sample): no per-pass row checks
 template <int EV, int EPI, int SMODE, bool FULL>
-__device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const float* __restrict__ cp, float* __restrict__ dp,
-                                              const float* __restrict__ ap, size_t gstep, int rs, int rows_valid, const float* bi,
-                                              const float* ea, const float* eb, bool has_bias, float* s1, float* s2) {
+__device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const P2Params& p, int b, int r0, int ncol, const float* __restrict__ cp,
+                                              float* __restrict__ dp, const float* __restrict__ ap, size_t gstep, int rs, int rows_valid,
+                                              const float* bi, const float* ea, const float* eb, bool has_bias, float* s1, float* s2) {
     constexpr int CPR = 32 / EV, RPP = 128 / CPR, NPASS = TC_BM / RPP;
     constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX;
     constexpr bool NEED_AUX = EPI_AUX || SMODE == CF_STATS_SUM_AUX;
@@ -434,13 +462,22 @@ __device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const float* 
                 else p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], vv[e], vv[e + 1]);
             }
         }
-        P2Vec<EV>::st(dp, vv);
+        if (p.gmode == 2) {                                      // strided 1x1x1 conv, data gradient: y[map(row)] += result
+            float* sp = a.y + (size_t)b * p.g_sample_stride + p2_map_row(p, r0 + rs + i * RPP) * a.N + ncol;
+            float old[EV];
+            P2Vec<EV>::ldrw(sp, old);
+#pragma unroll
+            for (int e = 0; e < EV; ++e) vv[e] += old[e];
+            P2Vec<EV>::st(sp, vv);
+        } else {
+            P2Vec<EV>::st(dp, vv);
+        }
     }
 }
 
 template <int EV, int EPI, int SMODE>
-__device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const float* __restrict__ Cs, float* __restrict__ redw, int b,
-                                              int r0, int rows_valid, int R, int n0, int col0, int nvalid, int gt) {
+__device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const P2Params& p, const float* __restrict__ Cs, float* __restrict__ redw,
+                                              int b, int r0, int rows_valid, int R, int n0, int col0, int nvalid, int gt) {
     constexpr int CPR = 32 / EV;             // column groups per row
     constexpr int RPP = 128 / CPR;           // rows per pass
     const int N = a.N;
@@ -464,9 +501,9 @@ __device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const float* 
         const float* cp = Cs + rs * P2_CS_LD + cg * EV;
         const float* ap = a.aux ? a.aux + g0 : nullptr;
         if (rows_valid == TC_BM)
-            p2_store_rows<EV, EPI, SMODE, true>(a, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
+            p2_store_rows<EV, EPI, SMODE, true>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
         else
-            p2_store_rows<EV, EPI, SMODE, false>(a, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
+            p2_store_rows<EV, EPI, SMODE, false>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
     }
     if (SMODE != CF_STATS_NONE) {
         // column sums: the 32 / CPR row groups of a warp meet by shuffle, then the first CPR lanes add into THIS WARP's
@@ -561,7 +598,7 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
             P2_ACC(4, tt);                                   // 4: accumulator rows -> shared slab
             named_bar_sync(2 + grp, 128);
             P2_ACC(3, tt);
-            p2_store_slab<EV, EPI, SMODE>(a, Cs, redw, it.b, it.r0, rows_valid, p.R, n0, slab * 32, nvalid, gt);
+            p2_store_slab<EV, EPI, SMODE>(a, p, Cs, redw, it.b, it.r0, rows_valid, p.R, n0, slab * 32, nvalid, gt);
             P2_ACC(5, tt);                                   // 5: slab -> global (+ aux, activation, statistics partials)
         }
         if (grp >= nslabs) {                                 // a group without slabs still releases the accumulator
@@ -753,7 +790,7 @@ static bool p2_use_v1() {
 
 // called by cf_pw_conv (x3d_pw.cu) for dense problems when the caller supplied a weight-pack workspace
 int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
-    if (p2_use_v1()) return cf_pw_conv_tc_v1(a, stream);
+    if (p2_use_v1()) return (a->gather_in || a->scatter_out) ? -1 : cf_pw_conv_tc_v1(a, stream);
     const int K = a->K, N = a->N;
     P2Params p;
     p2_tiling(K, N, p);
@@ -770,7 +807,18 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     int av = ((K & 3) == 0 && (xa & 15) == 0) ? 4 : (((K & 1) == 0 && (xa & 7) == 0) ? 2 : 1);
     uintptr_t ya = (uintptr_t)a->y | (uintptr_t)(a->aux ? a->aux : a->y);
     int ev = ((N & 3) == 0 && (ya & 15) == 0) ? 4 : (((N & 1) == 0 && (ya & 7) == 0) ? 2 : 1);
-    if (av == 1 || ev == 1 || a->accumulate || (a->stats_mode != CF_STATS_NONE && N > P2_RED_N)) return cf_pw_conv_tc_v1(a, stream);
+    const int taps1 = a->g.kt == 1 && a->g.kh == 1 && a->g.kw == 1 && a->g.pt == 0 && a->g.ph == 0 && a->g.pw == 0 && a->g.ch_stride == 1;
+    p.gmode = a->gather_in ? 1 : (a->scatter_out ? 2 : 0);
+    if (p.gmode) {
+        CF_CHECK_ARG(taps1 && a->g.pos_stride == (p.gmode == 1 ? K : N), "tensor-core path: strided 1x1x1 channels-last only");
+        CF_CHECK_ARG(p.gmode == 1 ? a->pro_mode != CF_PRO_AFFINE2 : (a->accumulate && a->stats_mode == CF_STATS_NONE && !a->aux),
+                     "tensor-core path: unsupported strided combination");
+        if (((a->g.sample_stride * 4) & 15) != 0) return -1;
+    }
+    p.gH = a->g.H; p.gW = a->g.W; p.gHi = a->g.Hi; p.gWi = a->g.Wi; p.gst = a->g.st; p.gsh = a->g.sh; p.gsw = a->g.sw;
+    p.g_sample_stride = a->g.sample_stride;
+    if (av == 1 || ev == 1 || (a->accumulate && p.gmode != 2) || (a->stats_mode != CF_STATS_NONE && N > P2_RED_N))
+        return p.gmode ? -1 : cf_pw_conv_tc_v1(a, stream);      // (-1: the caller falls back to the CUDA-core gather kernel)
     // shared-memory plan: weights resident next to >= 3 A stages, else streamed with each stage; if even two stages
     // of the widest channel tile do not fit (very long K: big prologue tables), narrow the channel tile
     size_t smem = 0;

@@ -38,6 +38,9 @@ struct WgParams {
     long long total_items;
     uint32_t chunk_bytes, stage_bytes, tmem_cols;
     int av_dy, av_x;
+    // strided 1x1x1 conv (downsample branch): the x rows are gathered from a [Ti,Hi,Wi] volume at (t*st, h*sh, w*sw)
+    int gmode, gH, gW, gHi, gWi, gst, gsh, gsw;
+    long long g_sample_stride;
 };
 
 // MN-major descriptor.  32-bit (tf32) MN-major operands only exist in the SWIZZLE_128B_BASE32B layout (layout type 1;
@@ -159,7 +162,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
             const size_t grow = (size_t)b * p.R + r0 + row;
             const float* dyp = a.dy + grow * N + n_base + q8 * 4;
             const float* dy2p = aff2 ? a.dy2 + grow * N + n_base + q8 * 4 : nullptr;
-            const float* xp = a.x + grow * K + k_base + q8 * 4;
+            const float* xp;
+            if (p.gmode) {
+                const int r = rv ? r0 + row : 0;
+                const int w = r % p.gW, q = r / p.gW;
+                const int h = q % p.gH, t = q / p.gH;
+                xp = a.x + (size_t)b * p.g_sample_stride + (((size_t)(t * p.gst) * p.gHi + h * p.gsh) * p.gWi + w * p.gsw) * K + k_base + q8 * 4;
+            } else {
+                xp = a.x + grow * K + k_base + q8 * 4;
+            }
 #pragma unroll
             for (int i = 0; i < WG_UB; ++i) {
                 const int u = u0 + i * groups;
@@ -377,13 +388,19 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     }
     if (disabled) return -1;
     const int N = a->N, K = a->K;
-    if (a->gather_in || a->dbias || (N & 1) || (K & 1) || N > 512 || K > 512) return -1;
+    if (a->dbias || (N & 1) || (K & 1) || N > 512 || K > 512) return -1;
+    if (a->gather_in && !(a->g.kt == 1 && a->g.kh == 1 && a->g.kw == 1 && a->g.pt == 0 && a->g.ph == 0 && a->g.pw == 0 && a->g.ch_stride == 1 &&
+                          a->g.pos_stride == K && a->x_mode == CF_PRO_NONE && ((a->g.sample_stride * 4) & 15) == 0))
+        return -1;
     if (a->dy_mode != CF_PRO_NONE && a->dy_mode != CF_PRO_AFFINE2) return -1;
     if (a->x_mode == CF_PRO_AFFINE2) return -1;
     const long long R = (long long)a->g.T * a->g.H * a->g.W;
     if (R * a->B < 4096) return -1;                          // tiny problems: launch overhead dominates, keep the simple kernel
     WgParams p;
     p.B = a->B; p.R = (int)R; p.N = N; p.K = K;
+    p.gmode = a->gather_in ? 1 : 0;
+    p.gH = a->g.H; p.gW = a->g.W; p.gHi = a->g.Hi; p.gWi = a->g.Wi; p.gst = a->g.st; p.gsh = a->g.sh; p.gsw = a->g.sw;
+    p.g_sample_stride = a->g.sample_stride;
     uintptr_t da = (uintptr_t)a->dy | (uintptr_t)(a->dy2 ? a->dy2 : a->dy);
     p.av_dy = ((N & 3) == 0 && (da & 15) == 0) ? 4 : 2;
     p.av_x = ((K & 3) == 0 && (((uintptr_t)a->x) & 15) == 0) ? 4 : 2;

@@ -49,7 +49,8 @@ def pw_conv(x, w, y, B, K, N, g, *, w_sn=None, w_sk=1, x2=None, bias=None, pro=P
             epi=EPI_NONE, aux=None, epi_tabs=(None, None), stats=None, stats_mode=STATS_NONE, gather_in=0, scatter_out=0,
             accumulate=0, tc=None):
     wpack, wbytes = None, 0
-    if (USE_TC if tc is None else tc) and not gather_in and not scatter_out:
+    strided_1x1 = (g.kt * g.kh * g.kw == 1 and g.ch_stride == 1 and g.pt == 0 and g.ph == 0 and g.pw == 0)
+    if (USE_TC if tc is None else tc) and ((not gather_in and not scatter_out) or strided_1x1):
         wbytes = int(lib.cf_pw_tc_ws_bytes(K, N))
         wpack = torch.empty(wbytes // 4, device=y.device, dtype=torch.float32)
     a = make("cf_pw_args", x=x, x2=x2, w=w, bias=bias, y=y, pro_a=pro_tabs[0], pro_b=pro_tabs[1], pro_c=pro_tabs[2],

@@ -120,9 +120,11 @@ def test_pw_conv_prologues_epilogues(X):
     close(dw, torch.einsum("bnthw,bkthw->nk", dyy, sw(v(ta) * x + v(tb))), rtol=1e-5, atol=1e-4, what="wgrad pro")
 
 
-@pytest.mark.parametrize("stride", [1, 2])
-def test_pw_conv_strided_gather_scatter(X, stride):
-    B, K, N, T, H, W = 2, 24, 48, 2, 9, 8
+@pytest.mark.parametrize("stride,dims", [(1, (2, 24, 48, 2, 9, 8)), (2, (2, 24, 48, 2, 9, 8)),
+                                         # enough rows for the tensor-core weight gradient with gathered rows; 54 channels = 8-byte path
+                                         (2, (3, 54, 24, 8, 30, 28)), (2, (2, 24, 108, 9, 27, 29))])
+def test_pw_conv_strided_gather_scatter(X, stride, dims):
+    B, K, N, T, H, W = dims
     x = synth_tensor((B, K, T, H, W), 31)
     w = synth_tensor((N, K, 1, 1, 1), 32, 0.2)
     ref = F.conv3d(x, w, stride=(1, stride, stride))
