@@ -434,21 +434,11 @@ __device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const P2Param
             }
         }
     }
-    // all shared-memory reads of the slab first (when no aux registers are held), so their latency overlaps
-    float cv[NEED_AUX ? 1 : NPASS][EV];
-    if (!NEED_AUX) {
-#pragma unroll
-        for (int i = 0; i < NPASS; ++i) P2Vec<EV>::ldrw(cp + i * (RPP * P2_CS_LD), cv[NEED_AUX ? 0 : i]);
-    }
 #pragma unroll
     for (int i = 0; i < NPASS; ++i, dp += gstep, cp += RPP * P2_CS_LD) {
         if (!FULL && rs + i * RPP >= rows_valid) break;
         float vv[EV];
-        if (NEED_AUX) P2Vec<EV>::ldrw(cp, vv);
-        else {
-#pragma unroll
-            for (int e = 0; e < EV; ++e) vv[e] = cv[NEED_AUX ? 0 : i][e];
-        }
+        P2Vec<EV>::ldrw(cp, vv);
         if (has_bias) {
 #pragma unroll
             for (int e = 0; e < EV; e += 2) p2_add2(vv[e], vv[e + 1], bi[e], bi[e + 1]);
