@@ -28,19 +28,6 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 
-#define P2_PROD_WARPS 16
-#define P2_PROD_PASSES (TC_BM / (P2_PROD_WARPS * 4))   /* rows per thread and chunk: 128 rows / (warps x 4 rows per warp) */
-#define P2_EPI_WARPS 8
-#define P2_PROD_THREADS (P2_PROD_WARPS * 32)
-#define P2_EPI_THREADS (P2_EPI_WARPS * 32)
-#define P2_MMA_WARP P2_PROD_WARPS
-#define P2_EPI_WARP0 (P2_PROD_WARPS + 4)          /* roles are warpgroup (4-warp) aligned for setmaxnreg */
-#define P2_THREADS ((P2_PROD_WARPS + 4 + P2_EPI_WARPS) * 32)
-// register budgets after setmaxnreg: registers only move WITHIN the CTA's launch allocation (896 threads x 72 = 64512),
-// an .inc beyond it waits forever: 512 x 72 + 128 x 24 + 256 x 96 = 64512
-#define P2_REGS_PROD 72
-#define P2_REGS_MMA 24
-#define P2_REGS_EPI 96
 #define P2_A_STAGE (2 * TC_BM * TC_KC * 4) /* hi + lo: 32 KB */
 #define P2_CS_LD 36
 #define P2_CS_FLOATS (TC_BM * P2_CS_LD)
@@ -73,645 +60,26 @@ struct P2Params {
     long long total_tiles;
 };
 
-// sigmoid from ex2.approx / rcp.approx (2^-22 relative: at the 3xTF32 level, far inside the 1e-3 parity bar): 5 issue
-// slots (2 of them MUFU) instead of ~16 for expf + IEEE division, which made the Swish producers instruction-bound
-__device__ __forceinline__ float p2_sigmoid(float x) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return r;
-}
-__device__ __forceinline__ float p2_swish(float v) { return v * p2_sigmoid(v); }
-__device__ __forceinline__ float p2_dswish(float v) {
-    float s = p2_sigmoid(v);
-    return s * (1.0f + v * (1.0f - s));
-}
-template <int PRO>
-__device__ __forceinline__ float p2_pro(float x, float x2, float a, float b, float c) {
-    if (PRO == CF_PRO_AFFINE) return fmaf(a, x, b);
-    if (PRO == CF_PRO_AFFINE_RELU) return fmaxf(fmaf(a, x, b), 0.f);
-    if (PRO == CF_PRO_AFFINE_SWISH) return p2_swish(fmaf(a, x, b));
-    if (PRO == CF_PRO_AFFINE2) return fmaf(a, x, fmaf(b, x2, c));
-    return x;
-}
-
-template <int W> struct P2Vec;
-template <> struct P2Vec<4> {
-    static __device__ __forceinline__ void ld(const float* p, float* v) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(p));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-    static __device__ __forceinline__ void ldrw(const float* p, float* v) {
-        float4 t = *reinterpret_cast<const float4*>(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-    static __device__ __forceinline__ void st(float* p, const float* v) {
-        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-};
-template <> struct P2Vec<2> {
-    static __device__ __forceinline__ void ld(const float* p, float* v) {
-        float2 t = __ldg(reinterpret_cast<const float2*>(p));
-        v[0] = t.x; v[1] = t.y;
-    }
-    static __device__ __forceinline__ void ldrw(const float* p, float* v) {
-        float2 t = *reinterpret_cast<const float2*>(p);
-        v[0] = t.x; v[1] = t.y;
-    }
-    static __device__ __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
-};
-template <> struct P2Vec<1> {
-    static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
-    static __device__ __forceinline__ void ldrw(const float* p, float* v) { v[0] = *p; }
-    static __device__ __forceinline__ void st(float* p, const float* v) { *p = v[0]; }
-};
-
-// position of one (tile, k-chunk) work item in a CTA's sequence.  tile = (b * tps + rtile) * ntiles + j; a CTA steps by
-// gridDim.x tiles at a time, done incrementally (g_j = grid % ntiles, g_rt = grid / ntiles from the host): no divisions
-// in the per-item path.
-struct P2Item {
-    int c, b, rtile, r0, j;
-    bool valid;
-};
-__device__ __forceinline__ void p2_first(P2Item& it, const P2Params& p) {
-    const int tile = (int)blockIdx.x;              // blockIdx.x < total_tiles (grid = min(SMs, tiles))
-    const int rt = tile / p.ntiles;
-    it.j = tile - rt * p.ntiles;
-    it.b = rt / p.tps;
-    it.rtile = rt - it.b * p.tps;
-    it.r0 = it.rtile * TC_BM;
-    it.c = 0;
-    it.valid = true;
-}
-__device__ __forceinline__ void p2_next_tile(P2Item& it, const P2Params& p) {
-    it.j += p.g_j;
-    it.rtile += p.g_rt;
-    if (it.j >= p.ntiles) { it.j -= p.ntiles; ++it.rtile; }
-    while (it.rtile >= p.tps) { it.rtile -= p.tps; ++it.b; }
-    it.r0 = it.rtile * TC_BM;
-    it.valid = it.b < p.B;
-}
-__device__ __forceinline__ void p2_advance(P2Item& it, const P2Params& p) {
-    if (++it.c == p.nchunks) {
-        it.c = 0;
-        p2_next_tile(it, p);
-    }
-}
-
-// row of the dense side -> row of the strided volume (within the sample)
-__device__ __forceinline__ long long p2_map_row(const P2Params& p, int r) {
-    const int w = r % p.gW, q = r / p.gW;
-    const int h = q % p.gH, t = q / p.gH;
-    return ((long long)(t * p.gst) * p.gHi + h * p.gsh) * p.gWi + w * p.gsw;
-}
-
-// ---------------------------------------------------------------------------------------
-// producers
-// ---------------------------------------------------------------------------------------
-template <int AV, bool X2>
-__device__ __forceinline__ void p2_load_item(const cf_pw_args& a, const P2Params& p, const P2Item& it, int q, int rr,
-                                             float (&v)[P2_PROD_PASSES][4], float (&v2)[X2 ? P2_PROD_PASSES : 1][4]) {
-    const int K = a.K;
-    const int k = it.c * TC_KC + q * 4;
-    const int rows_valid = min(TC_BM, p.R - it.r0);
-    constexpr int RPP = P2_PROD_WARPS * 4;                        // rows per pass
-    if (p.gmode == 1) {                                           // gathered rows (strided 1x1x1 conv): one row map per pass
-#pragma unroll
-        for (int pp = 0; pp < P2_PROD_PASSES; ++pp) {
-            const int row = pp * RPP + rr;
-            const bool rv = row < rows_valid;
-            const float* xp = a.x + (size_t)it.b * p.g_sample_stride + (rv ? p2_map_row(p, it.r0 + row) : 0) * K + k;
-#pragma unroll
-            for (int e = 0; e < 4; e += AV) {
-                if (rv && k + e < K) P2Vec<AV>::ld(xp + e, &v[pp][e]);
-                else {
-#pragma unroll
-                    for (int u = 0; u < AV; ++u) v[pp][e + u] = 0.f;
-                }
-            }
-        }
-        return;
-    }
-    const size_t off = ((size_t)it.b * p.R + it.r0 + rr) * K + k;
-    const float* xp = a.x + off;
-    const float* x2p = X2 ? a.x2 + off : nullptr;
-    const size_t step = (size_t)RPP * K;
-#pragma unroll
-    for (int pp = 0; pp < P2_PROD_PASSES; ++pp, xp += step, x2p += X2 ? step : 0) {
-        const bool rv = pp * RPP + rr < rows_valid;
-#pragma unroll
-        for (int e = 0; e < 4; e += AV) {
-            if (rv && k + e < K) {
-                P2Vec<AV>::ld(xp + e, &v[pp][e]);
-                if (X2) P2Vec<AV>::ld(x2p + e, &v2[X2 ? pp : 0][e]);
-            } else {
-#pragma unroll
-                for (int u = 0; u < AV; ++u) {
-                    v[pp][e + u] = 0.f;
-                    if (X2) v2[X2 ? pp : 0][e + u] = 0.f;
-                }
-            }
-        }
-    }
-}
-
-template <int AV, int PRO>
-__device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params& p, uint8_t* stages, float* tab, uint64_t* full,
-                                            uint64_t* empty, const float* __restrict__ pack, int tid) {
-    constexpr bool X2 = PRO == CF_PRO_AFFINE2;
-    constexpr int NSET = X2 ? 2 : 3;                              // register sets of loads in flight (8 / 16 floats each)
-    const int lane = tid & 31;
-    const int q = tid & 7, rr = tid >> 3;
-    float v[NSET][P2_PROD_PASSES][4];
-    float v2[NSET][X2 ? P2_PROD_PASSES : 1][4];
-    P2Item ld, pr;
-    p2_first(ld, p);
-    pr = ld;
-#pragma unroll
-    for (int u = 0; u < NSET - 1; ++u) {
-        if (ld.valid) {
-            p2_load_item<AV, X2>(a, p, ld, q, rr, v[u], v2[u]);
-            p2_advance(ld, p);
-        }
-    }
-    int cur_b = -1;
-    int s = 0;
-    uint32_t ph = 0;
-#ifdef CFNET_P2_TIMING
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tt = P2_T0();
-    const long long tstart = tt;
-#endif
-    while (pr.valid) {
-#pragma unroll
-        for (int u = 0; u < NSET; ++u) {
-            if (!pr.valid) break;
-            if (ld.valid) {
-                p2_load_item<AV, X2>(a, p, ld, q, rr, v[(u + NSET - 1) % NSET], v2[(u + NSET - 1) % NSET]);
-                p2_advance(ld, p);
-            }
-            // ---- prologue tables of this tile's sample (shared by the producer warps only)
-            if (PRO != CF_PRO_NONE && pr.c == 0 && pr.b != cur_b) {
-                named_bar_sync(1, P2_PROD_THREADS);
-                for (int t = tid; t < p.KP; t += P2_PROD_THREADS) {
-                    const bool kv = t < a.K;
-                    tab[t] = kv ? a.pro_a[(size_t)pr.b * a.K + t] : 0.f;
-                    tab[p.KP + t] = (kv && a.pro_b) ? a.pro_b[(size_t)pr.b * a.K + t] : 0.f;
-                    tab[2 * p.KP + t] = (kv && a.pro_c) ? a.pro_c[(size_t)pr.b * a.K + t] : 0.f;
-                }
-                named_bar_sync(1, P2_PROD_THREADS);
-                cur_b = pr.b;
-            }
-            P2_ACC(0, tt);                                   // 0: loads issued + tables
-            mbar_wait_b(&empty[s], ph ^ 1u);
-            P2_ACC(1, tt);                                   // 1: wait for a free stage
-            uint8_t* stage = stages + (size_t)s * p.stage_bytes;
-            if (!p.resident && tid == 0) {
-                mbar_expect_tx(&full[s], p.b_chunk_bytes);
-                bulk_g2s(stage + P2_A_STAGE, pack + ((size_t)pr.j * p.nchunks + pr.c) * (p.b_chunk_bytes / 4), p.b_chunk_bytes,
-                         &full[s]);
-            }
-            const int k = pr.c * TC_KC + q * 4;
-            float pa[4], pb[4], pc[4];
-            if (PRO != CF_PRO_NONE) {
-                const float4 ta = *reinterpret_cast<const float4*>(tab + k);
-                const float4 tb = *reinterpret_cast<const float4*>(tab + p.KP + k);
-                pa[0] = ta.x; pa[1] = ta.y; pa[2] = ta.z; pa[3] = ta.w;
-                pb[0] = tb.x; pb[1] = tb.y; pb[2] = tb.z; pb[3] = tb.w;
-                if (X2) {
-                    const float4 tc = *reinterpret_cast<const float4*>(tab + 2 * p.KP + k);
-                    pc[0] = tc.x; pc[1] = tc.y; pc[2] = tc.z; pc[3] = tc.w;
-                }
-            }
-            const int rows_valid = min(TC_BM, p.R - pr.r0);
-            uint8_t* a_hi = stage;
-            uint8_t* a_lo = stage + TC_BM * TC_KC * 4;
-#pragma unroll
-            for (int pp = 0; pp < P2_PROD_PASSES; ++pp) {
-                const int row = pp * (P2_PROD_WARPS * 4) + rr;
-                float hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float t = v[u][pp][e];
-                    if (PRO != CF_PRO_NONE) {
-                        // padded k: tables are zero there (every prologue maps 0 with zero tables to 0); padded rows: mask
-                        t = p2_pro<PRO>(t, X2 ? v2[u][X2 ? pp : 0][e] : 0.f, pa[e], pb[e], X2 ? pc[e] : 0.f);
-                        if (row >= rows_valid) t = 0.f;
-                    }
-                    tf32_split(t, hi[e], lo[e]);
-                }
-                const uint32_t off = sw128_off(row, q);
-                *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            P2_ACC(2, tt);                                   // 2: prologue + split + stores
-            fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncwarp();
-            P2_ACC(3, tt);                                   // 3: proxy fence + warp sync
-            if (lane == 0) mbar_arrive(&full[s]);
-            P2_ACC(4, tt);                                   // 4: arrive
-            if (++s == p.nstages) { s = 0; ph ^= 1u; }
-            p2_advance(pr, p);
-        }
-    }
-#ifdef CFNET_P2_TIMING
-    if (p.timing && blockIdx.x == 0 && tid == 0) {
-        for (int i = 0; i < 5; ++i) p2_dbg[i] = tacc[i];
-        p2_dbg[7] = clock64() - tstart;
-    }
-#endif
-}
-
-// ---------------------------------------------------------------------------------------
-// MMA issuer: one warp runs the loop convergently (descriptor arithmetic stays warp-uniform), one elected lane issues.
-// Issuing from a divergent `if (lane == 0)` inside a producer warp measured ~70 cycles per tcgen05.mma (per-lane
-// descriptor math moved to uniform registers one MMA at a time) and made that warp the pipeline's slowest stage.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ bool p2_elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void p2_mma_warp(const cf_pw_args& a, const P2Params& p, uint8_t* stages, uint8_t* wres, uint64_t* full,
-                                            uint64_t* empty, uint64_t* tfull, uint64_t* tempty, uint64_t* wres_bar, uint32_t tmem) {
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7, 10),
-    // both K-major (bits 15,16 = 0), N >> 3 @ bit 17, M >> 4 @ bit 24
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NTp >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    const uint64_t lo_off = (uint64_t)((TC_BM * TC_KC * 4) >> 4);          // A lo tile follows A hi (descriptor address units: 16 B)
-    const uint64_t blo_off = (uint64_t)(((uint32_t)p.NTp * 128u) >> 4);    // B lo tile follows B hi
-    const uint64_t stages_desc = make_desc_sw128(smem_u32(stages));
-    const uint64_t wres_desc = make_desc_sw128(smem_u32(wres));
-#ifdef CFNET_P2_TIMING
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tt = P2_T0();
-    const long long tstart = tt;
-#endif
-    if (p.resident) mbar_wait_b(wres_bar, 0u);
-    int s = 0;
-    uint32_t ph = 0, tcount = 0;
-    P2Item it;
-    for (p2_first(it, p); it.valid; p2_next_tile(it, p), ++tcount) {
-        const int acc = (int)(tcount & 1u);
-        P2_ACC(0, tt);
-        mbar_wait_b(&tempty[acc], ((tcount >> 1) & 1u) ^ 1u);             // the epilogue drained this accumulator
-        P2_ACC(1, tt);                                                     // 1: wait for the accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem + (uint32_t)(acc * p.acc_stride);
-        for (int c = 0; c < p.nchunks; ++c) {
-            mbar_wait_b(&full[s], ph);                                     // producers (and the weight block) filled this stage
-            P2_ACC(2, tt);                                                 // 2: wait for a full stage
-            tc_fence_after();
-            const uint64_t a_hi = stages_desc + (uint64_t)(((uint32_t)s * p.stage_bytes) >> 4);
-            const uint64_t a_lo = a_hi + lo_off;
-            const uint64_t b_hi = p.resident ? wres_desc + (uint64_t)(((uint32_t)c * p.b_chunk_bytes) >> 4) : a_hi + (uint64_t)(P2_A_STAGE >> 4);
-            const uint64_t b_lo = b_hi + blo_off;
-            const int nk8 = min(4, (a.K - c * TC_KC + 7) >> 3);
-            if (p2_elect_one()) {
-#pragma unroll
-                for (int k8 = 0; k8 < 4; ++k8) {
-                    if (k8 < nk8) {
-                        const uint64_t ko = (uint64_t)(k8 * 2);            // 8 tf32 = 32 bytes along K inside the swizzle row
-                        if (!p.dbg_1x) {
-                            umma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, (uint32_t)((c | k8) != 0));
-                            umma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-                            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
-                        } else {                                           // debug: single-pass TF32 (wrong results, timing only)
-                            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, (uint32_t)((c | k8) != 0));
-                        }
-                    }
-                }
-                umma_commit(&empty[s]);                                    // stage reusable once these MMAs retire
-                if (c == p.nchunks - 1) umma_commit(&tfull[acc]);          // accumulator complete
-            }
-            __syncwarp();
-            P2_ACC(3, tt);                                                 // 3: issue + commits
-            if (++s == p.nstages) { s = 0; ph ^= 1u; }
-        }
-    }
-#ifdef CFNET_P2_TIMING
-    if (p.timing && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
-        for (int i = 0; i < 4; ++i) p2_dbg[16 + i] = tacc[i];
-        p2_dbg[20] = clock64() - tstart;
-    }
-#endif
-}
-
-// ---------------------------------------------------------------------------------------
-// epilogue: one 32-column slab, shared tile -> global (coalesced along N)
-// ---------------------------------------------------------------------------------------
-#define P2_SCR_FLOATS (16 * 32 * 2)          /* per group: [rows per pass <= 16][32 columns][2 statistics] */
-
-// packed fp32x2 arithmetic (sm_100 FADD2 / FFMA2): halves the issue slots of the bias add and the statistics
-__device__ __forceinline__ void p2_add2(float& a0, float& a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
-        : "+f"(a0), "+f"(a1)
-        : "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ void p2_fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
-        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
-        : "+f"(c0), "+f"(c1)
-        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-
-// FULL: all 128 rows of the tile are valid (every tile but the last one of a sample): no per-pass row checks
-template <int EV, int EPI, int SMODE, bool FULL>
-__device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const P2Params& p, int b, int r0, int ncol, const float* __restrict__ cp,
-                                              float* __restrict__ dp, const float* __restrict__ ap, size_t gstep, int rs, int rows_valid,
-                                              const float* bi, const float* ea, const float* eb, bool has_bias, float* s1, float* s2) {
-    constexpr int CPR = 32 / EV, RPP = 128 / CPR, NPASS = TC_BM / RPP;
-    constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX;
-    constexpr bool NEED_AUX = EPI_AUX || SMODE == CF_STATS_SUM_AUX;
-    float ax[NEED_AUX ? NPASS : 1][EV];
-    if (NEED_AUX) {
-#pragma unroll
-        for (int i = 0; i < NPASS; ++i, ap += gstep) {
-            if (FULL || rs + i * RPP < rows_valid) P2Vec<EV>::ld(ap, ax[NEED_AUX ? i : 0]);
-            else {
-#pragma unroll
-                for (int e = 0; e < EV; ++e) ax[NEED_AUX ? i : 0][e] = 0.f;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NPASS; ++i, dp += gstep, cp += RPP * P2_CS_LD) {
-        if (!FULL && rs + i * RPP >= rows_valid) break;
-        float vv[EV];
-        P2Vec<EV>::ldrw(cp, vv);
-        if (has_bias) {
-#pragma unroll
-            for (int e = 0; e < EV; e += 2) p2_add2(vv[e], vv[e + 1], bi[e], bi[e + 1]);
-        }
-        const float* axe = ax[NEED_AUX ? i : 0];
-#pragma unroll
-        for (int e = 0; e < EV; ++e) {
-            float t = vv[e];
-            if (EPI == CF_EPI_RELU) t = fmaxf(t, 0.f);
-            else if (EPI == CF_EPI_DRELU) t = (fmaf(ea[e], axe[e], eb[e]) > 0.f) ? t : 0.f;
-            else if (EPI == CF_EPI_DSWISH) t *= p2_dswish(fmaf(ea[e], axe[e], eb[e]));
-            else if (EPI == CF_EPI_ADD_AUX) t += axe[e];
-            else if (EPI == CF_EPI_SIGMOID) t = p2_sigmoid(t);
-            vv[e] = t;
-        }
-        if (SMODE != CF_STATS_NONE) {
-#pragma unroll
-            for (int e = 0; e < EV; e += 2) {
-                p2_add2(s1[e], s1[e + 1], vv[e], vv[e + 1]);
-                if (SMODE == CF_STATS_SUM_AUX) p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], axe[e], axe[e + 1]);
-                else p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], vv[e], vv[e + 1]);
-            }
-        }
-        if (p.gmode == 2) {                                      // strided 1x1x1 conv, data gradient: y[map(row)] += result
-            float* sp = a.y + (size_t)b * p.g_sample_stride + p2_map_row(p, r0 + rs + i * RPP) * a.N + ncol;
-            float old[EV];
-            P2Vec<EV>::ldrw(sp, old);
-#pragma unroll
-            for (int e = 0; e < EV; ++e) vv[e] += old[e];
-            P2Vec<EV>::st(sp, vv);
-        } else {
-            P2Vec<EV>::st(dp, vv);
-        }
-    }
-}
-
-template <int EV, int EPI, int SMODE>
-__device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const P2Params& p, const float* __restrict__ Cs, float* __restrict__ redw,
-                                              int b, int r0, int rows_valid, int R, int n0, int col0, int nvalid, int gt) {
-    constexpr int CPR = 32 / EV;             // column groups per row
-    constexpr int RPP = 128 / CPR;           // rows per pass
-    const int N = a.N;
-    const int cg = gt % CPR, rs = gt / CPR;
-    const int nl = col0 + cg * EV;           // column within the channel tile
-    const bool active = nl < nvalid;         // nvalid and nl are multiples of EV: a column group is all-valid or all-padding
-    float s1[EV], s2[EV];
-#pragma unroll
-    for (int e = 0; e < EV; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
-    if (active) {
-        const int n = n0 + nl;
-        float bi[EV], ea[EV], eb[EV];
-#pragma unroll
-        for (int e = 0; e < EV; ++e) {
-            bi[e] = a.bias ? a.bias[n + e] : 0.f;
-            ea[e] = (EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH) ? a.epi_a[(size_t)b * N + n + e] : 1.f;
-            eb[e] = (EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH) ? a.epi_b[(size_t)b * N + n + e] : 0.f;
-        }
-        const size_t g0 = ((size_t)b * R + r0 + rs) * N + n;
-        const size_t gstep = (size_t)RPP * N;
-        const float* cp = Cs + rs * P2_CS_LD + cg * EV;
-        const float* ap = a.aux ? a.aux + g0 : nullptr;
-        if (rows_valid == TC_BM)
-            p2_store_rows<EV, EPI, SMODE, true>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
-        else
-            p2_store_rows<EV, EPI, SMODE, false>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
-    }
-    if (SMODE != CF_STATS_NONE) {
-        // column sums: the 32 / CPR row groups of a warp meet by shuffle, then the first CPR lanes add into THIS WARP's
-        // row of the per-CTA table (a slab belongs to one group, a table row to one warp: no atomics, no barrier)
-#pragma unroll
-        for (int o = CPR; o < 32; o <<= 1)
-#pragma unroll
-            for (int e = 0; e < EV; ++e) {
-                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
-                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
-            }
-        if (active && (gt & 31) < CPR) {
-            float* r1 = redw + n0 + nl;
-#pragma unroll
-            for (int e = 0; e < EV; ++e) {
-                r1[e] += s1[e];
-                r1[P2_RED_N + e] += s2[e];
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void p2_flush_stats(const cf_pw_args& a, float* red, int b, int et) {
-    named_bar_sync(4, P2_EPI_THREADS);
-    for (int i = et; i < a.N; i += P2_EPI_THREADS) {
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            t1 += red[w * 2 * P2_RED_N + i];
-            t2 += red[w * 2 * P2_RED_N + P2_RED_N + i];
-            red[w * 2 * P2_RED_N + i] = 0.f;
-            red[w * 2 * P2_RED_N + P2_RED_N + i] = 0.f;
-        }
-        double* st = a.stats + ((size_t)b * a.N + i) * 2;
-        atomicAdd(st, (double)t1);
-        atomicAdd(st + 1, (double)t2);
-    }
-    named_bar_sync(4, P2_EPI_THREADS);
-}
-
-template <int EV, int EPI, int SMODE>
-__device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params& p, float* Cs_all, float* red,
-                                            uint64_t* tfull, uint64_t* tempty, uint32_t tmem, int warp, int lane) {
-    constexpr int RPP = 128 / (32 / EV);
-    const int ew = warp - P2_EPI_WARP0;
-    const int grp = ew >> 2;
-    const int qd = warp & 3;                                 // TMEM lane quadrant this warp may read
-    const int gt = (ew & 3) * 32 + lane;                     // thread index within the group (phase 2)
-    const int et = ew * 32 + lane;
-    float* Cs = Cs_all + grp * P2_CS_FLOATS;
-    float* redw = red + (ew & 3) * 2 * P2_RED_N;                // this warp's row of the statistics table
-    const int row_own = qd * 32 + lane;
-    const int nslabs = (p.NTp + 31) >> 5;
-    int cur_b = -1;
-    uint32_t tcount = 0;
-#ifdef CFNET_P2_TIMING
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tt = P2_T0();
-    const long long tstart = tt;
-#endif
-    P2Item it;
-    for (p2_first(it, p); it.valid; p2_next_tile(it, p), ++tcount) {
-        if (SMODE != CF_STATS_NONE && it.b != cur_b) {
-            if (cur_b >= 0) p2_flush_stats(a, red, cur_b, et);
-            cur_b = it.b;
-        }
-        const int acc = (int)(tcount & 1u);
-        const uint32_t aph = (tcount >> 1) & 1u;
-        const int rows_valid = min(TC_BM, p.R - it.r0);
-        const int n0 = it.j * p.NT;
-        const int nvalid = min(p.NT, a.N - n0);
-        P2_ACC(0, tt);                                       // 0: tile bookkeeping (+ statistics flush)
-        mbar_wait_b(&tfull[acc], aph);
-        P2_ACC(1, tt);                                       // 1: wait for the accumulator
-        tc_fence_after();
-        const uint32_t tbase = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-        for (int slab = grp; slab < nslabs; slab += 2) {
-            float r32[32];
-            tmem_ld32(tbase + (uint32_t)(slab * 32), r32);
-            if (slab + 2 >= nslabs) {                        // last TMEM read of this warp for this tile: free the accumulator
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
-            }
-            P2_ACC(2, tt);                                   // 2: tcgen05.ld + release
-            named_bar_sync(2 + grp, 128);                    // the previous slab's readers are done with Cs
-            P2_ACC(3, tt);                                   // 3: group barriers
-            float* dst = Cs + row_own * P2_CS_LD;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(r32[4 * i], r32[4 * i + 1], r32[4 * i + 2], r32[4 * i + 3]);
-            P2_ACC(4, tt);                                   // 4: accumulator rows -> shared slab
-            named_bar_sync(2 + grp, 128);
-            P2_ACC(3, tt);
-            p2_store_slab<EV, EPI, SMODE>(a, p, Cs, redw, it.b, it.r0, rows_valid, p.R, n0, slab * 32, nvalid, gt);
-            P2_ACC(5, tt);                                   // 5: slab -> global (+ aux, activation, statistics partials)
-        }
-        if (grp >= nslabs) {                                 // a group without slabs still releases the accumulator
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
-    }
-    if (SMODE != CF_STATS_NONE && cur_b >= 0) p2_flush_stats(a, red, cur_b, et);
-#ifdef CFNET_P2_TIMING
-    if (p.timing && blockIdx.x == 0 && et == 0) {
-        for (int i = 0; i < 7; ++i) p2_dbg[8 + i] = tacc[i];
-        p2_dbg[15] = clock64() - tstart;
-    }
-#endif
-}
-
-// ---------------------------------------------------------------------------------------
-// kernel
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args a, const float* __restrict__ pack, const P2Params p,
-                                                               int av, int ev) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full[P2_MAX_STAGES];
-    __shared__ __align__(8) uint64_t empty[P2_MAX_STAGES];
-    __shared__ __align__(8) uint64_t tfull[2];
-    __shared__ __align__(8) uint64_t tempty[2];
-    __shared__ __align__(8) uint64_t wres_bar;
-    __shared__ uint32_t tmem_addr_s;
-    __shared__ float red[4 * 2 * P2_RED_N];                          // [epilogue warp in group][sum, sum2][channel]
-
-    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B tiles: 1024-B aligned
-    uint8_t* stages = base;
-    uint8_t* wres = stages + (size_t)p.nstages * p.stage_bytes;
-    float* Cs = reinterpret_cast<float*>(wres + (p.resident ? (size_t)p.nchunks * p.b_chunk_bytes : 0));
-    float* tab = Cs + 2 * P2_CS_FLOATS;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    if (warp == P2_PROD_WARPS) {
-        tmem_alloc(&tmem_addr_s, p.tmem_cols);
-        tmem_relinquish();
-    }
-    if (tid == 0) {
-        for (int s = 0; s < p.nstages; ++s) {
-            mbar_init(&full[s], P2_PROD_WARPS + (p.resident ? 0 : 1));   // + the streamed weight block's expect_tx arrival
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], P2_EPI_WARPS); mbar_init(&tempty[1], P2_EPI_WARPS);
-        mbar_init(&wres_bar, 1);
-        fence_mbar_init();
-    }
-    for (int i = tid; i < 4 * 2 * P2_RED_N; i += P2_THREADS) red[i] = 0.f;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_addr_s;
-
-    if (warp < P2_PROD_WARPS) {
-        // ================= producers =================
-#define P2_PARGS a, p, stages, tab, full, empty, pack, tid
-        if (p.resident && tid == 0) {
-            mbar_expect_tx(&wres_bar, (uint32_t)p.nchunks * p.b_chunk_bytes);
-            for (int c = 0; c < p.nchunks; ++c)
-                bulk_g2s(wres + (size_t)c * p.b_chunk_bytes, pack + (size_t)c * (p.b_chunk_bytes / 4), p.b_chunk_bytes, &wres_bar);
-        }
-#define P2_PROD(AV_)                                                                                              \
-    switch (a.pro_mode) {                                                                                         \
-        case CF_PRO_AFFINE: p2_producer<AV_, CF_PRO_AFFINE>(P2_PARGS); break;    \
-        case CF_PRO_AFFINE_RELU: p2_producer<AV_, CF_PRO_AFFINE_RELU>(P2_PARGS); break;   \
-        case CF_PRO_AFFINE_SWISH: p2_producer<AV_, CF_PRO_AFFINE_SWISH>(P2_PARGS); break; \
-        case CF_PRO_AFFINE2: p2_producer<AV_, CF_PRO_AFFINE2>(P2_PARGS); break;  \
-        default: p2_producer<AV_, CF_PRO_NONE>(P2_PARGS); break;                 \
-    }
-        if (av == 4) { P2_PROD(4) } else { P2_PROD(2) }
-#undef P2_PROD
-#undef P2_PARGS
-    } else if (warp < P2_EPI_WARP0) {
-        // ================= MMA issuer (first warp of its warpgroup; the other three only give up their registers) =================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_REGS_MMA));
-        if (warp == P2_MMA_WARP) p2_mma_warp(a, p, stages, wres, full, empty, tfull, tempty, &wres_bar, tmem);
-    } else {
-        // ================= epilogue =================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_REGS_EPI));
-#define P2_EARGS a, p, Cs, red, tfull, tempty, tmem, warp, lane
-#define P2_EPI_S(EV_, EPI_)                                                                  \
-    switch (a.stats_mode) {                                                                  \
-        case CF_STATS_SUM_SQ: p2_epilogue<EV_, EPI_, CF_STATS_SUM_SQ>(P2_EARGS); break;      \
-        case CF_STATS_SUM_AUX: p2_epilogue<EV_, EPI_, CF_STATS_SUM_AUX>(P2_EARGS); break;    \
-        default: p2_epilogue<EV_, EPI_, CF_STATS_NONE>(P2_EARGS); break;                     \
-    }
-#define P2_EPI(EV_)                                                      \
-    switch (a.epi_mode) {                                                \
-        case CF_EPI_RELU: P2_EPI_S(EV_, CF_EPI_RELU) break;              \
-        case CF_EPI_DRELU: P2_EPI_S(EV_, CF_EPI_DRELU) break;            \
-        case CF_EPI_DSWISH: P2_EPI_S(EV_, CF_EPI_DSWISH) break;          \
-        case CF_EPI_ADD_AUX: P2_EPI_S(EV_, CF_EPI_ADD_AUX) break;        \
-        case CF_EPI_SIGMOID: P2_EPI_S(EV_, CF_EPI_SIGMOID) break;        \
-        default: P2_EPI_S(EV_, CF_EPI_NONE) break;                       \
-    }
-        if (ev == 4) { P2_EPI(4) } else { P2_EPI(2) }
-#undef P2_EPI
-#undef P2_EPI_S
-#undef P2_EARGS
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == P2_PROD_WARPS) {
-        tc_fence_after();
-        tmem_dealloc(tmem, p.tmem_cols);
-    }
-}
+// ---- role split A: 8 producer warps
+#define P2_NS p2w8
+#define P2_PROD_WARPS 8
+#define P2_REGS_PROD 120
+#define P2_REGS_MMA 32
+#define P2_REGS_EPI 104
+#define P2_PROD_INC 1                  /* producers raise their register count (launch: 640 threads x 96) */
+#include "x3d_pw_tc2_roles.cuh"
+#include "x3d_pw_tc2_kernel.cuh"
+#include "x3d_pw_tc2_unroles.cuh"
+// ---- role split B: 16 producer warps
+#define P2_NS p2w16
+#define P2_PROD_WARPS 16
+#define P2_REGS_PROD 72
+#define P2_REGS_MMA 24
+#define P2_REGS_EPI 96
+#define P2_PROD_INC 0                  /* producers keep the launch count (896 threads x 72) */
+#include "x3d_pw_tc2_roles.cuh"
+#include "x3d_pw_tc2_kernel.cuh"
+#include "x3d_pw_tc2_unroles.cuh"
 
 // ---------------------------------------------------------------------------------------
 // host side
@@ -855,7 +223,9 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     // 16.5 KB static + 1 KB reserved) no L1 is left and the 8-byte loads / stores of the 54-channel layers (two per
     // 32-byte sector) go to L2 twice: measured -18 % .. -43 % on the layer-1 shapes.  A ring stage is worth less.
     {
-        const size_t l1_friendly = 196 * 1024 - 1024 - 17 * 1024;
+        static int l1cap = -1;                                       // CFNET_P2_L1CAP=0: A/B switch
+        if (l1cap < 0) { const char* e = getenv("CFNET_P2_L1CAP"); l1cap = (e && e[0] == '0') ? 0 : 1; }
+        const size_t l1_friendly = l1cap ? 196 * 1024 - 1024 - 17 * 1024 : (size_t)P2_SMEM_MAX;
         const int min_stages = p.resident ? 3 : 2;
         while (smem > l1_friendly && p.nstages > min_stages) {
             --p.nstages;
@@ -870,7 +240,8 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     cf_pw_tc_pack_launch(a->w, a->w_sn, a->w_sk, a->wpack, K, N, p.NT, p.NTp, p.ntiles, p.nchunks, stream);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
+        cudaError_t e = cudaFuncSetAttribute(p2w8::pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(p2w16::pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
         if (e != cudaSuccess) {
             cf_set_error("cf_pw_conv_tc: cannot opt in to %d B of shared memory: %s", P2_SMEM_MAX, cudaGetErrorString(e));
             return CF_ERR_CUDA;
@@ -886,7 +257,15 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     }
     p.g_j = (int)(grid % p.ntiles);
     p.g_rt = (int)(grid / p.ntiles);
-    pw_tc2_kernel<<<(unsigned)grid, P2_THREADS, smem, stream>>>(*a, a->wpack, p, av, ev);
+    // Role split.  Same-box A/B runs (gpurun_out/s25_ab*.log; boxes of this pool differ by 10-25 %, so only runs inside one
+    // call compare): 8 producer warps (120 / 32 / 104 registers) win or tie on every shape of the step except the Swish
+    // prologues with K = 54 and K = 216 (16 producer warps 6 % faster there, 10-20 % slower on the BatchNorm-backward
+    // prologues: their 72-register producers spill).  Default: 8; CFNET_PW_TC_PROD=16 selects the other split.
+    static int force_pw = -1;
+    if (force_pw < 0) { const char* e = getenv("CFNET_PW_TC_PROD"); force_pw = e ? atoi(e) : 0; }
+    const bool few_producers = force_pw != 16;
+    if (few_producers) p2w8::pw_tc2_kernel<<<(unsigned)grid, (8 + 4 + 8) * 32, smem, stream>>>(*a, a->wpack, p, av, ev);
+    else p2w16::pw_tc2_kernel<<<(unsigned)grid, (16 + 4 + 8) * 32, smem, stream>>>(*a, a->wpack, p, av, ev);
     CF_COUNT_LAUNCH(2);
     CF_CHECK_LAUNCH();
     return CF_OK;

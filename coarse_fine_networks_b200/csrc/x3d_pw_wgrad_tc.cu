@@ -423,7 +423,9 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.mt_per * p.npad_per) p.tmem_cols <<= 1;
     const size_t tab_bytes = (size_t)(3 * p.nchA + 2 * p.nchB) * 32 * 4;
-    p.RB = 64;                                               // rows per stage: as many as leave >= 2 stages (per-stage overhead amortised)
+    static int rb0 = -1;                                      // CFNET_WG_RB=32|16: A/B switch
+    if (rb0 < 0) { const char* e = getenv("CFNET_WG_RB"); rb0 = e ? atoi(e) : 64; if (rb0 != 16 && rb0 != 32) rb0 = 64; }
+    p.RB = rb0;                                              // rows per stage: as many as leave >= 2 stages (per-stage overhead amortised)
     for (;;) {
         p.chunk_bytes = (uint32_t)p.RB * 128u;
         p.stage_bytes = (uint32_t)(2 * (p.nchA_pad + p.nchB)) * p.chunk_bytes;
