@@ -224,9 +224,9 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     // 32-byte sector) go to L2 twice: measured -18 % .. -43 % on the layer-1 shapes.  A ring stage is worth less.
     {
         static int l1cap = -1;                                       // CFNET_P2_L1CAP=0: A/B switch
-        if (l1cap < 0) { const char* e = getenv("CFNET_P2_L1CAP"); l1cap = (e && e[0] == '0') ? 0 : 1; }
-        const size_t l1_friendly = l1cap ? 196 * 1024 - 1024 - 17 * 1024 : (size_t)P2_SMEM_MAX;
-        const int min_stages = p.resident ? 3 : 2;
+        if (l1cap < 0) { const char* e = getenv("CFNET_P2_L1CAP"); l1cap = e ? atoi(e) : 1; }
+        const size_t l1_friendly = l1cap == 2 ? 164 * 1024 - 1024 - 17 * 1024 : (l1cap ? 196 * 1024 - 1024 - 17 * 1024 : (size_t)P2_SMEM_MAX);
+        const int min_stages = (p.resident && l1cap != 2) ? 3 : 2;
         while (smem > l1_friendly && p.nstages > min_stages) {
             --p.nstages;
             smem -= p.stage_bytes;
