@@ -125,3 +125,49 @@ def coarse_fine_forward(fine_net, coarse_net, x_fine, start, n_coarse, feat_mask
         meta = torch.tensor([[float(start), float(n_coarse), float(Tf), 1.0]], device=x_fine.device).repeat(B, 1)
     x_coarse = x_fine[:, :, start:start + n_coarse]
     return coarse_net([x_coarse, feat, feat_masks, 0, meta])
+
+
+# ----------------------------------------------------------------------------------------
+# Evaluation path (train_coarse_fineFEAT.py:213-263)
+# ----------------------------------------------------------------------------------------
+T_LIM_INFERENCE = 1000       # train_coarse_fineFEAT.py:215
+
+
+def coarse_forward_chunked(coarse_net, inputs, feat, feat_masks, meta, t_lim=T_LIM_INFERENCE):
+    """Validation forward of long videos, train_coarse_fineFEAT.py:215-224: clips longer than t_lim + 5 frames are cut
+    into t_lim-frame pieces, each piece sees the whole fine features with its start offset meta[:,0] advanced, and the
+    per-frame logits are concatenated along T.  ``meta`` is advanced in place exactly like the reference does."""
+    T = inputs.shape[2]
+    if T < t_lim + 5:
+        return coarse_net([inputs, feat, feat_masks, 0, meta])
+    out = []
+    for t_ind in range(0, T // t_lim + 1):
+        piece = inputs[:, :, t_ind * t_lim:min(T, (t_ind + 1) * t_lim)]
+        if piece.shape[2] == 0:                                   # T an exact multiple of t_lim (the reference would fail here)
+            break
+        out.append(coarse_net([piece, feat, feat_masks, 0, meta]))
+        meta[:, 0] += t_lim
+    return torch.cat(out, dim=2)
+
+
+def eval_probs(per_frame_logits, masks, b, n):
+    """Multi-view validation scores, train_coarse_fineFEAT.py:231-235: logits [b*n,C,TL] -> max over the n views of
+    sigmoid(logits), masked; returns (probs [b,C,TL], logits [b,C,TL])."""
+    tl = per_frame_logits.shape[-1]
+    lg = per_frame_logits.view(b, n, -1, tl)
+    probs = torch.sigmoid(lg).max(dim=1)[0] * masks.unsqueeze(1)
+    return probs, lg.max(dim=1)[0]
+
+
+def localize_samples(probs, labels, valid_t):
+    """25 evenly spaced frames of one video (Charades localisation protocol), train_coarse_fineFEAT.py:249-253.
+    probs / labels [C,TL] -> ([C,<=25], [C,<=25])."""
+    step = int(valid_t / 25.0)
+    return probs[:, :valid_t][:, 1::step][:, :25], labels[:, :valid_t][:, 1::step][:, :25]
+
+
+def charades_csv_rows(name, p1, duration):
+    """Rows of the Charades localisation submission file, train_coarse_fineFEAT.py:255-261: (video id, 1 + i*dur/25,
+    space-separated class scores) for the <= 25 sampled frames p1 [C,<=25]."""
+    a = p1.transpose(0, 1).detach().cpu().numpy()
+    return [[name, 1 + i * duration / 25.0, " ".join(str(v) for v in a[i])] for i in range(a.shape[0])]

@@ -486,6 +486,12 @@ int cf_charades_loss(const float* logits, const float* labels, const float* mask
 int cf_sgd_flat(float* p, float* g, float* v, int64_t n, int64_t n_split, float lr0, float lr1, float momentum,
                 float weight_decay, float grad_scale, cudaStream_t stream);
 
+/* ---- evaluation: average precision per class (apmeter.py:98-136) ---------------------------------------- */
+/* truth_sorted [K,N]: the 0/1 targets of class k ordered by descending score of that class (the caller sorts);
+ * weight_sorted [K,N] per-sample weights in the same order, or NULL; ap [K] out:
+ * ap[k] = sum_{i: truth} (tp_i / rg_i) / max(sum truth, 1), tp = cumsum(truth*weight), rg = 1..N or cumsum(weight). */
+int cf_ap_sorted(const float* truth_sorted, const float* weight_sorted, float* ap, int N, int K, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -378,3 +378,37 @@ def coarse_forward(sd: StateDict, x: Tensor, feat: Dict[str, Tensor], feat_masks
     if return_aux:
         return out, {"cdf": cdf, "GX": GX}
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# Evaluation
+# ----------------------------------------------------------------------------------------
+
+def average_precision(scores: Tensor, targets: Tensor, weights: Optional[Tensor] = None) -> Tensor:
+    """APMeter.value(), apmeter.py:98-136: per class, sort the scores descending (:117), gather the targets (:118),
+    tp = cumsum(truth [* weight]) (:125-128), rg = 1..N or cumsum(weight) (:109,122), precision = tp / rg (:131),
+    ap = sum(precision[truth]) / max(sum(truth), 1) (:134).  scores [N,K] float, targets [N,K] 0/1, weights [N] or None."""
+    n, k = scores.shape
+    ap = torch.zeros(k)
+    rg0 = torch.arange(1, n + 1, dtype=torch.float32)
+    for c in range(k):
+        _, ind = torch.sort(scores[:, c], 0, True)
+        truth = targets[:, c][ind].float()
+        if weights is not None:
+            w = weights[ind].float()
+            tp = (truth * w).cumsum(0)
+            rg = w.cumsum(0)
+        else:
+            tp = truth.cumsum(0)
+            rg = rg0
+        precision = tp / rg
+        ap[c] = precision[truth.bool()].sum() / max(float(truth.sum()), 1.0)
+    return ap
+
+
+def localize_samples(probs: Tensor, labels: Tensor, valid_t: int) -> Tuple[Tensor, Tensor]:
+    """The 25-point sampling of the Charades localisation protocol, train_coarse_fineFEAT.py:249-253:
+    p1 = probs[:, :valid_t]; sc = valid_t / 25.; p1[:, 1::int(sc)][:, :25] (same for the labels).  probs / labels [C,TL]."""
+    sc = valid_t / 25.0
+    step = int(sc)
+    return probs[:, :valid_t][:, 1::step][:, :25], labels[:, :valid_t][:, 1::step][:, :25]

@@ -275,8 +275,30 @@ def gen_coarse_net():
     save("coarse_net", out_eval=out_eval, out_train=out, **gr)
 
 
+def gen_apmeter():
+    """apmeter.py:98-136 through the reference's own APMeter: unweighted (as the scripts use it,
+    train_coarse_fineFEAT.py:241-263) and weighted, batches added in pieces, ties in the scores, a class without positives."""
+    import apmeter as ref_apm
+    g = torch.Generator().manual_seed(101)
+    N, K = 700, 9
+    scores = torch.rand(N, K, generator=g)
+    scores[::7, 2] = 0.5                                   # ties
+    targets = (torch.rand(N, K, generator=g) < 0.2).long()
+    targets[:, 5] = 0                                      # a class without positives
+    weights = torch.rand(N, generator=g) + 0.1
+    m = ref_apm.APMeter()
+    for a in range(0, N, 250):
+        m.add(scores[a:a + 250].numpy(), targets[a:a + 250].numpy())
+    ap = m.value()
+    mw = ref_apm.APMeter()
+    for a in range(0, N, 250):
+        mw.add(scores[a:a + 250], targets[a:a + 250], weights[a:a + 250])
+    apw = mw.value()
+    save("apmeter", scores=scores, targets=targets, weights=weights, ap=ap, ap_weighted=apw)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["interp1d", "gridpool", "gridpool_cfgshape", "gridunpool", "gaussian", "rewight",
-                             "mixing", "bottleneck", "fine_net", "coarse_net"]
+                             "mixing", "bottleneck", "fine_net", "coarse_net", "apmeter"]
     for w in which:
         globals()["gen_" + w]()
