@@ -31,7 +31,11 @@
 struct WgParams {
     int B, R, N, K;                              // N = dy channels, K = x channels
     int RB, rbps, nstages;                       // rows per stage, row blocks per sample
-    int nchA, nchA_pad, nchB;                    // real / padded dy chunks and x chunks of ONE CTA
+    int nchA_pad, nchB;                          // padded M-side chunks (4 per 128-channel tile) and N-side chunks of ONE CTA
+    // The tensor with MORE channels is the M side (padded to 128 per tile), the other one the N side (padded to 32):
+    // swap = 0: M = dy channels, N = x channels;  swap = 1: M = x channels, N = dy channels (D is written transposed)
+    int swap, ndyc, nxc;                         // dy / x chunks this CTA loads
+    uint32_t dy_off, dy_lo, x_off, x_lo;         // stage offsets of the dy / x hi regions and hi -> lo distances
     int mt_per, npad_per;                        // dy channel tiles (128) and padded x channels of one CTA
     int msplit, nsplit;                          // blockIdx.y = ms * nsplit + ns
     int items_per_cta;
@@ -109,13 +113,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
 
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stages = base;
-    float* tabA = reinterpret_cast<float*>(stages + (size_t)p.nstages * p.stage_bytes);      // [3][nchA*32]
-    float* tabB = tabA + 3 * p.nchA * 32;                                                      // [2][nchB*32]
+    float* tabA = reinterpret_cast<float*>(stages + (size_t)p.nstages * p.stage_bytes);      // dy tables [3][ndyc*32]
+    float* tabB = tabA + 3 * p.ndyc * 32;                                                      // x tables  [2][nxc*32]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ms = blockIdx.y / p.nsplit, ns = blockIdx.y - ms * p.nsplit;
-    const int n_base = ms * p.mt_per * 128;                  // first dy channel of this CTA
-    const int k_base = ns * p.npad_per;                      // first x channel of this CTA
+    const int m_base = ms * p.mt_per * 128;                  // first M-side / N-side channel of this CTA
+    const int c_base = ns * p.npad_per;
+    const int n_base = p.swap ? c_base : m_base;             // first dy channel of this CTA
+    const int k_base = p.swap ? m_base : c_base;             // first x channel of this CTA
     const long long item0 = (long long)blockIdx.x * p.items_per_cta;
     const long long item1 = min(item0 + p.items_per_cta, p.total_items);
 
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
         const int grp = tid / TPC, lt = tid - grp * TPC;
         const int row = lt >> 3, q8 = lt & 7;
         const uint32_t soff = wg_sw_off(row, q8);
-        const int nunits = p.nchA + p.nchB;
+        const int nunits = p.ndyc + p.nxc;
         const int N = p.N, K = p.K;
         const int ustep = groups * WG_UB;
         constexpr bool aff2 = DYM == CF_PRO_AFFINE2;
@@ -175,13 +181,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
             for (int i = 0; i < WG_UB; ++i) {
                 const int u = u0 + i * groups;
                 if (u < nunits && rv) {
-                    if (u < p.nchA) {
+                    if (u < p.ndyc) {
                         const int c = n_base + u * 32 + q8 * 4;
                         wg_ld4(dyp + u * 32, c, N, p.av_dy, v[i]);
                         if (aff2) wg_ld4(dy2p + u * 32, c, N, p.av_dy, v2[i]);
                     } else {
-                        const int c = k_base + (u - p.nchA) * 32 + q8 * 4;
-                        wg_ld4(xp + (u - p.nchA) * 32, c, K, p.av_x, v[i]);
+                        const int c = k_base + (u - p.ndyc) * 32 + q8 * 4;
+                        wg_ld4(xp + (u - p.ndyc) * 32, c, K, p.av_x, v[i]);
                     }
                 } else {
                     v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
@@ -195,11 +201,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
                 const int u = u0 + i * groups;
                 if (u >= nunits) break;
                 float hi[4], lo[4];
-                if (u < p.nchA) {
+                if (u < p.ndyc) {
                     const int tl = u * 32 + q8 * 4;
                     const float4 ta = *reinterpret_cast<const float4*>(tabA + tl);
-                    const float4 tb = *reinterpret_cast<const float4*>(tabA + p.nchA * 32 + tl);
-                    const float4 tc = *reinterpret_cast<const float4*>(tabA + 2 * p.nchA * 32 + tl);
+                    const float4 tb = *reinterpret_cast<const float4*>(tabA + p.ndyc * 32 + tl);
+                    const float4 tc = *reinterpret_cast<const float4*>(tabA + 2 * p.ndyc * 32 + tl);
                     const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w}, pc[4] = {tc.x, tc.y, tc.z, tc.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -207,14 +213,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
                         if (DYM != CF_PRO_NONE) t = rv ? wg_pro<DYM>(t, v2[i][e], pa[e], pb[e], pc[e]) : 0.f;
                         tf32_split(t, hi[e], lo[e]);
                     }
-                    uint8_t* dst = stage + (uint32_t)u * p.chunk_bytes + soff;
+                    uint8_t* dst = stage + p.dy_off + (uint32_t)u * p.chunk_bytes + soff;
                     *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(dst + a_lo_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4*>(dst + p.dy_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 } else {
-                    const int j = u - p.nchA;
+                    const int j = u - p.ndyc;
                     const int tl = j * 32 + q8 * 4;
                     const float4 ta = *reinterpret_cast<const float4*>(tabB + tl);
-                    const float4 tb = *reinterpret_cast<const float4*>(tabB + p.nchB * 32 + tl);
+                    const float4 tb = *reinterpret_cast<const float4*>(tabB + p.nxc * 32 + tl);
                     const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -222,9 +228,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
                         if (XM != CF_PRO_NONE) t = rv ? wg_pro<XM>(t, 0.f, pa[e], pb[e], 0.f) : 0.f;
                         tf32_split(t, hi[e], lo[e]);
                     }
-                    uint8_t* dst = stage + b_hi_off + (uint32_t)j * p.chunk_bytes + soff;
+                    uint8_t* dst = stage + p.x_off + (uint32_t)j * p.chunk_bytes + soff;
                     *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(dst + (b_lo_off - b_hi_off)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4*>(dst + p.x_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
         };
@@ -245,18 +251,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
             if (nrb == p.rbps) { nrb = 0; ++nb; }
             if (b != cur_b) {                                // per-sample prologue tables (zero beyond the real channels)
                 named_bar_sync(1, WG_PROD_THREADS);
-                for (int t = tid; t < p.nchA * 32; t += WG_PROD_THREADS) {
+                for (int t = tid; t < p.ndyc * 32; t += WG_PROD_THREADS) {
                     const int n = n_base + t;
                     const bool v = n < N && DYM != CF_PRO_NONE;
                     tabA[t] = v ? a.dy_a[(size_t)b * N + n] : 0.f;
-                    tabA[p.nchA * 32 + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
-                    tabA[2 * p.nchA * 32 + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
+                    tabA[p.ndyc * 32 + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
+                    tabA[2 * p.ndyc * 32 + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
                 }
-                for (int t = tid; t < p.nchB * 32; t += WG_PROD_THREADS) {
+                for (int t = tid; t < p.nxc * 32; t += WG_PROD_THREADS) {
                     const int k = k_base + t;
                     const bool v = k < K && XM != CF_PRO_NONE;
                     tabB[t] = v ? a.x_a[(size_t)b * K + k] : 0.f;
-                    tabB[p.nchB * 32 + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
+                    tabB[p.nxc * 32 + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
                 }
                 named_bar_sync(1, WG_PROD_THREADS);
                 cur_b = b;
@@ -348,14 +354,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
         const int njobs = p.mt_per * nslab;                  // (channel tile, 32-column slab) jobs, spread over warps / 4
         for (int job = warp >> 2; warp < WG_PROD_WARPS && job < njobs; job += WG_PROD_WARPS / 4) {
             const int mt = job / nslab, sl = job - mt * nslab;
-            const int n = n_base + mt * 128 + qd * 32 + lane;
+            const int m = m_base + mt * 128 + qd * 32 + lane;    // M-side channel of this TMEM lane
             float r32[32];
             tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mt * p.npad_per + sl * 32), r32);
-            if (n < p.N && n < n_base + p.mt_per * 128) {
-                float* dst = a.dw + (size_t)n * p.K + k_base + sl * 32;
+            const int msize = p.swap ? p.K : p.N, csize = p.swap ? p.N : p.K;
+            if (m < msize) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (k_base + sl * 32 + i < p.K && sl * 32 + i < p.npad_per) atomicAdd(dst + i, r32[i]);
+                for (int i = 0; i < 32; ++i) {
+                    const int c = c_base + sl * 32 + i;           // N-side channel of this column
+                    if (c < csize && sl * 32 + i < p.npad_per)
+                        atomicAdd(a.dw + (p.swap ? (size_t)c * p.K + m : (size_t)m * p.K + c), r32[i]);
+                }
             }
         }
     }
@@ -405,24 +414,37 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     p.av_dy = ((N & 3) == 0 && (da & 15) == 0) ? 4 : 2;
     p.av_x = ((K & 3) == 0 && (((uintptr_t)a->x) & 15) == 0) ? 4 : 2;
     if ((da & 7) || (((uintptr_t)a->x) & 7)) return -1;
-    // split so that the partial fits 512 TMEM columns and one MMA covers <= 256 x channels
-    const int mtiles = (N + 127) / 128;
-    const int kpad = (K + 31) / 32 * 32;
-    p.nsplit = kpad > 256 ? 2 : 1;
-    p.npad_per = ((kpad / 32 + p.nsplit - 1) / p.nsplit) * 32;
+    // The tensor with more channels is the M side (128 per tile), the other the N side (32 per chunk): the tensor work of
+    // one 8-row step is ceil(M/128)*128 x ceil32(N).  Then split so that the partial fits 512 TMEM columns and one MMA
+    // covers <= 256 N-side channels.
+    {
+        const long long cost0 = (long long)((N + 127) / 128) * 128 * ((K + 31) / 32 * 32);
+        const long long cost1 = (long long)((K + 127) / 128) * 128 * ((N + 31) / 32 * 32);
+        static int noswap = -1;                               // CFNET_WG_NOSWAP=1: A/B switch
+        if (noswap < 0) { const char* e = getenv("CFNET_WG_NOSWAP"); noswap = (e && e[0] == '1') ? 1 : 0; }
+        p.swap = (cost1 < cost0 && !noswap) ? 1 : 0;
+    }
+    const int Msz = p.swap ? K : N, Csz = p.swap ? N : K;
+    const int mtiles = (Msz + 127) / 128;
+    const int cpad = (Csz + 31) / 32 * 32;
+    p.nsplit = cpad > 256 ? 2 : 1;
+    p.npad_per = ((cpad / 32 + p.nsplit - 1) / p.nsplit) * 32;
     p.msplit = 1;
     while (((mtiles + p.msplit - 1) / p.msplit) * p.npad_per > 512) ++p.msplit;
     p.mt_per = (mtiles + p.msplit - 1) / p.msplit;
     p.nchB = p.npad_per / 32;
     p.nchA_pad = 4 * p.mt_per;
+    int nchA;                                                // M-side chunks a CTA actually loads
     {
-        int nreal = (N + 31) / 32;                           // real 32-channel chunks of dy; a CTA loads at most its own tiles'
-        p.nchA = nreal < p.nchA_pad ? nreal : p.nchA_pad;
-        if (p.msplit > 1) p.nchA = p.nchA_pad;               // (padded channels of the last tile load as zeros)
+        int nreal = (Msz + 31) / 32;
+        nchA = nreal < p.nchA_pad ? nreal : p.nchA_pad;
+        if (p.msplit > 1) nchA = p.nchA_pad;                 // (padded channels of the last tile load as zeros)
     }
+    p.ndyc = p.swap ? p.nchB : nchA;
+    p.nxc = p.swap ? nchA : p.nchB;
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.mt_per * p.npad_per) p.tmem_cols <<= 1;
-    const size_t tab_bytes = (size_t)(3 * p.nchA + 2 * p.nchB) * 32 * 4;
+    const size_t tab_bytes = (size_t)(3 * p.ndyc + 2 * p.nxc) * 32 * 4;
     static int rb0 = -1;                                      // CFNET_WG_RB=32|16: A/B switch
     if (rb0 < 0) { const char* e = getenv("CFNET_WG_RB"); rb0 = e ? atoi(e) : 64; if (rb0 != 16 && rb0 != 32) rb0 = 64; }
     p.RB = rb0;                                              // rows per stage: as many as leave >= 2 stages (per-stage overhead amortised)
@@ -437,6 +459,11 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     if (p.nstages > WG_MAX_STAGES) p.nstages = WG_MAX_STAGES;
     // keep the shared-memory carve-out at <= 196 KB (some L1 left for the 8-byte loads of the 54-channel tensors: see x3d_pw_tc2.cu)
     while (p.nstages > 2 && 1024 + (size_t)p.nstages * p.stage_bytes + tab_bytes > 193 * 1024) --p.nstages;
+    {
+        const uint32_t m_lo = (uint32_t)p.nchA_pad * p.chunk_bytes, c_off = 2u * m_lo, c_lo = (uint32_t)p.nchB * p.chunk_bytes;
+        if (p.swap) { p.x_off = 0; p.x_lo = m_lo; p.dy_off = c_off; p.dy_lo = c_lo; }
+        else { p.dy_off = 0; p.dy_lo = m_lo; p.x_off = c_off; p.x_lo = c_lo; }
+    }
     p.rbps = (int)((R + p.RB - 1) / p.RB);
     p.total_items = (long long)a->B * p.rbps;
     int gx = wg_sm_count() / (p.msplit * p.nsplit);
