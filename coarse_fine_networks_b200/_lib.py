@@ -9,7 +9,7 @@ import re
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcfnet_b200.so")
+LIB_PATH = os.environ.get("CFNET_LIB") or os.path.join(_PKG, "libcfnet_b200.so")     # CFNET_LIB: another build of the same library (A/B runs)
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "cfnet_b200.h")
 
 if not os.path.exists(LIB_PATH):
