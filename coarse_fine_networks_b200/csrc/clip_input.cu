@@ -1,0 +1,233 @@
+// Clip input pipeline: decoded RGB frames (uint8, HWC) -> normalised fp32 clip [3,T,S,S] in one kernel
+// (SURVEY 8(f) next-4).  Replaces, per frame, the reference's CPU chain
+//   charades_fine.py:170-172                    [spatial_transform(img) for img in imgs]; stack; permute -> [3,T,S,S]
+//   transforms/spatial_transforms.py:488-503    MultiScaleRandomCropMultigrid  (crop box, img.resize(BILINEAR))
+//   transforms/spatial_transforms.py:216-230    CenterCropScaled               (centre box, img.resize(BILINEAR))
+//   transforms/spatial_transforms.py:342-354    RandomHorizontalFlip
+//   transforms/spatial_transforms.py:46-87      ToTensor(255)
+//   transforms/spatial_transforms.py:108-118    Normalize(mean, std)
+//   charades_fine.py:215-226                    mt_collate_fn's zero padding of the shorter clips
+//
+// img.resize is Pillow's ImagingResample (Resample.c): separable triangle filter, 22-bit fixed-point coefficients,
+// horizontal pass then vertical pass, each rounded and clipped to uint8.  The integer arithmetic below is the same,
+// so the uint8 image and therefore the fp32 clip are bit-identical to the reference's.
+//
+// Byte/integer work bound by HBM: per frame 3*crop^2 bytes in, 12*S^2 bytes out.  CTA = (band of BAND output rows,
+// frame).  Horizontal pass: the input rows the band needs are resampled straight from global memory (adjacent output
+// columns read adjacent bytes -> sector-coalesced through L1) into a planar uint8 tile in shared memory; vertical pass:
+// a thread owns 4 adjacent output columns, reads uchar4 per tap from the tile, maps the three uint8 results through a
+// 768-entry shared-memory table (the only place the fp32 divisions of ToTensor/Normalize are evaluated: IEEE-exact
+// __fdiv_rn once per table entry instead of 6 divisions per pixel, which would bound the kernel by the FP32 pipe) and
+// streams three float4 out (st.global.cs, reversed when flipped).
+#include "cf_common.cuh"
+#include "../../include/cfnet_b200.h"
+#include <math.h>
+
+#define CLIP_PRECISION_BITS 22
+#define CLIP_BAND 16
+#define CLIP_THREADS 256
+
+// ------------------------------------------------------------------------------------------------------------
+// Host: Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter (support 1.0), whole axis.
+// Plain double arithmetic on the host, statement by statement as Resample.c evaluates it.
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int cf_resample_ksize(int in_size, int out_size) {
+    if (in_size <= 0 || out_size <= 0) return 0;
+    double scale = (double)in_size / (double)out_size;
+    double filterscale = scale < 1.0 ? 1.0 : scale;
+    double support = 1.0 * filterscale;
+    return (int)ceil(support) * 2 + 1;
+}
+
+extern "C" int cf_resample_coeffs(int in_size, int out_size, int* bounds, int* kk) {
+    CF_CHECK_ARG(in_size > 0 && out_size > 0 && bounds && kk, "bad arguments");
+    const double scale = (double)in_size / (double)out_size;
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = 1.0 * filterscale;
+    const int ksize = (int)ceil(support) * 2 + 1;
+    const double ss = 1.0 / filterscale;
+    double* w = new double[ksize];
+    for (int xx = 0; xx < out_size; ++xx) {
+        volatile double center = (xx + 0.5) * scale;      // volatile: no contraction / excess precision across statements
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        volatile double ww = 0.0;
+        for (int x = 0; x < xmax; ++x) {
+            volatile double a = (x + xmin - center + 0.5) * ss;
+            if (a < 0.0) a = -a;
+            w[x] = a < 1.0 ? 1.0 - a : 0.0;
+            ww = ww + w[x];
+        }
+        for (int x = 0; x < xmax; ++x)
+            if (ww != 0.0) w[x] = w[x] / ww;
+        int* k = kk + (size_t)xx * ksize;
+        for (int x = 0; x < ksize; ++x) {
+            if (x >= xmax) { k[x] = 0; continue; }
+            volatile double v = w[x] * (double)(1 << CLIP_PRECISION_BITS);
+            k[x] = w[x] < 0.0 ? (int)(-0.5 + v) : (int)(0.5 + v);
+        }
+        bounds[2 * xx] = xmin;
+        bounds[2 * xx + 1] = xmax;
+    }
+    delete[] w;
+    return CF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Device
+// ------------------------------------------------------------------------------------------------------------
+__global__ void normalize_lut_kernel(float* __restrict__ lut, float m0, float m1, float m2, float s0, float s1, float s2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 768) return;
+    const int c = i >> 8, v = i & 255;
+    const float m = c == 0 ? m0 : (c == 1 ? m1 : m2), s = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), m), s);     // img.float().div(255); t.sub_(m).div_(s)
+}
+
+__device__ __forceinline__ int clip8(int acc) {
+    const int v = acc >> CLIP_PRECISION_BITS;
+    return min(max(v, 0), 255);
+}
+
+struct ClipArgs {
+    const uint8_t* frames;     // [T,H,W,3]
+    float* out;                // sample base; channel stride out_stride_c, frame stride S*S
+    const int* bounds_h;       // [S,2]
+    const int* kk_h;           // [S,ksize_h]
+    const int* bounds_v;
+    const int* kk_v;
+    const float* lut;          // [3,256]
+    int T, H, W, x1, y1, S, Sp, ksize_h, ksize_v, flip, rows_max;
+    long long out_stride_c;
+};
+
+__global__ void __launch_bounds__(CLIP_THREADS) clip_preprocess_kernel(const ClipArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* lut_s = reinterpret_cast<float*>(smem_raw);                 // 768 floats
+    unsigned char* hs = smem_raw + 768 * sizeof(float);               // [rows_max][3][Sp]
+    const int tid = threadIdx.x, t = blockIdx.y, S = a.S, Sp = a.Sp;
+    const int oy0 = blockIdx.x * CLIP_BAND;
+    const int nrow_out = min(CLIP_BAND, S - oy0);
+    const int quads = S >> 2;
+    float* outf = a.out + (size_t)t * S * S;
+
+    if (t >= a.T) {                                                    // collate padding: literal zeros
+        for (int i = tid; i < nrow_out * quads; i += CLIP_THREADS) {
+            const int oy = oy0 + i / quads, q = i % quads;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                stcs4(reinterpret_cast<float4*>(outf + (size_t)c * a.out_stride_c + (size_t)oy * S) + q, f4_zero());
+        }
+        return;
+    }
+
+    for (int i = tid; i < 768; i += CLIP_THREADS) lut_s[i] = __ldg(a.lut + i);
+
+    // input rows (relative to the crop) this band needs: bounds are monotone in oy
+    const int r0 = __ldg(a.bounds_v + 2 * oy0);
+    const int last = oy0 + nrow_out - 1;
+    const int r1 = __ldg(a.bounds_v + 2 * last) + __ldg(a.bounds_v + 2 * last + 1);
+    const int nrows = r1 - r0;
+
+    // ---- horizontal pass: crop rows [r0, r1) -> hs[r][c][ox] ----
+    const uint8_t* fr = a.frames + ((size_t)t * a.H + (a.y1 + r0)) * a.W * 3 + (size_t)a.x1 * 3;
+    for (int i = tid; i < nrows * S; i += CLIP_THREADS) {
+        const int r = i / S, ox = i - r * S;
+        const int xmin = __ldg(a.bounds_h + 2 * ox), n = __ldg(a.bounds_h + 2 * ox + 1);
+        const int* k = a.kk_h + ox * a.ksize_h;
+        const uint8_t* src = fr + (size_t)r * a.W * 3 + xmin * 3;
+        int s0 = 1 << (CLIP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+        for (int j = 0; j < n; ++j) {
+            const int kj = __ldg(k + j);
+            s0 += (int)__ldg(src + 3 * j) * kj;
+            s1 += (int)__ldg(src + 3 * j + 1) * kj;
+            s2 += (int)__ldg(src + 3 * j + 2) * kj;
+        }
+        unsigned char* d = hs + (size_t)r * 3 * Sp + ox;
+        d[0] = (unsigned char)clip8(s0);
+        d[Sp] = (unsigned char)clip8(s1);
+        d[2 * Sp] = (unsigned char)clip8(s2);
+    }
+    __syncthreads();
+
+    // ---- vertical pass + normalisation table + store ----
+    for (int i = tid; i < nrow_out * quads; i += CLIP_THREADS) {
+        const int oy = oy0 + i / quads, q = i % quads;
+        const int lo = __ldg(a.bounds_v + 2 * oy) - r0, n = __ldg(a.bounds_v + 2 * oy + 1);
+        const int* k = a.kk_v + oy * a.ksize_v;
+        int acc[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[c][e] = 1 << (CLIP_PRECISION_BITS - 1);
+        for (int j = 0; j < n; ++j) {
+            const int kj = __ldg(k + j);
+            const unsigned char* row = hs + (size_t)(lo + j) * 3 * Sp + 4 * q;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uchar4 u = *reinterpret_cast<const uchar4*>(row + c * Sp);
+                acc[c][0] += (int)u.x * kj;
+                acc[c][1] += (int)u.y * kj;
+                acc[c][2] += (int)u.z * kj;
+                acc[c][3] += (int)u.w * kj;
+            }
+        }
+        const int qo = a.flip ? quads - 1 - q : q;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* l = lut_s + c * 256;
+            float4 v;
+            if (a.flip) v = make_float4(l[clip8(acc[c][3])], l[clip8(acc[c][2])], l[clip8(acc[c][1])], l[clip8(acc[c][0])]);
+            else        v = make_float4(l[clip8(acc[c][0])], l[clip8(acc[c][1])], l[clip8(acc[c][2])], l[clip8(acc[c][3])]);
+            stcs4(reinterpret_cast<float4*>(outf + (size_t)c * a.out_stride_c + (size_t)oy * S) + qo, v);
+        }
+    }
+}
+
+extern "C" int cf_normalize_lut(float* lut, float mean0, float mean1, float mean2, float std0, float std1, float std2,
+                                cudaStream_t stream) {
+    CF_CHECK_ARG(lut != nullptr, "lut is NULL");
+    normalize_lut_kernel<<<3, 256, 0, stream>>>(lut, mean0, mean1, mean2, std0, std1, std2);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}
+
+extern "C" size_t cf_clip_preprocess_smem_bytes(int size, int rows_max) {
+    const int Sp = (size + 15) & ~15;
+    return 768 * sizeof(float) + (size_t)rows_max * 3 * Sp;
+}
+
+extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* bounds_h, const int* kk_h,
+                                  const int* bounds_v, const int* kk_v, const float* lut, int T, int H, int W, int x1,
+                                  int y1, int crop, int size, int ksize_h, int ksize_v, int rows_max, int flip,
+                                  int t_out, int64_t out_stride_c, cudaStream_t stream) {
+    CF_CHECK_ARG(out && bounds_h && kk_h && bounds_v && kk_v && lut, "NULL pointer");
+    CF_CHECK_ARG(T >= 0 && t_out >= T && t_out > 0, "need 0 <= T <= t_out");
+    CF_CHECK_ARG(T == 0 || frames != nullptr, "frames is NULL");
+    CF_CHECK_ARG(size > 0 && size % 4 == 0, "output size must be a positive multiple of 4");
+    CF_CHECK_ARG(crop > 0 && x1 >= 0 && y1 >= 0 && x1 + crop <= W && y1 + crop <= H, "crop box outside the frame");
+    CF_CHECK_ARG(ksize_h == cf_resample_ksize(crop, size) && ksize_v == ksize_h, "coefficient tables do not match crop/size");
+    CF_CHECK_ARG(rows_max > 0, "rows_max must be positive");
+    CF_CHECK_ARG(((uintptr_t)out & 15) == 0 && (out_stride_c % 4) == 0, "out must be 16-byte aligned with a channel stride % 4 == 0");
+    CF_CHECK_ARG(out_stride_c >= (int64_t)t_out * size * size, "channel stride smaller than t_out frames");
+    CF_CHECK_ARG(t_out <= 65535, "t_out above the grid limit");
+    ClipArgs a;
+    a.frames = frames; a.out = out; a.bounds_h = bounds_h; a.kk_h = kk_h; a.bounds_v = bounds_v; a.kk_v = kk_v; a.lut = lut;
+    a.T = T; a.H = H; a.W = W; a.x1 = x1; a.y1 = y1; a.S = size; a.Sp = (size + 15) & ~15;
+    a.ksize_h = ksize_h; a.ksize_v = ksize_v; a.flip = flip ? 1 : 0; a.rows_max = rows_max; a.out_stride_c = out_stride_c;
+    const size_t smem = cf_clip_preprocess_smem_bytes(size, rows_max);
+    CF_CHECK_ARG(smem <= 200 * 1024, "band of input rows does not fit in shared memory (down-scale factor too large)");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(clip_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cf_set_error("cf_clip_preprocess: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
+    }
+    dim3 grid(cf_cdiv(size, CLIP_BAND), t_out);
+    clip_preprocess_kernel<<<grid, CLIP_THREADS, smem, stream>>>(a);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}

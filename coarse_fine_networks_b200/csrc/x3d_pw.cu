@@ -393,6 +393,37 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
     return launch_pw<128, false>(a, R, stream);
 }
 
+// dbias[n] += sum_rows dy[row,n] for a dense [rows,N] gradient: the bias half of a weight gradient whose GEMM half runs
+// on the tensor-core kernel.  CTA = 32 columns x a chunk of rows, 8 row lanes, 128-byte row segments per warp.
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ dbias, long long rows,
+                                                        int N, int chunk) {
+    __shared__ float part[8][33];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lx;
+    const long long r0 = (long long)blockIdx.y * chunk;
+    const long long r1 = r0 + chunk < rows ? r0 + chunk : rows;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (col < N) {
+        const float* p = dy + col;
+        long long r = r0 + ly;
+        for (; r + 24 < r1; r += 32) {
+            a0 += __ldg(p + r * N);
+            a1 += __ldg(p + (r + 8) * N);
+            a2 += __ldg(p + (r + 16) * N);
+            a3 += __ldg(p + (r + 24) * N);
+        }
+        for (; r < r1; r += 8) a0 += __ldg(p + r * N);
+    }
+    part[ly][lx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ly == 0 && col < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += part[q][lx];
+        atomicAdd(dbias + col, s);
+    }
+}
+
 extern "C" int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->dy && a->x && a->dw, "null pointer");
     CF_CHECK_ARG(a->B > 0 && a->K > 0 && a->N > 0 && geom_ok(a->g, a->gather_in != 0), "bad shape");
@@ -404,6 +435,24 @@ extern "C" int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     {
         int rc = cf_pw_wgrad_tc(a, stream);                 // dense problems: tensor cores
         if (rc >= 0) return rc;
+        if (a->dbias && a->dy_mode == CF_PRO_NONE) {        // GEMM half on the tensor cores, bias half as a column sum
+            cf_pw_wgrad_args nb = *a;
+            nb.dbias = nullptr;
+            rc = cf_pw_wgrad_tc(&nb, stream);
+            if (rc > 0) return rc;
+            if (rc == 0) {
+                const long long rows = (long long)a->B * a->g.T * a->g.H * a->g.W;
+                const int ct = cf_cdiv(a->N, 32);
+                long long want = cf_cdiv64(148 * 4, ct);
+                int chunk = (int)cf_cdiv64(rows, want < 1 ? 1 : want);
+                chunk = chunk < 256 ? 256 : ((chunk + 31) / 32) * 32;
+                dim3 grid((unsigned)ct, (unsigned)cf_cdiv64(rows, chunk));
+                bias_grad_kernel<<<grid, 256, 0, stream>>>(a->dy, a->dbias, rows, a->N, chunk);
+                CF_COUNT_LAUNCH(1);
+                CF_CHECK_LAUNCH();
+                return CF_OK;
+            }
+        }
         rc = cf_stem_wgrad_try(a, stream);                  // conv1_s: specialised kernel
         if (rc >= 0) return rc;
     }

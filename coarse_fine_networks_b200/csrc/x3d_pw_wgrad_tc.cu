@@ -404,7 +404,9 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     if (a->dy_mode != CF_PRO_NONE && a->dy_mode != CF_PRO_AFFINE2) return -1;
     if (a->x_mode == CF_PRO_AFFINE2) return -1;
     const long long R = (long long)a->g.T * a->g.H * a->g.W;
-    if (R * a->B < 4096) return -1;                          // tiny problems: launch overhead dominates, keep the simple kernel
+    static long long min_rows = -1;                          // tiny problems: launch overhead dominates, keep the simple kernel
+    if (min_rows < 0) { const char* e = getenv("CFNET_WG_MINROWS"); min_rows = e ? atoll(e) : 4096; }
+    if (R * a->B < min_rows) return -1;
     WgParams p;
     p.B = a->B; p.R = (int)R; p.N = N; p.K = K;
     p.gmode = a->gather_in ? 1 : 0;

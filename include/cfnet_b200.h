@@ -492,6 +492,33 @@ int cf_sgd_flat(float* p, float* g, float* v, int64_t n, int64_t n_split, float 
  * ap[k] = sum_{i: truth} (tp_i / rg_i) / max(sum truth, 1), tp = cumsum(truth*weight), rg = 1..N or cumsum(weight). */
 int cf_ap_sorted(const float* truth_sorted, const float* weight_sorted, float* ap, int N, int K, cudaStream_t stream);
 
+/* ---- input pipeline: decoded RGB frames -> normalised clip ---------------------------
+ * Replaces the per-frame CPU chain of charades_fine.py:170-172 with the transforms of train_fine.py:74-80:
+ * MultiScaleRandomCropMultigrid / CenterCropScaled (transforms/spatial_transforms.py:488-503, 216-230: crop box +
+ * PIL img.resize(BILINEAR)), RandomHorizontalFlip (342-354), ToTensor(255) (46-87), Normalize (108-118), and the
+ * zero padding of mt_collate_fn (charades_fine.py:215-226).  Bit-exact with Pillow's 8-bit ImagingResample. */
+
+/* HOST functions (no GPU): Pillow's bilinear coefficient table for resampling a whole axis in_size -> out_size.
+ * ksize = 2*ceil(max(in/out,1)) + 1 taps per output; bounds [out,2] = (first input index, tap count);
+ * kk [out,ksize] 22-bit fixed-point weights (host pointers, caller-allocated). */
+int cf_resample_ksize(int in_size, int out_size);
+int cf_resample_coeffs(int in_size, int out_size, int* bounds, int* kk);
+
+/* lut [3,256] (device) = ((v/255) - mean_c) / std_c with every step rounded to fp32 (ToTensor + Normalize). */
+int cf_normalize_lut(float* lut, float mean0, float mean1, float mean2, float std0, float std1, float std2,
+                     cudaStream_t stream);
+
+/* frames [T,H,W,3] uint8 (device, RGB interleaved = PIL tobytes()); crop box (x1,y1,crop,crop); bounds_h, kk_h, bounds_v, kk_v: the
+ * device copies of cf_resample_coeffs(crop, size) (horizontal and vertical tables may be the same buffers);
+ * rows_max >= the largest number of crop rows any band of 16 output rows touches; flip != 0 mirrors left-right.
+ * out: base of one sample of a [B,3,t_out,size,size] fp32 batch (channel stride out_stride_c elements >=
+ * t_out*size*size); frames [T,t_out) are written as zeros (collate padding).  size % 4 == 0. */
+size_t cf_clip_preprocess_smem_bytes(int size, int rows_max);
+int cf_clip_preprocess(const uint8_t* frames, float* out, const int* bounds_h, const int* kk_h,
+                       const int* bounds_v, const int* kk_v, const float* lut, int T, int H, int W, int x1,
+                       int y1, int crop, int size, int ksize_h, int ksize_v, int rows_max, int flip,
+                       int t_out, int64_t out_stride_c, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -297,8 +297,68 @@ def gen_apmeter():
     save("apmeter", scores=scores, targets=targets, weights=weights, ap=ap, ap_weighted=apw)
 
 
+def synth_frames(T, H, W, seed):
+    """Deterministic uint8 video [T,H,W,3]: smooth colour gradients that drift over time plus per-pixel noise (both the
+    interpolation weights and the rounding of the 8-bit passes are exercised)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    frames = np.empty((T, H, W, 3), np.uint8)
+    for t in range(T):
+        for c in range(3):
+            ph = rng.uniform(0, 6.28, 3)
+            base = 127.5 + 80 * np.sin(xx * (0.05 + 0.03 * c) + ph[0] + 0.3 * t) * np.cos(yy * (0.04 + 0.02 * c) + ph[1]) \
+                + 40 * np.sin((xx + yy) * 0.21 + ph[2])
+            frames[t, ..., c] = np.clip(base + rng.integers(-25, 26, (H, W)), 0, 255).astype(np.uint8)
+    return frames
+
+
+def gen_clip_pipeline():
+    """The loader's per-frame transform chain through the reference's OWN classes and Pillow
+    (transforms/spatial_transforms.py; composition of train_fine.py:74-80; call protocol of charades_fine.py:170-172):
+    training chain (random multi-scale crop, flip) and validation chain (centre crop), up- and down-scaling."""
+    import random
+    from PIL import Image
+    from transforms import spatial_transforms as ST
+    MEAN, STD = [0.413, 0.368, 0.338], [0.131, 0.125, 0.132]           # train_fine.py:48-49
+    out = {"mean": np.array(MEAN), "std": np.array(STD)}
+    cases = [  # name, mode, (T,H,W), c_size, python random seed
+        ("train_up_112", "train", (3, 120, 160), 112, 5),
+        ("train_up_112_b", "train", (2, 120, 160), 112, 8),
+        ("train_224", "train", (1, 240, 320), 224, 1),
+        ("val_down_112", "val", (2, 120, 160), 112, 0),
+        ("val_down_64", "val", (2, 270, 480), 64, 0),
+        ("val_same_96", "val", (1, 96, 130), 96, 0),
+    ]
+    names = []
+    for name, mode, (T, H, W), size, seed in cases:
+        frames = synth_frames(T, H, W, 1000 + len(names))
+        if mode == "train":
+            tr = ST.Compose([ST.MultiScaleRandomCropMultigrid([224 / 256., 224 / 320.], size), ST.RandomHorizontalFlip(),
+                             ST.ToTensor(255), ST.Normalize(MEAN, STD)])
+        else:
+            tr = ST.Compose([ST.CenterCropScaled(size), ST.ToTensor(255), ST.Normalize(MEAN, STD)])
+        random.seed(seed)
+        tr.randomize_parameters(size)
+        imgs = [tr(Image.fromarray(frames[t])) for t in range(T)]
+        clip = torch.stack(imgs, 0).permute(1, 0, 2, 3).contiguous()                       # charades_fine.py:172
+        if mode == "train":
+            m, f = tr.transforms[0], tr.transforms[1]
+            draw = np.array([m.scale, m.tl_x, m.tl_y, f.p], np.float64)
+        else:
+            draw = np.zeros(4)
+        out.update({f"{name}/frames": frames, f"{name}/clip": clip, f"{name}/draw": draw,
+                    f"{name}/meta": np.array([size, seed, 1 if mode == "train" else 0])})
+        names.append(name)
+    # Pillow's coefficient tables indirectly: a one-pixel-high ramp resized along x pins bounds / weights for more size pairs
+    for (i, o) in [(210, 224), (168, 224), (240, 224), (500, 224), (157, 160), (360, 312)]:
+        ramp = (np.arange(i * 3) * 37 % 256).astype(np.uint8).reshape(1, i, 3)
+        img = Image.fromarray(np.repeat(ramp, 2, 0)).resize((o, 2), Image.BILINEAR)
+        out[f"ramp/{i}_{o}"] = np.asarray(img)[0]
+    save("clip_pipeline", names=np.array(names), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["interp1d", "gridpool", "gridpool_cfgshape", "gridunpool", "gaussian", "rewight",
-                             "mixing", "bottleneck", "fine_net", "coarse_net", "apmeter"]
+                             "mixing", "bottleneck", "fine_net", "coarse_net", "apmeter", "clip_pipeline"]
     for w in which:
         globals()["gen_" + w]()

@@ -140,3 +140,20 @@ def test_tc_wgrad_vs_fp64(X, K, N):
         X.pw_wgrad(rows(dy), rows(x), dw, B, K, N, g, dy2=rows(dy2), dy_mode=X.PRO_AFFINE2, dy_tabs=(cu(da), cu(db), cu(dc)),
                    x_mode=mode, x_tabs=(cu(ta), cu(tb)))
         assert relerr(dw, torch.einsum("bnthw,bkthw->nk", dyy, xx)) <= 1e-5, f"x_mode {mode}"
+
+
+@pytest.mark.parametrize("K,N", [(432, 432), (96, 96), (192, 24), (34, 130)])
+def test_tc_wgrad_with_bias_gradient(X, K, N):
+    """Weight gradient with a bias gradient (the k=1 Conv1d layers of the fusion block, x3d_coarse.py:216-219): the GEMM
+    half runs on the tensor-core kernel and the bias half as a column sum; both accumulate (+=).  R*B = 6612 rows is
+    above the tensor-core row threshold and not a multiple of any tile size."""
+    B, T, H, W = 3, 4, 29, 19
+    dy, x = synth_tensor((B, N, T, H, W), 31), synth_tensor((B, K, T, H, W), 32)
+    g = X.geom(T, H, W)
+    dw = torch.zeros(N, K, device="cuda")
+    db = torch.ones(N, device="cuda")
+    n0 = X.lib.cf_launch_count()
+    X.pw_wgrad(rows(dy), rows(x), dw, B, K, N, g, dbias=db)
+    assert X.lib.cf_launch_count() - n0 == 2, "expected tensor-core GEMM + bias column sum"
+    assert relerr(dw, torch.einsum("bnthw,bkthw->nk", dy.double(), x.double())) <= 1e-5
+    assert relerr(db, 1.0 + dy.double().sum(dim=(0, 2, 3, 4))) <= 1e-5
