@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const cf_pw_wgrad_args a,
 // ---------------------------------------------------------------------------------------
 int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream);      // x3d_pw_tc2.cu
 int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream);   // x3d_pw_wgrad_tc.cu (-1: not eligible)
+int cf_dense_s2_dgrad_try(const cf_pw_args* a, cudaStream_t stream);  // x3d_dense_dgrad.cu (-1: not eligible)
 int cf_stem_fwd_try(const cf_pw_args* a, cudaStream_t stream);         // x3d_stem.cu (-1: not the stem conv)
 int cf_stem_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream);
 
@@ -380,6 +381,10 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
                       : (a->g.pos_stride == a->N && a->accumulate && a->stats_mode == CF_STATS_NONE && !a->aux))) {
         int rct = cf_pw_conv_tc(a, stream);                  // strided 1x1x1 conv (downsample branch): row gather / scatter in the GEMM
         if (rct >= 0) return rct;
+    }
+    if (a->scatter_out) {
+        int rcd = cf_dense_s2_dgrad_try(a, stream);          // pool_1.conv1/conv2 data gradient: gather form, no atomics
+        if (rcd >= 0) return rcd;
     }
     if (a->gather_in) {
         int rcs = cf_stem_fwd_try(a, stream);               // conv1_s: specialised kernel

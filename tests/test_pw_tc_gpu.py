@@ -157,3 +157,29 @@ def test_tc_wgrad_with_bias_gradient(X, K, N):
     assert X.lib.cf_launch_count() - n0 == 2, "expected tensor-core GEMM + bias column sum"
     assert relerr(dw, torch.einsum("bnthw,bkthw->nk", dy.double(), x.double())) <= 1e-5
     assert relerr(db, 1.0 + dy.double().sum(dim=(0, 2, 3, 4))) <= 1e-5
+
+
+@pytest.mark.parametrize("Ti,Hi,Wi", [(9, 11, 14), (8, 14, 14), (4, 7, 7), (1, 2, 5)])
+@pytest.mark.parametrize("affine2", [False, True])
+def test_dense_s2_dgrad_gather_form(X, Ti, Hi, Wi, affine2):
+    """Data gradient of the dense 3x3x3 stride-2 pad-1 conv (pool_1.conv1/conv2, x3d_coarse.py:362-365) through cf_pw_conv
+    with scatter_out: 24 channels take the gather-form kernel (one launch, every input position written once, so the
+    output buffer may hold garbage); checked against autograd of F.conv3d in fp64, odd and even extents, with and without
+    the BatchNorm-backward prologue P*dz + Q*y + R."""
+    B, C = 2, 24
+    o = lambda n: (n - 1) // 2 + 1
+    To, Ho, Wo = o(Ti), o(Hi), o(Wi)
+    w = synth_tensor((C, C, 3, 3, 3), 41, 0.1)
+    dz, y = synth_tensor((B, C, To, Ho, Wo), 42), synth_tensor((B, C, To, Ho, Wo), 43)
+    P, Q, R = synth_tensor((B, C), 44), synth_tensor((B, C), 45), synth_tensor((B, C), 46)
+    v = lambda t: t.double().view(B, C, 1, 1, 1)
+    gout = v(P) * dz.double() + v(Q) * y.double() + v(R) if affine2 else dz.double()
+    xin = torch.zeros(B, C, Ti, Hi, Wi, dtype=torch.float64, requires_grad=True)
+    F.conv3d(xin, w.double(), stride=2, padding=1).backward(gout)
+    g = X.geom(To, Ho, Wo, Ti, Hi, Wi, k=(3, 3, 3), s=(2, 2, 2), p=(1, 1, 1), pos_stride=C, sample_stride=Ti * Hi * Wi * C)
+    dx = torch.full((B, C, Ti, Hi, Wi), float("nan"), device="cuda").contiguous(memory_format=CL3)
+    n0 = X.lib.cf_launch_count()
+    kw = dict(x2=rows(y), pro=X.PRO_AFFINE2, pro_tabs=(P.cuda(), Q.cuda(), R.cuda())) if affine2 else {}
+    X.pw_conv(rows(dz), w.reshape(C, C * 27).cuda(), dx, B, C, C * 27, g, w_sn=1, w_sk=C * 27, scatter_out=1, **kw)
+    assert X.lib.cf_launch_count() - n0 == 1
+    assert relerr(dx, xin.grad) <= 2e-6
