@@ -25,7 +25,6 @@
 
 #define CLIP_PRECISION_BITS 22
 #define CLIP_BAND 16
-#define CLIP_THREADS 256
 
 // ------------------------------------------------------------------------------------------------------------
 // Host: Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter (support 1.0), whole axis.
@@ -87,10 +86,9 @@ __global__ void normalize_lut_kernel(float* __restrict__ lut, float m0, float m1
     lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), m), s);     // img.float().div(255); t.sub_(m).div_(s)
 }
 
-__device__ __forceinline__ int clip8(int acc) {
-    const int v = acc >> CLIP_PRECISION_BITS;
-    return min(max(v, 0), 255);
-}
+// Bilinear (triangle) weights are >= 0 and sum to 2^22 +- ksize, so acc >> 22 is already in [0,255]:
+// acc <= 2^21 + 255 * (2^22 + ksize) < 256 * 2^22.  Pillow's clip8() is the identity here.
+__device__ __forceinline__ int round8(int acc) { return acc >> CLIP_PRECISION_BITS; }
 
 struct ClipArgs {
     const uint8_t* frames;     // [T,H,W,3]
@@ -104,18 +102,20 @@ struct ClipArgs {
     long long out_stride_c;
 };
 
-__global__ void __launch_bounds__(CLIP_THREADS) clip_preprocess_kernel(const ClipArgs a) {
+// KS3: ksize == 3 (every up-scale and the identity): tap weights live in registers.
+template <bool KS3>
+__global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* lut_s = reinterpret_cast<float*>(smem_raw);                 // 768 floats
     unsigned char* hs = smem_raw + 768 * sizeof(float);               // [rows_max][3][Sp]
-    const int tid = threadIdx.x, t = blockIdx.y, S = a.S, Sp = a.Sp;
+    const int tid = threadIdx.x, nthr = blockDim.x, t = blockIdx.y, S = a.S, Sp = a.Sp;
     const int oy0 = blockIdx.x * CLIP_BAND;
     const int nrow_out = min(CLIP_BAND, S - oy0);
     const int quads = S >> 2;
     float* outf = a.out + (size_t)t * S * S;
 
     if (t >= a.T) {                                                    // collate padding: literal zeros
-        for (int i = tid; i < nrow_out * quads; i += CLIP_THREADS) {
+        for (int i = tid; i < nrow_out * quads; i += nthr) {
             const int oy = oy0 + i / quads, q = i % quads;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) clip_preprocess_kernel(const Cli
         return;
     }
 
-    for (int i = tid; i < 768; i += CLIP_THREADS) lut_s[i] = __ldg(a.lut + i);
+    for (int i = tid; i < 768; i += nthr) lut_s[i] = __ldg(a.lut + i);
 
     // input rows (relative to the crop) this band needs: bounds are monotone in oy
     const int r0 = __ldg(a.bounds_v + 2 * oy0);
@@ -132,57 +132,94 @@ __global__ void __launch_bounds__(CLIP_THREADS) clip_preprocess_kernel(const Cli
     const int r1 = __ldg(a.bounds_v + 2 * last) + __ldg(a.bounds_v + 2 * last + 1);
     const int nrows = r1 - r0;
 
-    // ---- horizontal pass: crop rows [r0, r1) -> hs[r][c][ox] ----
-    const uint8_t* fr = a.frames + ((size_t)t * a.H + (a.y1 + r0)) * a.W * 3 + (size_t)a.x1 * 3;
-    for (int i = tid; i < nrows * S; i += CLIP_THREADS) {
-        const int r = i / S, ox = i - r * S;
+    // ---- horizontal pass: a thread owns output column ox and walks down the crop rows [r0, r1) -> hs[r][c][ox] ----
+    const size_t row_bytes = (size_t)a.W * 3;
+    const uint8_t* fr = a.frames + ((size_t)t * a.H + (a.y1 + r0)) * row_bytes + (size_t)a.x1 * 3;
+    for (int ox = tid; ox < S; ox += nthr) {
         const int xmin = __ldg(a.bounds_h + 2 * ox), n = __ldg(a.bounds_h + 2 * ox + 1);
-        const int* k = a.kk_h + ox * a.ksize_h;
-        const uint8_t* src = fr + (size_t)r * a.W * 3 + xmin * 3;
-        int s0 = 1 << (CLIP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
-        for (int j = 0; j < n; ++j) {
-            const int kj = __ldg(k + j);
-            s0 += (int)__ldg(src + 3 * j) * kj;
-            s1 += (int)__ldg(src + 3 * j + 1) * kj;
-            s2 += (int)__ldg(src + 3 * j + 2) * kj;
+        const uint8_t* src = fr + xmin * 3;
+        unsigned char* d = hs + ox;
+        if (KS3) {
+            const int k0 = __ldg(a.kk_h + ox * 3), k1 = __ldg(a.kk_h + ox * 3 + 1), k2 = __ldg(a.kk_h + ox * 3 + 2);
+            // taps beyond n have weight 0 (zero-filled table); their address is clamped onto a valid pixel.  With support 1 the
+            // window holds at most 2 pixels (xmax - xmin = 2 away from the borders), so the 2-tap loop is the one that runs.
+            const int o1 = n > 1 ? 3 : 0;
+            if (n <= 2) {
+#pragma unroll 4
+                for (int r = 0; r < nrows; ++r) {
+                    const uint8_t* p = src + (size_t)r * row_bytes;
+                    const int half = 1 << (CLIP_PRECISION_BITS - 1);
+                    const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + o1) * k1;
+                    const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + o1 + 1) * k1;
+                    const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + o1 + 2) * k1;
+                    d[(size_t)r * 3 * Sp] = (unsigned char)round8(s0);
+                    d[(size_t)r * 3 * Sp + Sp] = (unsigned char)round8(s1);
+                    d[(size_t)r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
+                }
+            } else {
+                for (int r = 0; r < nrows; ++r) {
+                    const uint8_t* p = src + (size_t)r * row_bytes;
+                    const int half = 1 << (CLIP_PRECISION_BITS - 1);
+                    const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + 3) * k1 + (int)__ldg(p + 6) * k2;
+                    const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + 4) * k1 + (int)__ldg(p + 7) * k2;
+                    const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + 5) * k1 + (int)__ldg(p + 8) * k2;
+                    d[(size_t)r * 3 * Sp] = (unsigned char)round8(s0);
+                    d[(size_t)r * 3 * Sp + Sp] = (unsigned char)round8(s1);
+                    d[(size_t)r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
+                }
+            }
+        } else {
+            const int* k = a.kk_h + ox * a.ksize_h;
+            for (int r = 0; r < nrows; ++r) {
+                const uint8_t* p = src + (size_t)r * row_bytes;
+                int s0 = 1 << (CLIP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+                for (int j = 0; j < n; ++j) {
+                    const int kj = __ldg(k + j);
+                    s0 += (int)__ldg(p + 3 * j) * kj;
+                    s1 += (int)__ldg(p + 3 * j + 1) * kj;
+                    s2 += (int)__ldg(p + 3 * j + 2) * kj;
+                }
+                d[(size_t)r * 3 * Sp] = (unsigned char)round8(s0);
+                d[(size_t)r * 3 * Sp + Sp] = (unsigned char)round8(s1);
+                d[(size_t)r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
+            }
         }
-        unsigned char* d = hs + (size_t)r * 3 * Sp + ox;
-        d[0] = (unsigned char)clip8(s0);
-        d[Sp] = (unsigned char)clip8(s1);
-        d[2 * Sp] = (unsigned char)clip8(s2);
     }
     __syncthreads();
 
-    // ---- vertical pass + normalisation table + store ----
-    for (int i = tid; i < nrow_out * quads; i += CLIP_THREADS) {
-        const int oy = oy0 + i / quads, q = i % quads;
-        const int lo = __ldg(a.bounds_v + 2 * oy) - r0, n = __ldg(a.bounds_v + 2 * oy + 1);
-        const int* k = a.kk_v + oy * a.ksize_v;
-        int acc[3][4];
+    // ---- vertical pass + normalisation table + store: a thread owns 4 adjacent columns and every (nthr/quads)-th row ----
+    const int rgs = max(nthr / quads, 1);                               // row groups working in parallel
+    const int rg = tid / quads;                                         // threads with rg >= rgs idle
+    for (int q = rg < rgs ? tid - rg * quads : quads; q < quads; q += (nthr < quads ? nthr : quads)) {
+        const int qo = a.flip ? quads - 1 - q : q;
+        for (int oy = oy0 + rg; oy < oy0 + nrow_out; oy += rgs) {
+            const int lo = __ldg(a.bounds_v + 2 * oy) - r0, n = __ldg(a.bounds_v + 2 * oy + 1);
+            const int* k = a.kk_v + oy * a.ksize_v;
+            int acc[3][4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[c][e] = 1 << (CLIP_PRECISION_BITS - 1);
-        for (int j = 0; j < n; ++j) {
-            const int kj = __ldg(k + j);
-            const unsigned char* row = hs + (size_t)(lo + j) * 3 * Sp + 4 * q;
+                for (int e = 0; e < 4; ++e) acc[c][e] = 1 << (CLIP_PRECISION_BITS - 1);
+            const unsigned char* row = hs + (size_t)lo * 3 * Sp + 4 * q;
+            for (int j = 0; j < n; ++j, row += 3 * Sp) {
+                const int kj = __ldg(k + j);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned u = *reinterpret_cast<const unsigned*>(row + c * Sp);
+                    acc[c][0] += (int)(u & 255u) * kj;
+                    acc[c][1] += (int)((u >> 8) & 255u) * kj;
+                    acc[c][2] += (int)((u >> 16) & 255u) * kj;
+                    acc[c][3] += (int)(u >> 24) * kj;
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const uchar4 u = *reinterpret_cast<const uchar4*>(row + c * Sp);
-                acc[c][0] += (int)u.x * kj;
-                acc[c][1] += (int)u.y * kj;
-                acc[c][2] += (int)u.z * kj;
-                acc[c][3] += (int)u.w * kj;
+                const float* l = lut_s + c * 256;
+                float4 v;
+                if (a.flip) v = make_float4(l[round8(acc[c][3])], l[round8(acc[c][2])], l[round8(acc[c][1])], l[round8(acc[c][0])]);
+                else        v = make_float4(l[round8(acc[c][0])], l[round8(acc[c][1])], l[round8(acc[c][2])], l[round8(acc[c][3])]);
+                stcs4(reinterpret_cast<float4*>(outf + (size_t)c * a.out_stride_c + (size_t)oy * S) + qo, v);
             }
-        }
-        const int qo = a.flip ? quads - 1 - q : q;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* l = lut_s + c * 256;
-            float4 v;
-            if (a.flip) v = make_float4(l[clip8(acc[c][3])], l[clip8(acc[c][2])], l[clip8(acc[c][1])], l[clip8(acc[c][0])]);
-            else        v = make_float4(l[clip8(acc[c][0])], l[clip8(acc[c][1])], l[clip8(acc[c][2])], l[clip8(acc[c][3])]);
-            stcs4(reinterpret_cast<float4*>(outf + (size_t)c * a.out_stride_c + (size_t)oy * S) + qo, v);
         }
     }
 }
@@ -221,12 +258,18 @@ extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* 
     a.ksize_h = ksize_h; a.ksize_v = ksize_v; a.flip = flip ? 1 : 0; a.rows_max = rows_max; a.out_stride_c = out_stride_c;
     const size_t smem = cf_clip_preprocess_smem_bytes(size, rows_max);
     CF_CHECK_ARG(smem <= 200 * 1024, "band of input rows does not fit in shared memory (down-scale factor too large)");
+    const bool ks3 = ksize_h == 3;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(clip_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ks3 ? cudaFuncSetAttribute(clip_preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(clip_preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cf_set_error("cf_clip_preprocess: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
     }
     dim3 grid(cf_cdiv(size, CLIP_BAND), t_out);
-    clip_preprocess_kernel<<<grid, CLIP_THREADS, smem, stream>>>(a);
+    // one thread per output column in the horizontal pass; (size/4) x row-groups in the vertical pass
+    int threads = ((size + 31) / 32) * 32;
+    threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
+    if (ks3) clip_preprocess_kernel<true><<<grid, threads, smem, stream>>>(a);
+    else clip_preprocess_kernel<false><<<grid, threads, smem, stream>>>(a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
