@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const cf_pw_wgrad_args a,
 // ---------------------------------------------------------------------------------------
 int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream);      // x3d_pw_tc2.cu
 int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream);   // x3d_pw_wgrad_tc.cu (-1: not eligible)
-int cf_dense_s2_dgrad_try(const cf_pw_args* a, cudaStream_t stream);  // x3d_dense_dgrad.cu (-1: not eligible)
+int cf_dense_s2_dgrad_try(const cf_pw_args* a, cudaStream_t stream);  // x3d_dense3s2.cu (-1: not eligible)
+int cf_dense_s2_fwd_try(const cf_pw_args* a, cudaStream_t stream);    // x3d_dense3s2.cu (-1: not eligible)
 int cf_stem_fwd_try(const cf_pw_args* a, cudaStream_t stream);         // x3d_stem.cu (-1: not the stem conv)
 int cf_stem_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream);
 
@@ -387,6 +388,8 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
         if (rcd >= 0) return rcd;
     }
     if (a->gather_in) {
+        int rcf = cf_dense_s2_fwd_try(a, stream);            // pool_1.conv1/conv2 forward: direct kernel
+        if (rcf >= 0) return rcf;
         int rcs = cf_stem_fwd_try(a, stream);               // conv1_s: specialised kernel
         if (rcs >= 0) return rcs;
         if (a->N <= 32) return launch_pw<32, true>(a, R, stream);

@@ -183,3 +183,32 @@ def test_dense_s2_dgrad_gather_form(X, Ti, Hi, Wi, affine2):
     X.pw_conv(rows(dz), w.reshape(C, C * 27).cuda(), dx, B, C, C * 27, g, w_sn=1, w_sk=C * 27, scatter_out=1, **kw)
     assert X.lib.cf_launch_count() - n0 == 1
     assert relerr(dx, xin.grad) <= 2e-6
+
+
+@pytest.mark.parametrize("Ti,Hi,Wi", [(9, 11, 14), (8, 14, 14), (4, 7, 7), (1, 2, 5), (16, 28, 28)])
+@pytest.mark.parametrize("pro", ["none", "affine_relu"])
+def test_dense_s2_forward_direct(X, Ti, Hi, Wi, pro):
+    """Forward of the dense 3x3x3 stride-2 pad-1 24->24 conv with bias (pool_1.conv1/conv2) through cf_pw_conv with
+    gather_in: the direct kernel (one launch) against F.conv3d in fp64, with the bn+ReLU prologue of conv2 (zero padding
+    AFTER the prologue) and the BatchNorm statistics of the output; (16,28,28) spans several CTAs per sample."""
+    B, C = 2, 24
+    o = lambda n: (n - 1) // 2 + 1
+    To, Ho, Wo = o(Ti), o(Hi), o(Wi)
+    w, bias = synth_tensor((C, C, 3, 3, 3), 51, 0.1), synth_tensor((C,), 52)
+    x = synth_tensor((B, C, Ti, Hi, Wi), 53)
+    pa, pb = synth_tensor((B, C), 54), synth_tensor((B, C), 55)
+    xin = x.double()
+    if pro == "affine_relu":
+        xin = F.relu(pa.double().view(B, C, 1, 1, 1) * xin + pb.double().view(B, C, 1, 1, 1))
+    ref = F.conv3d(xin, w.double(), bias.double(), stride=2, padding=1)
+    g = X.geom(To, Ho, Wo, Ti, Hi, Wi, k=(3, 3, 3), s=(2, 2, 2), p=(1, 1, 1), pos_stride=C, sample_stride=Ti * Hi * Wi * C)
+    y = torch.full((B, C, To, Ho, Wo), float("nan"), device="cuda").contiguous(memory_format=CL3)
+    stats = torch.zeros(B, C, 2, device="cuda", dtype=torch.float64)
+    kw = dict(pro=X.PRO_AFFINE_RELU, pro_tabs=(pa.cuda(), pb.cuda(), None)) if pro == "affine_relu" else {}
+    n0 = X.lib.cf_launch_count()
+    X.pw_conv(rows(x), w.reshape(C, C * 27).cuda(), y, B, C * 27, C, g, bias=bias.cuda(), gather_in=1, stats=stats,
+              stats_mode=X.STATS_SUM_SQ, **kw)
+    assert X.lib.cf_launch_count() - n0 == 1
+    assert relerr(y, ref) <= 2e-6
+    assert relerr(stats[..., 0], ref.sum(dim=(2, 3, 4))) <= 1e-5
+    assert relerr(stats[..., 1], (ref * ref).sum(dim=(2, 3, 4))) <= 1e-5
