@@ -98,129 +98,149 @@ struct ClipArgs {
     const int* bounds_v;
     const int* kk_v;
     const float* lut;          // [3,256]
-    int T, H, W, x1, y1, S, Sp, ksize_h, ksize_v, flip, rows_max;
+    int T, Tout, H, W, x1, y1, S, Sp, ksize_h, ksize_v, flip, rows_max;
     long long out_stride_c;
 };
 
-// KS3: ksize == 3 (every up-scale and the identity): tap weights live in registers.
-template <bool KS3>
+#define CLIP_FPB 4        // frames per CTA: tables, bounds and per-thread set-up are amortised over them
+
+// byte i of a 32-bit word as an int (one PRMT)
+__device__ __forceinline__ int byte_of(unsigned u, int i) { return (int)__byte_perm(u, 0u, 0x4440u + (unsigned)i); }
+// table[(acc >> 22)] with the index scaled in one shift + mask
+__device__ __forceinline__ float lut_at(const float* l, int acc) {
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(l) + ((acc >> (CLIP_PRECISION_BITS - 2)) & 0x3fc));
+}
+
+// KS3: ksize == 3 (every up-scale and the identity): horizontal tap weights live in registers.
+template <bool KS3, bool FLIP>
 __global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* lut_s = reinterpret_cast<float*>(smem_raw);                 // 768 floats
-    unsigned char* hs = smem_raw + 768 * sizeof(float);               // [rows_max][3][Sp]
-    const int tid = threadIdx.x, nthr = blockDim.x, t = blockIdx.y, S = a.S, Sp = a.Sp;
+    int* vb = reinterpret_cast<int*>(smem_raw + 768 * sizeof(float));  // [CLIP_BAND][2]  (first row relative to r0, taps)
+    int* vk = vb + 2 * CLIP_BAND;                                      // [CLIP_BAND][ksize_v]
+    unsigned char* hs = reinterpret_cast<unsigned char*>(vk + CLIP_BAND * a.ksize_v);   // [rows_max][3][Sp], 16-byte aligned by the host
+    const int tid = threadIdx.x, nthr = blockDim.x, S = a.S, Sp = a.Sp;
     const int oy0 = blockIdx.x * CLIP_BAND;
     const int nrow_out = min(CLIP_BAND, S - oy0);
     const int quads = S >> 2;
-    float* outf = a.out + (size_t)t * S * S;
-
-    if (t >= a.T) {                                                    // collate padding: literal zeros
-        for (int i = tid; i < nrow_out * quads; i += nthr) {
-            const int oy = oy0 + i / quads, q = i % quads;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                stcs4(reinterpret_cast<float4*>(outf + (size_t)c * a.out_stride_c + (size_t)oy * S) + q, f4_zero());
-        }
-        return;
-    }
-
-    for (int i = tid; i < 768; i += nthr) lut_s[i] = __ldg(a.lut + i);
 
     // input rows (relative to the crop) this band needs: bounds are monotone in oy
     const int r0 = __ldg(a.bounds_v + 2 * oy0);
     const int last = oy0 + nrow_out - 1;
-    const int r1 = __ldg(a.bounds_v + 2 * last) + __ldg(a.bounds_v + 2 * last + 1);
-    const int nrows = r1 - r0;
+    const int nrows = __ldg(a.bounds_v + 2 * last) + __ldg(a.bounds_v + 2 * last + 1) - r0;
+    for (int i = tid; i < 768; i += nthr) lut_s[i] = __ldg(a.lut + i);
+    for (int i = tid; i < nrow_out; i += nthr) {
+        vb[2 * i] = __ldg(a.bounds_v + 2 * (oy0 + i)) - r0;
+        vb[2 * i + 1] = __ldg(a.bounds_v + 2 * (oy0 + i) + 1);
+    }
+    for (int i = tid; i < nrow_out * a.ksize_v; i += nthr) vk[i] = __ldg(a.kk_v + oy0 * a.ksize_v + i);
 
-    // ---- horizontal pass: a thread owns output column ox and walks down the crop rows [r0, r1) -> hs[r][c][ox] ----
+    // vertical-pass role of this thread: 4 adjacent columns (quad q) of every rgs-th row of the band
+    const int rgs = max(nthr / quads, 1);
+    const int rg = tid / quads;
+    const int q_first = rg < rgs ? tid - rg * quads : quads;            // threads beyond rgs*quads idle in the vertical pass
+    const int q_step = nthr < quads ? nthr : quads;
     const size_t row_bytes = (size_t)a.W * 3;
-    const uint8_t* fr = a.frames + ((size_t)t * a.H + (a.y1 + r0)) * row_bytes + (size_t)a.x1 * 3;
-    for (int ox = tid; ox < S; ox += nthr) {
-        const int xmin = __ldg(a.bounds_h + 2 * ox), n = __ldg(a.bounds_h + 2 * ox + 1);
-        const uint8_t* src = fr + xmin * 3;
-        unsigned char* d = hs + ox;
-        if (KS3) {
-            const int k0 = __ldg(a.kk_h + ox * 3), k1 = __ldg(a.kk_h + ox * 3 + 1), k2 = __ldg(a.kk_h + ox * 3 + 2);
-            // taps beyond n have weight 0 (zero-filled table); their address is clamped onto a valid pixel.  With support 1 the
-            // window holds at most 2 pixels (xmax - xmin = 2 away from the borders), so the 2-tap loop is the one that runs.
-            const int o1 = n > 1 ? 3 : 0;
-            if (n <= 2) {
+    const int t_end = (blockIdx.y + 1) * CLIP_FPB;
+
+    for (int t = blockIdx.y * CLIP_FPB; t < t_end; ++t) {
+        float* outf = a.out + (size_t)t * S * S;
+        const bool live = t < a.T;
+        if (t >= a.Tout) break;                                         // uniform over the CTA
+        if (live) {
+            // ---- horizontal pass: a thread owns output column ox and walks down the crop rows [r0, r0+nrows) -> hs[r][c][ox] ----
+            const uint8_t* fr = a.frames + ((size_t)t * a.H + (a.y1 + r0)) * row_bytes + (size_t)a.x1 * 3;
+            for (int ox = tid; ox < S; ox += nthr) {
+                const int xmin = __ldg(a.bounds_h + 2 * ox), n = __ldg(a.bounds_h + 2 * ox + 1);
+                const uint8_t* src = fr + xmin * 3;
+                unsigned char* d = hs + ox;
+                const int half = 1 << (CLIP_PRECISION_BITS - 1);
+                if (KS3) {
+                    const int k0 = __ldg(a.kk_h + ox * 3), k1 = __ldg(a.kk_h + ox * 3 + 1), k2 = __ldg(a.kk_h + ox * 3 + 2);
+                    // taps beyond n have weight 0 (zero-filled table); their address is clamped onto a valid pixel.  With support 1
+                    // the window holds at most 2 pixels (xmax - xmin = 2 away from the borders): the 2-tap loop is the one that runs.
+                    const int o1 = n > 1 ? 3 : 0;
+                    if (n <= 2) {
 #pragma unroll 4
-                for (int r = 0; r < nrows; ++r) {
-                    const uint8_t* p = src + (size_t)r * row_bytes;
-                    const int half = 1 << (CLIP_PRECISION_BITS - 1);
-                    const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + o1) * k1;
-                    const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + o1 + 1) * k1;
-                    const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + o1 + 2) * k1;
-                    d[(size_t)r * 3 * Sp] = (unsigned char)round8(s0);
-                    d[(size_t)r * 3 * Sp + Sp] = (unsigned char)round8(s1);
-                    d[(size_t)r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
+                        for (int r = 0; r < nrows; ++r) {
+                            const uint8_t* p = src + (size_t)r * row_bytes;
+                            const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + o1) * k1;
+                            const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + o1 + 1) * k1;
+                            const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + o1 + 2) * k1;
+                            d[r * 3 * Sp] = (unsigned char)round8(s0);
+                            d[r * 3 * Sp + Sp] = (unsigned char)round8(s1);
+                            d[r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
+                        }
+                    } else {
+                        for (int r = 0; r < nrows; ++r) {
+                            const uint8_t* p = src + (size_t)r * row_bytes;
+                            const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + 3) * k1 + (int)__ldg(p + 6) * k2;
+                            const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + 4) * k1 + (int)__ldg(p + 7) * k2;
+                            const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + 5) * k1 + (int)__ldg(p + 8) * k2;
+                            d[r * 3 * Sp] = (unsigned char)round8(s0);
+                            d[r * 3 * Sp + Sp] = (unsigned char)round8(s1);
+                            d[r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
+                        }
+                    }
+                } else {
+                    const int* k = a.kk_h + ox * a.ksize_h;
+#pragma unroll 2
+                    for (int r = 0; r < nrows; ++r) {
+                        const uint8_t* p = src + (size_t)r * row_bytes;
+                        int s0 = half, s1 = half, s2 = half;
+                        for (int j = 0; j < n; ++j) {
+                            const int kj = __ldg(k + j);
+                            s0 += (int)__ldg(p + 3 * j) * kj;
+                            s1 += (int)__ldg(p + 3 * j + 1) * kj;
+                            s2 += (int)__ldg(p + 3 * j + 2) * kj;
+                        }
+                        d[r * 3 * Sp] = (unsigned char)round8(s0);
+                        d[r * 3 * Sp + Sp] = (unsigned char)round8(s1);
+                        d[r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
+                    }
                 }
-            } else {
-                for (int r = 0; r < nrows; ++r) {
-                    const uint8_t* p = src + (size_t)r * row_bytes;
-                    const int half = 1 << (CLIP_PRECISION_BITS - 1);
-                    const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + 3) * k1 + (int)__ldg(p + 6) * k2;
-                    const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + 4) * k1 + (int)__ldg(p + 7) * k2;
-                    const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + 5) * k1 + (int)__ldg(p + 8) * k2;
-                    d[(size_t)r * 3 * Sp] = (unsigned char)round8(s0);
-                    d[(size_t)r * 3 * Sp + Sp] = (unsigned char)round8(s1);
-                    d[(size_t)r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
-                }
-            }
-        } else {
-            const int* k = a.kk_h + ox * a.ksize_h;
-            for (int r = 0; r < nrows; ++r) {
-                const uint8_t* p = src + (size_t)r * row_bytes;
-                int s0 = 1 << (CLIP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
-                for (int j = 0; j < n; ++j) {
-                    const int kj = __ldg(k + j);
-                    s0 += (int)__ldg(p + 3 * j) * kj;
-                    s1 += (int)__ldg(p + 3 * j + 1) * kj;
-                    s2 += (int)__ldg(p + 3 * j + 2) * kj;
-                }
-                d[(size_t)r * 3 * Sp] = (unsigned char)round8(s0);
-                d[(size_t)r * 3 * Sp + Sp] = (unsigned char)round8(s1);
-                d[(size_t)r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();                                                // hs (and, first time, the tables) complete
 
-    // ---- vertical pass + normalisation table + store: a thread owns 4 adjacent columns and every (nthr/quads)-th row ----
-    const int rgs = max(nthr / quads, 1);                               // row groups working in parallel
-    const int rg = tid / quads;                                         // threads with rg >= rgs idle
-    for (int q = rg < rgs ? tid - rg * quads : quads; q < quads; q += (nthr < quads ? nthr : quads)) {
-        const int qo = a.flip ? quads - 1 - q : q;
-        for (int oy = oy0 + rg; oy < oy0 + nrow_out; oy += rgs) {
-            const int lo = __ldg(a.bounds_v + 2 * oy) - r0, n = __ldg(a.bounds_v + 2 * oy + 1);
-            const int* k = a.kk_v + oy * a.ksize_v;
-            int acc[3][4];
+        // ---- vertical pass + normalisation table + store ----
+        for (int q = q_first; q < quads; q += q_step) {
+            const int qo = FLIP ? quads - 1 - q : q;
+            for (int i = rg; i < nrow_out; i += rgs) {
+                float* orow = outf + (size_t)(oy0 + i) * S + 4 * qo;
+                if (!live) {                                            // collate padding: literal zeros
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+                    for (int c = 0; c < 3; ++c) stcs4(reinterpret_cast<float4*>(orow + (size_t)c * a.out_stride_c), f4_zero());
+                    continue;
+                }
+                const int lo = vb[2 * i], n = vb[2 * i + 1];
+                const int* k = vk + i * a.ksize_v;
+                int acc[3][4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) acc[c][e] = 1 << (CLIP_PRECISION_BITS - 1);
-            const unsigned char* row = hs + (size_t)lo * 3 * Sp + 4 * q;
-            for (int j = 0; j < n; ++j, row += 3 * Sp) {
-                const int kj = __ldg(k + j);
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[c][e] = 1 << (CLIP_PRECISION_BITS - 1);
+                const unsigned char* row = hs + lo * 3 * Sp + 4 * q;
+                for (int j = 0; j < n; ++j, row += 3 * Sp) {
+                    const int kj = k[j];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const unsigned u = *reinterpret_cast<const unsigned*>(row + c * Sp);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[c][e] += byte_of(u, e) * kj;
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const unsigned u = *reinterpret_cast<const unsigned*>(row + c * Sp);
-                    acc[c][0] += (int)(u & 255u) * kj;
-                    acc[c][1] += (int)((u >> 8) & 255u) * kj;
-                    acc[c][2] += (int)((u >> 16) & 255u) * kj;
-                    acc[c][3] += (int)(u >> 24) * kj;
+                    const float* l = lut_s + c * 256;
+                    float4 v;
+                    if (FLIP) v = make_float4(lut_at(l, acc[c][3]), lut_at(l, acc[c][2]), lut_at(l, acc[c][1]), lut_at(l, acc[c][0]));
+                    else      v = make_float4(lut_at(l, acc[c][0]), lut_at(l, acc[c][1]), lut_at(l, acc[c][2]), lut_at(l, acc[c][3]));
+                    stcs4(reinterpret_cast<float4*>(orow + (size_t)c * a.out_stride_c), v);
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float* l = lut_s + c * 256;
-                float4 v;
-                if (a.flip) v = make_float4(l[round8(acc[c][3])], l[round8(acc[c][2])], l[round8(acc[c][1])], l[round8(acc[c][0])]);
-                else        v = make_float4(l[round8(acc[c][0])], l[round8(acc[c][1])], l[round8(acc[c][2])], l[round8(acc[c][3])]);
-                stcs4(reinterpret_cast<float4*>(outf + (size_t)c * a.out_stride_c + (size_t)oy * S) + qo, v);
-            }
         }
+        __syncthreads();                                                // hs is rewritten by the next frame
     }
 }
 
@@ -233,9 +253,15 @@ extern "C" int cf_normalize_lut(float* lut, float mean0, float mean1, float mean
     return CF_OK;
 }
 
-extern "C" size_t cf_clip_preprocess_smem_bytes(int size, int rows_max) {
+static size_t clip_smem_bytes(int size, int rows_max, int ksize_v) {
     const int Sp = (size + 15) & ~15;
-    return 768 * sizeof(float) + (size_t)rows_max * 3 * Sp;
+    size_t tables = 768 * sizeof(float) + (size_t)CLIP_BAND * (2 + ksize_v) * sizeof(int);
+    tables = (tables + 15) & ~(size_t)15;
+    return tables + (size_t)rows_max * 3 * Sp;
+}
+
+extern "C" size_t cf_clip_preprocess_smem_bytes(int size, int rows_max, int ksize) {
+    return clip_smem_bytes(size, rows_max, ksize);
 }
 
 extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* bounds_h, const int* kk_h,
@@ -254,22 +280,22 @@ extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* 
     CF_CHECK_ARG(t_out <= 65535, "t_out above the grid limit");
     ClipArgs a;
     a.frames = frames; a.out = out; a.bounds_h = bounds_h; a.kk_h = kk_h; a.bounds_v = bounds_v; a.kk_v = kk_v; a.lut = lut;
-    a.T = T; a.H = H; a.W = W; a.x1 = x1; a.y1 = y1; a.S = size; a.Sp = (size + 15) & ~15;
+    a.T = T; a.Tout = t_out; a.H = H; a.W = W; a.x1 = x1; a.y1 = y1; a.S = size; a.Sp = (size + 15) & ~15;
     a.ksize_h = ksize_h; a.ksize_v = ksize_v; a.flip = flip ? 1 : 0; a.rows_max = rows_max; a.out_stride_c = out_stride_c;
-    const size_t smem = cf_clip_preprocess_smem_bytes(size, rows_max);
+    const size_t smem = clip_smem_bytes(size, rows_max, ksize_v);
     CF_CHECK_ARG(smem <= 200 * 1024, "band of input rows does not fit in shared memory (down-scale factor too large)");
     const bool ks3 = ksize_h == 3;
+    void (*kern)(const ClipArgs) = ks3 ? (flip ? clip_preprocess_kernel<true, true> : clip_preprocess_kernel<true, false>)
+                                       : (flip ? clip_preprocess_kernel<false, true> : clip_preprocess_kernel<false, false>);
     if (smem > 48 * 1024) {
-        cudaError_t e = ks3 ? cudaFuncSetAttribute(clip_preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(clip_preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cf_set_error("cf_clip_preprocess: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
     }
-    dim3 grid(cf_cdiv(size, CLIP_BAND), t_out);
+    dim3 grid(cf_cdiv(size, CLIP_BAND), cf_cdiv(t_out, CLIP_FPB));
     // one thread per output column in the horizontal pass; (size/4) x row-groups in the vertical pass
     int threads = ((size + 31) / 32) * 32;
     threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
-    if (ks3) clip_preprocess_kernel<true><<<grid, threads, smem, stream>>>(a);
-    else clip_preprocess_kernel<false><<<grid, threads, smem, stream>>>(a);
+    kern<<<grid, threads, smem, stream>>>(a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

@@ -513,7 +513,7 @@ int cf_normalize_lut(float* lut, float mean0, float mean1, float mean2, float st
  * rows_max >= the largest number of crop rows any band of 16 output rows touches; flip != 0 mirrors left-right.
  * out: base of one sample of a [B,3,t_out,size,size] fp32 batch (channel stride out_stride_c elements >=
  * t_out*size*size); frames [T,t_out) are written as zeros (collate padding).  size % 4 == 0. */
-size_t cf_clip_preprocess_smem_bytes(int size, int rows_max);
+size_t cf_clip_preprocess_smem_bytes(int size, int rows_max, int ksize);   /* dynamic shared memory of the launch (<= 200 KB) */
 int cf_clip_preprocess(const uint8_t* frames, float* out, const int* bounds_h, const int* kk_h,
                        const int* bounds_v, const int* kk_v, const float* lut, int T, int H, int W, int x1,
                        int y1, int crop, int size, int ksize_h, int ksize_v, int rows_max, int flip,
