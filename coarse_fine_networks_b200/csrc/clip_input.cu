@@ -102,7 +102,8 @@ struct ClipArgs {
     long long out_stride_c;
 };
 
-#define CLIP_FPB 4        // frames per CTA: tables, bounds and per-thread set-up are amortised over them
+// A CTA keeps its band and walks over the frames t = blockIdx.y, blockIdx.y + gridDim.y, ...: tables, bounds and the
+// per-thread set-up are amortised over them, and the grid is sized to ONE resident wave (no tail wave).
 
 // byte i of a 32-bit word as an int (one PRMT)
 __device__ __forceinline__ int byte_of(unsigned u, int i) { return (int)__byte_perm(u, 0u, 0x4440u + (unsigned)i); }
@@ -141,12 +142,10 @@ __global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) 
     const int q_first = rg < rgs ? tid - rg * quads : quads;            // threads beyond rgs*quads idle in the vertical pass
     const int q_step = nthr < quads ? nthr : quads;
     const size_t row_bytes = (size_t)a.W * 3;
-    const int t_end = (blockIdx.y + 1) * CLIP_FPB;
 
-    for (int t = blockIdx.y * CLIP_FPB; t < t_end; ++t) {
+    for (int t = blockIdx.y; t < a.Tout; t += gridDim.y) {             // uniform over the CTA
         float* outf = a.out + (size_t)t * S * S;
         const bool live = t < a.T;
-        if (t >= a.Tout) break;                                         // uniform over the CTA
         if (live) {
             // ---- horizontal pass: a thread owns output column ox and walks down the crop rows [r0, r0+nrows) -> hs[r][c][ox] ----
             const uint8_t* fr = a.frames + ((size_t)t * a.H + (a.y1 + r0)) * row_bytes + (size_t)a.x1 * 3;
@@ -155,48 +154,62 @@ __global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) 
                 const uint8_t* src = fr + xmin * 3;
                 unsigned char* d = hs + ox;
                 const int half = 1 << (CLIP_PRECISION_BITS - 1);
-                if (KS3) {
-                    const int k0 = __ldg(a.kk_h + ox * 3), k1 = __ldg(a.kk_h + ox * 3 + 1), k2 = __ldg(a.kk_h + ox * 3 + 2);
-                    // taps beyond n have weight 0 (zero-filled table); their address is clamped onto a valid pixel.  With support 1
-                    // the window holds at most 2 pixels (xmax - xmin = 2 away from the borders): the 2-tap loop is the one that runs.
-                    const int o1 = n > 1 ? 3 : 0;
-                    if (n <= 2) {
+                if (KS3 && n == 2) {
+                    // support 1: the window holds exactly 2 pixels away from the borders -> 6 adjacent bytes, immediate offsets,
+                    // one global and three shared pointers advanced per row
+                    const int k0 = __ldg(a.kk_h + ox * 3), k1 = __ldg(a.kk_h + ox * 3 + 1);
+                    const uint8_t* p = src;
+                    unsigned char *d0 = d, *d1 = d + Sp, *d2 = d + 2 * Sp;
+                    const int dstep = 3 * Sp;
 #pragma unroll 4
-                        for (int r = 0; r < nrows; ++r) {
-                            const uint8_t* p = src + (size_t)r * row_bytes;
-                            const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + o1) * k1;
-                            const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + o1 + 1) * k1;
-                            const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + o1 + 2) * k1;
-                            d[r * 3 * Sp] = (unsigned char)round8(s0);
-                            d[r * 3 * Sp + Sp] = (unsigned char)round8(s1);
-                            d[r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
-                        }
-                    } else {
-                        for (int r = 0; r < nrows; ++r) {
-                            const uint8_t* p = src + (size_t)r * row_bytes;
-                            const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + 3) * k1 + (int)__ldg(p + 6) * k2;
-                            const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + 4) * k1 + (int)__ldg(p + 7) * k2;
-                            const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + 5) * k1 + (int)__ldg(p + 8) * k2;
-                            d[r * 3 * Sp] = (unsigned char)round8(s0);
-                            d[r * 3 * Sp + Sp] = (unsigned char)round8(s1);
-                            d[r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
-                        }
+                    for (int r = 0; r < nrows; ++r) {
+                        const int s0 = half + (int)__ldg(p) * k0 + (int)__ldg(p + 3) * k1;
+                        const int s1 = half + (int)__ldg(p + 1) * k0 + (int)__ldg(p + 4) * k1;
+                        const int s2 = half + (int)__ldg(p + 2) * k0 + (int)__ldg(p + 5) * k1;
+                        *d0 = (unsigned char)round8(s0);
+                        *d1 = (unsigned char)round8(s1);
+                        *d2 = (unsigned char)round8(s2);
+                        p += row_bytes; d0 += dstep; d1 += dstep; d2 += dstep;
                     }
                 } else {
                     const int* k = a.kk_h + ox * a.ksize_h;
+                    const uint8_t* p = src;
+                    unsigned char *d0 = d, *d1 = d + Sp, *d2 = d + 2 * Sp;
+                    const int dstep = 3 * Sp;
+                    if (n <= 4) {                                       // down-scales below 1.5x and border columns: weights in registers
+                        int kr[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) kr[j] = j < n ? __ldg(k + j) : 0;
 #pragma unroll 2
-                    for (int r = 0; r < nrows; ++r) {
-                        const uint8_t* p = src + (size_t)r * row_bytes;
-                        int s0 = half, s1 = half, s2 = half;
-                        for (int j = 0; j < n; ++j) {
-                            const int kj = __ldg(k + j);
-                            s0 += (int)__ldg(p + 3 * j) * kj;
-                            s1 += (int)__ldg(p + 3 * j + 1) * kj;
-                            s2 += (int)__ldg(p + 3 * j + 2) * kj;
+                        for (int r = 0; r < nrows; ++r) {
+                            int s0 = half, s1 = half, s2 = half;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (j < n) {
+                                    s0 += (int)__ldg(p + 3 * j) * kr[j];
+                                    s1 += (int)__ldg(p + 3 * j + 1) * kr[j];
+                                    s2 += (int)__ldg(p + 3 * j + 2) * kr[j];
+                                }
+                            }
+                            *d0 = (unsigned char)round8(s0);
+                            *d1 = (unsigned char)round8(s1);
+                            *d2 = (unsigned char)round8(s2);
+                            p += row_bytes; d0 += dstep; d1 += dstep; d2 += dstep;
                         }
-                        d[r * 3 * Sp] = (unsigned char)round8(s0);
-                        d[r * 3 * Sp + Sp] = (unsigned char)round8(s1);
-                        d[r * 3 * Sp + 2 * Sp] = (unsigned char)round8(s2);
+                    } else {
+                        for (int r = 0; r < nrows; ++r) {
+                            int s0 = half, s1 = half, s2 = half;
+                            for (int j = 0; j < n; ++j) {
+                                const int kj = __ldg(k + j);
+                                s0 += (int)__ldg(p + 3 * j) * kj;
+                                s1 += (int)__ldg(p + 3 * j + 1) * kj;
+                                s2 += (int)__ldg(p + 3 * j + 2) * kj;
+                            }
+                            *d0 = (unsigned char)round8(s0);
+                            *d1 = (unsigned char)round8(s1);
+                            *d2 = (unsigned char)round8(s2);
+                            p += row_bytes; d0 += dstep; d1 += dstep; d2 += dstep;
+                        }
                     }
                 }
             }
@@ -291,10 +304,17 @@ extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* 
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cf_set_error("cf_clip_preprocess: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
     }
-    dim3 grid(cf_cdiv(size, CLIP_BAND), cf_cdiv(t_out, CLIP_FPB));
     // one thread per output column in the horizontal pass; (size/4) x row-groups in the vertical pass
     int threads = ((size + 31) / 32) * 32;
     threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int sms = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int bands = cf_cdiv(size, CLIP_BAND);
+    int groups = (per_sm * sms) / bands;                                // frame groups that fit in one resident wave
+    groups = groups < 1 ? 1 : (groups > t_out ? t_out : groups);
+    dim3 grid(bands, groups);
     kern<<<grid, threads, smem, stream>>>(a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();

@@ -326,3 +326,178 @@ int cf_dense_s2_fwd_try(const cf_pw_args* a, cudaStream_t stream) {
     CF_CHECK_LAUNCH();
     return CF_OK;
 }
+
+// ---- weight gradient ----
+// dw[co][ci*27 + tap] += sum_{b,o} pro_dy(dz[b,o,co]) * pro_x(x[b, 2*o - 1 + tap, ci]);   dbias[co] += sum pro_dy(...)
+// The generic path (pw_wgrad_kernel with the tap gather) tiles the 24 x 648 result 64 x 64 and re-gathers the input for
+// every tile (1.1 ms for pool_1.conv1 at the bench shape).  Here a persistent CTA stages 32 output rows at a time --
+// the prologue'd output gradient [32][24] and the gathered, prologue'd input [32][27][24] (zeros outside the volume) -- in
+// shared memory, and 252 threads each own a 4 taps x 4 co x 4 ci block of the result in registers (64 accumulators,
+// one float4 of dz and four float4 of x per row: 64 FMAs per 5 shared-memory reads).  One atomicAdd per result element
+// and CTA at the end.
+#define WG3_THREADS 256
+#define WG3_ROWS 32
+
+struct Wg3Args {
+    const float* dz;      // dense [B,R,C]
+    const float* y;       // second input of AFFINE2 or NULL
+    const float* P;       // [B,C] or NULL
+    const float* Q;
+    const float* Rc;
+    const float* x;       // gathered side
+    const float* xa;      // [B,C] or NULL
+    const float* xb;
+    float* dw;            // [C][C*27]
+    float* dbias;         // [C] or NULL
+    int B, To, Ho, Wo, Ti, Hi, Wi;
+    long long sample_stride;
+    int dy_affine2, x_mode;
+    int chunks_per_sample;
+};
+
+template <int C>
+__global__ void __launch_bounds__(WG3_THREADS, 2) dense3_s2_wgrad_kernel(const Wg3Args a) {
+    constexpr int C4 = C / 4;                                 // 6
+    extern __shared__ __align__(16) float wg_smem[];
+    float* dzs = wg_smem;                                     // [WG3_ROWS][C]
+    float* xs = dzs + WG3_ROWS * C;                           // [WG3_ROWS][27][C]
+    const int tid = threadIdx.x;
+    const int R = a.To * a.Ho * a.Wo;
+    // compute role: (tap group, co group, ci group)
+    const int cig = tid % C4, cog = (tid / C4) % C4, tg = tid / (C4 * C4);
+    const bool worker = tg < 7;
+    const int ntap = worker ? min(4, 27 - tg * 4) : 0;
+    float acc[4][4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+    float bsum = 0.f;                                         // threads 0..C-1: bias gradient of channel tid
+
+    const int total = a.B * a.chunks_per_sample;
+    for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+        const int b = chunk / a.chunks_per_sample;
+        const int row0 = (chunk - b * a.chunks_per_sample) * WG3_ROWS;
+        // ---- stage dz (prologue applied; rows beyond R are zero) ----
+        if (tid < WG3_ROWS * C4) {
+            const int r = tid / C4, q = tid - r * C4;
+            float4 d = f4_zero();
+            if (row0 + r < R) {
+                const size_t off = ((size_t)b * R + row0 + r) * C + 4 * q;
+                d = __ldg(reinterpret_cast<const float4*>(a.dz + off));
+                if (a.dy_affine2) {
+                    const float4 yy = __ldg(reinterpret_cast<const float4*>(a.y + off));
+                    const float* P = a.P + (size_t)b * C + 4 * q;
+                    const float* Q = a.Q + (size_t)b * C + 4 * q;
+                    const float4 rc = a.Rc ? *reinterpret_cast<const float4*>(a.Rc + (size_t)b * C + 4 * q) : f4_zero();
+                    d.x = fmaf(P[0], d.x, fmaf(Q[0], yy.x, rc.x));
+                    d.y = fmaf(P[1], d.y, fmaf(Q[1], yy.y, rc.y));
+                    d.z = fmaf(P[2], d.z, fmaf(Q[2], yy.z, rc.z));
+                    d.w = fmaf(P[3], d.w, fmaf(Q[3], yy.w, rc.w));
+                }
+            }
+            *reinterpret_cast<float4*>(dzs + r * C + 4 * q) = d;
+        }
+        // ---- stage the gathered input: item = (row, tap, channel quad) ----
+        const float* xbase = a.x + (size_t)b * a.sample_stride;
+        for (int e = tid; e < WG3_ROWS * 27 * C4; e += WG3_THREADS) {
+            const int q = e % C4, rt = e / C4, tap = rt % 27, r = rt / 27;
+            float4 v = f4_zero();
+            const int row = row0 + r;
+            if (row < R) {
+                const int ow = row % a.Wo, qq = row / a.Wo, oh = qq % a.Ho, ot = qq / a.Ho;
+                const int ti = 2 * ot - 1 + tap / 9, hi = 2 * oh - 1 + (tap / 3) % 3, wi = 2 * ow - 1 + tap % 3;
+                if ((unsigned)ti < (unsigned)a.Ti && (unsigned)hi < (unsigned)a.Hi && (unsigned)wi < (unsigned)a.Wi) {
+                    v = __ldg(reinterpret_cast<const float4*>(xbase + (((size_t)ti * a.Hi + hi) * a.Wi + wi) * C + 4 * q));
+                    if (a.x_mode != CF_PRO_NONE) {
+                        const float* xa = a.xa + (size_t)b * C + 4 * q;
+                        const float* xb = a.xb + (size_t)b * C + 4 * q;
+                        v.x = fmaf(xa[0], v.x, xb[0]); v.y = fmaf(xa[1], v.y, xb[1]);
+                        v.z = fmaf(xa[2], v.z, xb[2]); v.w = fmaf(xa[3], v.w, xb[3]);
+                        if (a.x_mode == CF_PRO_AFFINE_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(xs + (size_t)rt * C + 4 * q) = v;
+        }
+        __syncthreads();
+        // ---- accumulate ----
+        if (worker) {
+#pragma unroll 2
+            for (int r = 0; r < WG3_ROWS; ++r) {
+                const float4 d = *reinterpret_cast<const float4*>(dzs + r * C + 4 * cog);
+                const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t < ntap) {
+                        const float4 xv = *reinterpret_cast<const float4*>(xs + ((size_t)r * 27 + tg * 4 + t) * C + 4 * cig);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            acc[t][i][0] = fmaf(dd[i], xv.x, acc[t][i][0]);
+                            acc[t][i][1] = fmaf(dd[i], xv.y, acc[t][i][1]);
+                            acc[t][i][2] = fmaf(dd[i], xv.z, acc[t][i][2]);
+                            acc[t][i][3] = fmaf(dd[i], xv.w, acc[t][i][3]);
+                        }
+                    }
+                }
+            }
+        }
+        if (a.dbias && tid < C) {
+#pragma unroll 8
+            for (int r = 0; r < WG3_ROWS; ++r) bsum += dzs[r * C + tid];
+        }
+        __syncthreads();
+    }
+    if (worker) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (t < ntap)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        atomicAdd(a.dw + (size_t)(4 * cog + i) * (C * 27) + (4 * cig + j) * 27 + tg * 4 + t, acc[t][i][j]);
+    }
+    if (a.dbias && tid < C) atomicAdd(a.dbias + tid, bsum);
+}
+
+// -1: not this kernel's problem (the caller falls through to the generic gathered weight gradient)
+int cf_dense_s2_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("CFNET_DENSE_WGRAD_OFF"); off = (e && e[0] == '1') ? 1 : 0; }
+    if (off) return -1;
+    const cf_geom& g = a->g;
+    if (!a->gather_in) return -1;
+    if (!(g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 2 && g.sh == 2 && g.sw == 2 && g.pt == 1 && g.ph == 1 && g.pw == 1)) return -1;
+    if (a->N != 24 || a->K != 24 * 27 || g.ch_stride != 1 || g.pos_stride != 24) return -1;
+    if (a->dy_mode != CF_PRO_NONE && a->dy_mode != CF_PRO_AFFINE2) return -1;
+    if (a->dy_mode == CF_PRO_AFFINE2 && !(a->dy2 && a->dy_a && a->dy_b)) return -1;
+    if (a->x_mode != CF_PRO_NONE && a->x_mode != CF_PRO_AFFINE && a->x_mode != CF_PRO_AFFINE_RELU) return -1;
+    if (a->x_mode != CF_PRO_NONE && !(a->x_a && a->x_b)) return -1;
+    if ((g.sample_stride & 3) || ((uintptr_t)a->x & 15) || ((uintptr_t)a->dy & 15) || (a->dy2 && ((uintptr_t)a->dy2 & 15))) return -1;
+    if (a->dy_c && ((uintptr_t)a->dy_c & 15)) return -1;
+    const long long R = (long long)g.T * g.H * g.W;
+    const long long cps = (R + WG3_ROWS - 1) / WG3_ROWS;
+    if (cps * a->B > 0x7fffffffLL) return -1;
+    Wg3Args w;
+    w.dz = a->dy; w.y = a->dy2; w.P = a->dy_a; w.Q = a->dy_b; w.Rc = a->dy_c; w.x = a->x; w.xa = a->x_a; w.xb = a->x_b;
+    w.dw = a->dw; w.dbias = a->dbias; w.B = a->B;
+    w.To = g.T; w.Ho = g.H; w.Wo = g.W; w.Ti = g.Ti; w.Hi = g.Hi; w.Wi = g.Wi;
+    w.sample_stride = g.sample_stride; w.dy_affine2 = a->dy_mode == CF_PRO_AFFINE2; w.x_mode = a->x_mode;
+    w.chunks_per_sample = (int)cps;
+    const size_t smem = (size_t)(WG3_ROWS * 24 + WG3_ROWS * 27 * 24) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(dense3_s2_wgrad_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cf_set_error("cf_dense_s2_wgrad: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
+        attr_done = true;
+    }
+    long long ctas = cps * a->B;
+    if (ctas > 148 * 2) ctas = 148 * 2;
+    dense3_s2_wgrad_kernel<24><<<(unsigned)ctas, WG3_THREADS, smem, stream>>>(w);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}

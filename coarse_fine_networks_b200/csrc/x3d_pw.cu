@@ -330,6 +330,7 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream);      // x3d_pw_tc2.
 int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream);   // x3d_pw_wgrad_tc.cu (-1: not eligible)
 int cf_dense_s2_dgrad_try(const cf_pw_args* a, cudaStream_t stream);  // x3d_dense3s2.cu (-1: not eligible)
 int cf_dense_s2_fwd_try(const cf_pw_args* a, cudaStream_t stream);    // x3d_dense3s2.cu (-1: not eligible)
+int cf_dense_s2_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream);   // x3d_dense3s2.cu (-1: not eligible)
 int cf_stem_fwd_try(const cf_pw_args* a, cudaStream_t stream);         // x3d_stem.cu (-1: not the stem conv)
 int cf_stem_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream);
 
@@ -462,6 +463,8 @@ extern "C" int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream) {
             }
         }
         rc = cf_stem_wgrad_try(a, stream);                  // conv1_s: specialised kernel
+        if (rc >= 0) return rc;
+        rc = cf_dense_s2_wgrad_try(a, stream);              // pool_1.conv1/conv2: staged rows, register-resident result
         if (rc >= 0) return rc;
     }
     int R = a->g.T * a->g.H * a->g.W;

@@ -212,3 +212,35 @@ def test_dense_s2_forward_direct(X, Ti, Hi, Wi, pro):
     assert relerr(y, ref) <= 2e-6
     assert relerr(stats[..., 0], ref.sum(dim=(2, 3, 4))) <= 1e-5
     assert relerr(stats[..., 1], (ref * ref).sum(dim=(2, 3, 4))) <= 1e-5
+
+
+@pytest.mark.parametrize("Ti,Hi,Wi", [(9, 11, 14), (4, 7, 7), (1, 2, 5), (16, 28, 28)])
+@pytest.mark.parametrize("modes", ["plain", "bn"])
+def test_dense_s2_wgrad_direct(X, Ti, Hi, Wi, modes):
+    """Weight + bias gradient of the dense 3x3x3 stride-2 pad-1 24->24 conv (pool_1.conv1/conv2) through cf_pw_wgrad with
+    gather_in: one launch of the staged-row kernel, accumulating (+=) into non-zero buffers; against autograd of F.conv3d
+    in fp64, with the BatchNorm-backward map on the output gradient and the bn+ReLU prologue on the input ("bn")."""
+    B, C = 2, 24
+    o = lambda n: (n - 1) // 2 + 1
+    To, Ho, Wo = o(Ti), o(Hi), o(Wi)
+    x = synth_tensor((B, C, Ti, Hi, Wi), 61)
+    dz, y = synth_tensor((B, C, To, Ho, Wo), 62), synth_tensor((B, C, To, Ho, Wo), 63)
+    P, Q, R = synth_tensor((B, C), 64), synth_tensor((B, C), 65), synth_tensor((B, C), 66)
+    xa, xb = synth_tensor((B, C), 67), synth_tensor((B, C), 68)
+    v = lambda t: t.double().view(B, C, 1, 1, 1)
+    bn = modes == "bn"
+    gout = v(P) * dz.double() + v(Q) * y.double() + v(R) if bn else dz.double()
+    xin = F.relu(v(xa) * x.double() + v(xb)) if bn else x.double()
+    w = torch.zeros(C, C, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+    bias = torch.zeros(C, dtype=torch.float64, requires_grad=True)
+    F.conv3d(xin, w, bias, stride=2, padding=1).backward(gout)
+    g = X.geom(To, Ho, Wo, Ti, Hi, Wi, k=(3, 3, 3), s=(2, 2, 2), p=(1, 1, 1), pos_stride=C, sample_stride=Ti * Hi * Wi * C)
+    dw = torch.ones(C, C * 27, device="cuda")
+    db = torch.ones(C, device="cuda")
+    kw = dict(dy2=rows(y), dy_mode=X.PRO_AFFINE2, dy_tabs=(P.cuda(), Q.cuda(), R.cuda()), x_mode=X.PRO_AFFINE_RELU,
+              x_tabs=(xa.cuda(), xb.cuda())) if bn else {}
+    n0 = X.lib.cf_launch_count()
+    X.pw_wgrad(rows(dz), rows(x), dw, B, C * 27, C, g, dbias=db, gather_in=1, **kw)
+    assert X.lib.cf_launch_count() - n0 == 1
+    assert relerr(dw, 1.0 + w.grad.reshape(C, C * 27)) <= 1e-5
+    assert relerr(db, 1.0 + bias.grad) <= 1e-5
