@@ -113,14 +113,19 @@ __device__ __forceinline__ float lut_at(const float* l, int acc) {
 }
 
 // KS3: ksize == 3 (every up-scale and the identity): horizontal tap weights live in registers.
-template <bool KS3, bool FLIP>
-__global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) {
+// SPLIT: the CTA is two thread groups of blockDim/2 -- group 0 runs the horizontal pass of frame k+1 into one half of a double
+// buffered tile while group 1 runs the vertical pass + stores of frame k from the other half (one barrier per frame), so the
+// global-load latency of one pass hides behind the arithmetic and stores of the other.  !SPLIT: one group does both in turn.
+template <bool KS3, bool FLIP, bool SPLIT>
+__global__ void __launch_bounds__(1024) clip_preprocess_kernel(const ClipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* lut_s = reinterpret_cast<float*>(smem_raw);                 // 768 floats
     int* vb = reinterpret_cast<int*>(smem_raw + 768 * sizeof(float));  // [CLIP_BAND][2]  (first row relative to r0, taps)
     int* vk = vb + 2 * CLIP_BAND;                                      // [CLIP_BAND][ksize_v]
     unsigned char* hs = reinterpret_cast<unsigned char*>(vk + CLIP_BAND * a.ksize_v);   // [rows_max][3][Sp], 16-byte aligned by the host
-    const int tid = threadIdx.x, nthr = blockDim.x, S = a.S, Sp = a.Sp;
+    const int nthr = SPLIT ? blockDim.x >> 1 : blockDim.x;              // threads per role
+    const int role = SPLIT ? (threadIdx.x >= nthr ? 1 : 0) : 0;
+    const int tid = threadIdx.x - role * nthr, S = a.S, Sp = a.Sp;
     const int oy0 = blockIdx.x * CLIP_BAND;
     const int nrow_out = min(CLIP_BAND, S - oy0);
     const int quads = S >> 2;
@@ -143,16 +148,26 @@ __global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) 
     const int q_step = nthr < quads ? nthr : quads;
     const size_t row_bytes = (size_t)a.W * 3;
 
-    for (int t = blockIdx.y; t < a.Tout; t += gridDim.y) {             // uniform over the CTA
-        float* outf = a.out + (size_t)t * S * S;
-        const bool live = t < a.T;
-        if (live) {
+    const int hs_bytes = a.rows_max * 3 * Sp;
+    const int nf = a.Tout > (int)blockIdx.y ? (a.Tout - 1 - (int)blockIdx.y) / (int)gridDim.y + 1 : 0;   // frames of this CTA
+    for (int it = 0; it < nf + (SPLIT ? 1 : 0); ++it) {                // uniform over the CTA
+        // frame of the horizontal pass (th) and of the vertical pass (tv) in this iteration
+        const int th = blockIdx.y + it * gridDim.y;
+        const int tv = SPLIT ? th - (int)gridDim.y : th;
+        unsigned char* hs_h = SPLIT ? hs + (it & 1) * hs_bytes : hs;
+        const unsigned char* hs_v = SPLIT ? hs + ((it + 1) & 1) * hs_bytes : hs;
+        const bool do_h = (!SPLIT || role == 0) && it < nf && th < a.T;
+        const bool do_v = (!SPLIT || role == 1) && (!SPLIT || it > 0);
+        const bool live = tv < a.T;
+        float* outf = a.out + (size_t)(tv > 0 ? tv : 0) * S * S;
+        const int t = th;
+        if (do_h) {
             // ---- horizontal pass: a thread owns output column ox and walks down the crop rows [r0, r0+nrows) -> hs[r][c][ox] ----
             const uint8_t* fr = a.frames + ((size_t)t * a.H + (a.y1 + r0)) * row_bytes + (size_t)a.x1 * 3;
             for (int ox = tid; ox < S; ox += nthr) {
                 const int xmin = __ldg(a.bounds_h + 2 * ox), n = __ldg(a.bounds_h + 2 * ox + 1);
                 const uint8_t* src = fr + xmin * 3;
-                unsigned char* d = hs + ox;
+                unsigned char* d = hs_h + ox;
                 const int half = 1 << (CLIP_PRECISION_BITS - 1);
                 if (KS3 && n == 2) {
                     // support 1: the window holds exactly 2 pixels away from the borders -> 6 adjacent bytes, immediate offsets,
@@ -214,10 +229,10 @@ __global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) 
                 }
             }
         }
-        __syncthreads();                                                // hs (and, first time, the tables) complete
+        if (!SPLIT) __syncthreads();                                    // hs (and, first time, the tables) complete
 
         // ---- vertical pass + normalisation table + store ----
-        for (int q = q_first; q < quads; q += q_step) {
+        for (int q = do_v ? q_first : quads; q < quads; q += q_step) {
             const int qo = FLIP ? quads - 1 - q : q;
             for (int i = rg; i < nrow_out; i += rgs) {
                 float* orow = outf + (size_t)(oy0 + i) * S + 4 * qo;
@@ -233,7 +248,7 @@ __global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) 
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc[c][e] = 1 << (CLIP_PRECISION_BITS - 1);
-                const unsigned char* row = hs + lo * 3 * Sp + 4 * q;
+                const unsigned char* row = hs_v + lo * 3 * Sp + 4 * q;
                 for (int j = 0; j < n; ++j, row += 3 * Sp) {
                     const int kj = k[j];
 #pragma unroll
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(512) clip_preprocess_kernel(const ClipArgs a) 
                 }
             }
         }
-        __syncthreads();                                                // hs is rewritten by the next frame
+        __syncthreads();                                                // SPLIT: hand the tile over; else hs is rewritten by the next frame
     }
 }
 
@@ -266,15 +281,15 @@ extern "C" int cf_normalize_lut(float* lut, float mean0, float mean1, float mean
     return CF_OK;
 }
 
-static size_t clip_smem_bytes(int size, int rows_max, int ksize_v) {
+static size_t clip_smem_bytes(int size, int rows_max, int ksize_v, int buffers) {
     const int Sp = (size + 15) & ~15;
     size_t tables = 768 * sizeof(float) + (size_t)CLIP_BAND * (2 + ksize_v) * sizeof(int);
     tables = (tables + 15) & ~(size_t)15;
-    return tables + (size_t)rows_max * 3 * Sp;
+    return tables + (size_t)buffers * rows_max * 3 * Sp;
 }
 
 extern "C" size_t cf_clip_preprocess_smem_bytes(int size, int rows_max, int ksize) {
-    return clip_smem_bytes(size, rows_max, ksize);
+    return clip_smem_bytes(size, rows_max, ksize, 2);
 }
 
 extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* bounds_h, const int* kk_h,
@@ -295,11 +310,18 @@ extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* 
     a.frames = frames; a.out = out; a.bounds_h = bounds_h; a.kk_h = kk_h; a.bounds_v = bounds_v; a.kk_v = kk_v; a.lut = lut;
     a.T = T; a.Tout = t_out; a.H = H; a.W = W; a.x1 = x1; a.y1 = y1; a.S = size; a.Sp = (size + 15) & ~15;
     a.ksize_h = ksize_h; a.ksize_v = ksize_v; a.flip = flip ? 1 : 0; a.rows_max = rows_max; a.out_stride_c = out_stride_c;
-    const size_t smem = clip_smem_bytes(size, rows_max, ksize_v);
+    static int nosplit = -1;
+    if (nosplit < 0) { const char* e = getenv("CFNET_CLIP_NOSPLIT"); nosplit = (e && e[0] == '1') ? 1 : 0; }
+    size_t smem = clip_smem_bytes(size, rows_max, ksize_v, 2);
+    const bool split = !nosplit && smem <= 200 * 1024;                 // two thread groups + double-buffered tile
+    if (!split) smem = clip_smem_bytes(size, rows_max, ksize_v, 1);
     CF_CHECK_ARG(smem <= 200 * 1024, "band of input rows does not fit in shared memory (down-scale factor too large)");
     const bool ks3 = ksize_h == 3;
-    void (*kern)(const ClipArgs) = ks3 ? (flip ? clip_preprocess_kernel<true, true> : clip_preprocess_kernel<true, false>)
-                                       : (flip ? clip_preprocess_kernel<false, true> : clip_preprocess_kernel<false, false>);
+    void (*kern)(const ClipArgs);
+    if (split) kern = ks3 ? (flip ? clip_preprocess_kernel<true, true, true> : clip_preprocess_kernel<true, false, true>)
+                          : (flip ? clip_preprocess_kernel<false, true, true> : clip_preprocess_kernel<false, false, true>);
+    else       kern = ks3 ? (flip ? clip_preprocess_kernel<true, true, false> : clip_preprocess_kernel<true, false, false>)
+                          : (flip ? clip_preprocess_kernel<false, true, false> : clip_preprocess_kernel<false, false, false>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cf_set_error("cf_clip_preprocess: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
@@ -307,6 +329,7 @@ extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* 
     // one thread per output column in the horizontal pass; (size/4) x row-groups in the vertical pass
     int threads = ((size + 31) / 32) * 32;
     threads = threads < 64 ? 64 : (threads > 512 ? 512 : threads);
+    if (split) threads *= 2;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     int sms = 148;
