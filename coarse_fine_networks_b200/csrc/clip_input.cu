@@ -310,10 +310,12 @@ extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* 
     a.frames = frames; a.out = out; a.bounds_h = bounds_h; a.kk_h = kk_h; a.bounds_v = bounds_v; a.kk_v = kk_v; a.lut = lut;
     a.T = T; a.Tout = t_out; a.H = H; a.W = W; a.x1 = x1; a.y1 = y1; a.S = size; a.Sp = (size + 15) & ~15;
     a.ksize_h = ksize_h; a.ksize_v = ksize_v; a.flip = flip ? 1 : 0; a.rows_max = rows_max; a.out_stride_c = out_stride_c;
-    static int nosplit = -1;
-    if (nosplit < 0) { const char* e = getenv("CFNET_CLIP_NOSPLIT"); nosplit = (e && e[0] == '1') ? 1 : 0; }
+    // CFNET_CLIP_SPLIT=1 selects the two-group variant (A/B only: it lost the same-box comparison, 313 vs 272 us -- the kernel is
+    // bound by the L1/LSU data pipe (byte loads, table look-ups), not by exposed load latency)
+    static int want_split = -1;
+    if (want_split < 0) { const char* e = getenv("CFNET_CLIP_SPLIT"); want_split = (e && e[0] == '1') ? 1 : 0; }
     size_t smem = clip_smem_bytes(size, rows_max, ksize_v, 2);
-    const bool split = !nosplit && smem <= 200 * 1024;                 // two thread groups + double-buffered tile
+    const bool split = want_split && smem <= 200 * 1024;               // two thread groups + double-buffered tile
     if (!split) smem = clip_smem_bytes(size, rows_max, ksize_v, 1);
     CF_CHECK_ARG(smem <= 200 * 1024, "band of input rows does not fit in shared memory (down-scale factor too large)");
     const bool ks3 = ksize_h == 3;
