@@ -1,0 +1,167 @@
+"""Fine-stream Charades loader with the surface of the reference's charades_fine.py, feeding the GPU
+clip kernel instead of per-image PIL transforms.
+
+    make_dataset(split_file, split, root, num_classes=157)        charades_fine.py:83-122
+    Charades(split_file, split, root, spatial_transform, task, frames, gamma_tau, crops, extract_feat)   125-202
+    mt_collate_fn(batch)                                          205-229
+
+Host logic (which videos, which frame indices, the per-frame label matrix, the multi-view slicing, the zero padding) follows
+the reference statement by statement, including the order of the draws from Python's `random` (start frame first, then the
+transform's parameters), so one seed selects the same clips on both sides.  What changes is where the pixels are processed:
+the decoded frames of a video go to the GPU as ONE uint8 tensor [T,H,W,3] and `spatial_transform.clip()` (one launch of
+cf_clip_preprocess) produces the normalised [3,T,S,S] clip -- bit-identical to `[transform(img) for img in imgs]` + stack +
+permute (charades_fine.py:170-172).  JPEG decoding stays on the host (PIL, as in the reference's pil_loader, 22-26).
+
+Differences, on purpose: the label cache `<split>_<split>labeldata_160.npy` is written as an object array (the reference's
+`np.save(list_of_tuples)` raises on numpy >= 1.24) and read back the way the reference reads it; the accimage backend is not
+used.  `Charades.sample()` is the host half of `__getitem__` (no GPU needed).
+"""
+import json
+import os
+import random
+
+import numpy as np
+import torch
+from PIL import Image
+
+
+def pil_loader(path):
+    """charades_fine.py:22-26 -> uint8 [H,W,3]."""
+    with open(path, "rb") as f:
+        with Image.open(f) as img:
+            return np.asarray(img.convert("RGB"))
+
+
+def video_loader(video_dir_path, vid, frame_indices, image_loader=pil_loader):
+    """charades_fine.py:46-56: frames <root>/<vid>/<vid>-<000001>.jpg, stopping at the first missing index."""
+    video = []
+    for i in frame_indices:
+        image_path = os.path.join(video_dir_path, vid, vid + "-" + str(i).zfill(6) + ".jpg")
+        if not os.path.exists(image_path):
+            return video
+        video.append(image_loader(image_path))
+    return video
+
+
+def load_rgb_frames(image_dir, vid, start, num, stride, loader=video_loader):
+    """charades_fine.py:73-80."""
+    return loader(image_dir, vid, list(range(start, start + num, stride)))
+
+
+def make_dataset(split_file, split, root, num_classes=157, cache=True):
+    """charades_fine.py:83-122 -> list of (vid, label float32 [num_classes, num_frames], duration, num_frames).
+    label[c, fr] = 1 iff ann.start < fr / fps < ann.end, fps = num_frames / duration (same float64 operations)."""
+    pre_data_file = split_file[:-5] + "_" + split + "labeldata_160.npy"
+    if cache and os.path.exists(pre_data_file) and os.path.getsize(pre_data_file) > 0:
+        return [tuple(d) for d in np.load(pre_data_file, allow_pickle=True)]
+    with open(split_file, "r") as f:
+        data = json.load(f)
+    dataset = []
+    for vid in data.keys():
+        if data[vid]["subset"] != split:
+            continue
+        if not os.path.exists(os.path.join(root, vid)):
+            continue
+        num_frames = len(os.listdir(os.path.join(root, vid)))
+        if num_frames < (2 * 80 + 2):
+            continue
+        label = np.zeros((num_classes, num_frames), np.float32)
+        fps = num_frames / data[vid]["duration"]
+        t = np.arange(num_frames) / fps
+        for ann in data[vid]["actions"]:
+            label[ann[0], (t > ann[1]) & (t < ann[2])] = 1
+        dataset.append((vid, label, data[vid]["duration"], num_frames))
+    if cache:
+        arr = np.empty(len(dataset), dtype=object)
+        for i, d in enumerate(dataset):
+            arr[i] = d
+        np.save(pre_data_file, arr, allow_pickle=True)
+    return dataset
+
+
+class Charades(torch.utils.data.Dataset):
+    """charades_fine.py:125-202.  `spatial_transform` is a coarse_fine_networks_b200.spatial_transforms.Compose (or any
+    object with randomize_parameters(c_size) and clip(frames_u8)); `device` is where the frames are processed."""
+
+    def __init__(self, split_file, split, root, spatial_transform=None, task="class", frames=80, gamma_tau=5, crops=1,
+                 extract_feat=False, device="cuda", cache=True):
+        self.data = make_dataset(split_file, split, root, cache=cache)
+        self.split_file = split_file
+        self.root = root
+        self.frames = frames * 2
+        self.gamma_tau = gamma_tau * 2
+        self.spatial_transform = spatial_transform
+        self.crops = crops
+        self.split = "testing" if extract_feat else split
+        self.task = task
+        self.device = device
+
+    def __len__(self):
+        return len(self.data)
+
+    def sample(self, index):
+        """Host half of __getitem__ (charades_fine.py:147-168, 193-194): draws the start frame, decodes the frames, slices the
+        labels.  -> dict(frames uint8 [T,H,W,3], label, vid, frame_count, start_f, stride_f, meta int64 [4])."""
+        vid, label, dur, nf = self.data[index]
+        if self.split == "testing":
+            frames = nf
+            start_f = 1
+        else:
+            frames = min(self.frames, nf)
+            start_f = random.randint(1, max(self.gamma_tau, nf - frames))
+        stride_f = self.gamma_tau
+        if self.split == "testing" and self.task == "loc":
+            stride_f = stride_f // self.crops
+        imgs = load_rgb_frames(self.root, vid, start_f, frames, stride_f)
+        label = torch.from_numpy(np.ascontiguousarray(label[:, start_f - 1:start_f - 1 + frames:1]))
+        if self.task == "class":
+            label = torch.max(label, dim=1)[0]
+        meta = torch.from_numpy(np.array([start_f // self.gamma_tau, frames // self.gamma_tau, nf // self.gamma_tau,
+                                          stride_f // self.gamma_tau]))
+        return dict(frames=np.stack(imgs, 0), label=label, vid=vid, frame_count=frames, start_f=start_f, stride_f=stride_f,
+                    meta=meta)
+
+    def views(self, imgs_l, label, frames):
+        """charades_fine.py:174-191: [3,T,S,S] -> [N,3,T',S,S] (N = crops in testing mode, else 1) and the label window."""
+        if self.split == "testing":
+            per_view = self.frames // self.gamma_tau
+            if self.task == "class":
+                step = int((imgs_l.shape[1] - 1 - per_view) // (self.crops - 1))
+                if step == 0:
+                    clips = torch.stack([imgs_l[:, :per_view, ...] for _ in range(self.crops)], 0)
+                else:
+                    clips = torch.stack([imgs_l[:, i:i + per_view, ...] for i in range(0, step * self.crops, step)], 0)
+            elif self.task == "loc":
+                clips = torch.stack([imgs_l[:, i::self.crops, ...][:, :frames // self.gamma_tau, ...] for i in range(0, self.crops)], 0)
+                label = label[:, :(frames // self.gamma_tau) * self.gamma_tau]
+            else:
+                clips = imgs_l.unsqueeze(0)
+        else:
+            clips = imgs_l.unsqueeze(0)
+        return clips, label
+
+    def __getitem__(self, index):
+        """-> (clips [N,3,T,S,S] fp32 on `device`, label, vid), as the reference's (charades_fine.py:196)."""
+        s = self.sample(index)
+        frames_u8 = torch.from_numpy(s["frames"]).to(self.device, non_blocking=True)
+        self.spatial_transform.randomize_parameters(224)                  # charades_fine.py:170 (224 is hard-coded there)
+        imgs_l = self.spatial_transform.clip(frames_u8)                   # [3,T,S,S]: 171-172 in one kernel
+        clips, label = self.views(imgs_l, s["label"], s["frame_count"])
+        return clips, label, s["vid"]
+
+
+def mt_collate_fn(batch):
+    """charades_fine.py:205-229: zero-pad clips [N,3,T,S,S] along T and labels [C,TL] along TL to the longest of the batch,
+    mask = 1 over the valid label frames.  -> [clips [B,N,3,Tmax,S,S], labels [B,C,TLmax], masks [B,TLmax], vids]."""
+    max_len_clips = max(b[0].shape[2] for b in batch)
+    max_len_labels = max(b[1].shape[1] for b in batch)
+    dev = batch[0][0].device
+    clips = torch.zeros((len(batch),) + tuple(batch[0][0].shape[:2]) + (max_len_clips,) + tuple(batch[0][0].shape[3:]),
+                        dtype=torch.float32, device=dev)
+    labels = torch.zeros(len(batch), batch[0][1].shape[0], max_len_labels, dtype=torch.float32)
+    masks = torch.zeros(len(batch), max_len_labels, dtype=torch.float32)
+    for i, b in enumerate(batch):
+        clips[i, :, :, :b[0].shape[2]] = b[0]
+        labels[i, :, :b[1].shape[1]] = b[1]
+        masks[i, :b[1].shape[1]] = 1
+    return [clips, labels, masks, tuple(b[2] for b in batch)]

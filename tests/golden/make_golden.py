@@ -357,8 +357,96 @@ def gen_clip_pipeline():
     save("clip_pipeline", names=np.array(names), **out)
 
 
+def gen_charades_loader():
+    """The reference's own fine-stream loader (charades_fine.py: make_dataset, Charades.__getitem__, mt_collate_fn) on two
+    synthetic videos stored as JPEG frames.  Harness-only patches (nothing of the reference is modified): stub modules for the
+    imports that are absent here (h5py, cv2 -- unused by the loader; accimage -- its Image raises IOError so that the
+    reference's accimage_loader falls back to its pil_loader), and np.save -> no-op (np.save(list of ragged tuples) raises
+    on numpy >= 1.24, charades_fine.py:120).  The fp32 clips (9.6 MB each) are stored as SHA-256 digests plus a strided
+    sample: the comparison is bit-exact, so a digest loses nothing."""
+    import hashlib
+    import io
+    import json
+    import random
+    import tempfile
+    import types
+    from PIL import Image
+    for m in ("h5py", "cv2"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    acc = types.ModuleType("accimage")
+
+    class _AccImage:
+        def __init__(self, path):
+            raise IOError("accimage stub: fall back to PIL")
+    acc.Image = _AccImage
+    sys.modules["accimage"] = acc
+    import charades_fine as ref_cf
+    from transforms import spatial_transforms as ST
+    real_save = np.save
+    np.save = lambda *a, **k: None
+    try:
+        tmp = tempfile.mkdtemp()
+        root = os.path.join(tmp, "frames")
+        rng = np.random.default_rng(0)
+        vids = {"VIDA": 170, "VIDB": 185, "SHORT": 100}                 # SHORT is below the 162-frame threshold
+        blobs, names = [], []
+        for vid, nf in vids.items():
+            os.makedirs(os.path.join(root, vid))
+            base = rng.integers(0, 256, (6, 8, 3), dtype=np.uint8)
+            for i in range(1, nf + 1):
+                a = np.asarray(Image.fromarray(np.roll(base, i, axis=1)).resize((64, 48), Image.BICUBIC))
+                buf = io.BytesIO()
+                Image.fromarray(a).save(buf, format="JPEG", quality=90)
+                name = f"{vid}/{vid}-{i:06d}.jpg"
+                with open(os.path.join(root, name), "wb") as f:
+                    f.write(buf.getvalue())
+                blobs.append(np.frombuffer(buf.getvalue(), np.uint8))
+                names.append(name)
+        split = {"VIDA": {"subset": "training", "duration": 17.0, "actions": [[3, 1.0, 5.5], [100, 4.0, 16.0]]},
+                 "VIDB": {"subset": "training", "duration": 18.5, "actions": [[7, 0.5, 2.0], [7, 9.0, 9.3]]},
+                 "SHORT": {"subset": "training", "duration": 10.0, "actions": []},
+                 "OTHER": {"subset": "testing", "duration": 10.0, "actions": []}}
+        split_file = os.path.join(tmp, "split.json")
+        json.dump(split, open(split_file, "w"))
+        MEAN, STD = [0.413, 0.368, 0.338], [0.131, 0.125, 0.132]
+        train_tr = ST.Compose([ST.MultiScaleRandomCropMultigrid([224 / 256., 224 / 320.], 224), ST.RandomHorizontalFlip(),
+                               ST.ToTensor(255), ST.Normalize(MEAN, STD)])
+        val_tr = ST.Compose([ST.CenterCropScaled(224), ST.ToTensor(255), ST.Normalize(MEAN, STD)])
+        out = {"jpeg_bytes": np.concatenate(blobs), "jpeg_sizes": np.array([len(b) for b in blobs]), "jpeg_names": np.array(names),
+               "split_json": np.array(json.dumps(split)), "mean": np.array(MEAN), "std": np.array(STD)}
+
+        def digest(t):
+            return np.array(hashlib.sha256(np.ascontiguousarray(t.numpy()).tobytes()).hexdigest())
+
+        def put(name, clips, label, vid):
+            out[name + "/shape"] = np.array(clips.shape)
+            out[name + "/sha256"] = digest(clips)
+            out[name + "/sample"] = clips[..., ::37, ::41].contiguous()
+            out[name + "/label"] = label
+            out[name + "/vid"] = np.array(vid)
+
+        ds = ref_cf.Charades(split_file, "training", root, train_tr, task="class", frames=80, gamma_tau=5, crops=1)
+        out["dataset_vids"] = np.array([d[0] for d in ds.data])
+        out["dataset_label_VIDB"] = ds.data[1][1]
+        for seed in (3, 12):
+            random.seed(seed)
+            put(f"train_class_seed{seed}", *ds[seed % 2])
+        cases = [("test_loc_c1", "loc", 1, 1), ("test_loc_c2", "loc", 2, 1), ("test_class_c2", "class", 2, 1), ("test_loc_c1_a", "loc", 1, 0)]
+        for name, task, crops, idx in cases:
+            dv = ref_cf.Charades(split_file, "training", root, val_tr, task=task, frames=80, gamma_tau=5, crops=crops, extract_feat=True)
+            random.seed(0)
+            put(name, *dv[idx])
+        dv = ref_cf.Charades(split_file, "training", root, val_tr, task="loc", frames=80, gamma_tau=5, crops=1, extract_feat=True)
+        b = ref_cf.mt_collate_fn([dv[0], dv[1]])
+        out.update({"collate/shape": np.array(b[0].shape), "collate/sha256": digest(b[0]), "collate/labels": b[1], "collate/masks": b[2],
+                    "collate/vids": np.array(list(b[3]))})
+    finally:
+        np.save = real_save
+    save("charades_loader", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["interp1d", "gridpool", "gridpool_cfgshape", "gridunpool", "gaussian", "rewight",
-                             "mixing", "bottleneck", "fine_net", "coarse_net", "apmeter", "clip_pipeline"]
+                             "mixing", "bottleneck", "fine_net", "coarse_net", "apmeter", "clip_pipeline", "charades_loader"]
     for w in which:
         globals()["gen_" + w]()
