@@ -99,45 +99,53 @@ class Charades(torch.utils.data.Dataset):
     def __len__(self):
         return len(self.data)
 
+    def plan(self, nf):
+        """Which frames of an nf-frame video one item reads (charades_fine.py:147-166): -> (start_f, frame_count, stride_f).
+        Testing mode reads the whole video from frame 1 (at 1/crops of the stride for localisation); training mode draws the
+        start of a self.frames-long window with random.randint -- the first draw of the item, before the transform's."""
+        testing = self.split == "testing"
+        count = nf if testing else min(self.frames, nf)
+        start = 1 if testing else random.randint(1, max(self.gamma_tau, nf - count))
+        stride = self.gamma_tau // self.crops if (testing and self.task == "loc") else self.gamma_tau
+        return start, count, stride
+
     def sample(self, index):
-        """Host half of __getitem__ (charades_fine.py:147-168, 193-194): draws the start frame, decodes the frames, slices the
-        labels.  -> dict(frames uint8 [T,H,W,3], label, vid, frame_count, start_f, stride_f, meta int64 [4])."""
-        vid, label, dur, nf = self.data[index]
-        if self.split == "testing":
-            frames = nf
-            start_f = 1
-        else:
-            frames = min(self.frames, nf)
-            start_f = random.randint(1, max(self.gamma_tau, nf - frames))
-        stride_f = self.gamma_tau
-        if self.split == "testing" and self.task == "loc":
-            stride_f = stride_f // self.crops
-        imgs = load_rgb_frames(self.root, vid, start_f, frames, stride_f)
-        label = torch.from_numpy(np.ascontiguousarray(label[:, start_f - 1:start_f - 1 + frames:1]))
+        """Host half of __getitem__ (no GPU): draws the window, decodes its frames, cuts the labels to it.
+        -> dict(frames uint8 [T,H,W,3], label, vid, frame_count, start_f, stride_f, meta int64 [4])."""
+        vid, full_label, _, nf = self.data[index]
+        start, count, stride = self.plan(nf)
+        decoded = load_rgb_frames(self.root, vid, start, count, stride)
+        window = torch.from_numpy(np.ascontiguousarray(full_label[:, start - 1:start - 1 + count]))
         if self.task == "class":
-            label = torch.max(label, dim=1)[0]
-        meta = torch.from_numpy(np.array([start_f // self.gamma_tau, frames // self.gamma_tau, nf // self.gamma_tau,
-                                          stride_f // self.gamma_tau]))
-        return dict(frames=np.stack(imgs, 0), label=label, vid=vid, frame_count=frames, start_f=start_f, stride_f=stride_f,
+            window = window.max(dim=1).values                             # clip-level label: any frame positive
+        g = self.gamma_tau
+        meta = torch.tensor([start // g, count // g, nf // g, stride // g], dtype=torch.int64)      # charades_fine.py:193-194
+        return dict(frames=np.stack(decoded, 0), label=window, vid=vid, frame_count=count, start_f=start, stride_f=stride,
                     meta=meta)
 
-    def views(self, imgs_l, label, frames):
-        """charades_fine.py:174-191: [3,T,S,S] -> [N,3,T',S,S] (N = crops in testing mode, else 1) and the label window."""
-        if self.split == "testing":
+    def view_indices(self, n_decoded, frame_count):
+        """Frame positions (into the decoded clip) of every view of the item (charades_fine.py:174-191): one view holding all
+        frames in training; in testing `crops` views -- evenly spaced windows of self.frames // gamma_tau frames for
+        classification, interleaved sub-samplings (i, i + crops, ...) cut to frame_count // gamma_tau for localisation."""
+        everything = [list(range(n_decoded))]
+        if self.split != "testing":
+            return everything
+        if self.task == "class":
             per_view = self.frames // self.gamma_tau
-            if self.task == "class":
-                step = int((imgs_l.shape[1] - 1 - per_view) // (self.crops - 1))
-                if step == 0:
-                    clips = torch.stack([imgs_l[:, :per_view, ...] for _ in range(self.crops)], 0)
-                else:
-                    clips = torch.stack([imgs_l[:, i:i + per_view, ...] for i in range(0, step * self.crops, step)], 0)
-            elif self.task == "loc":
-                clips = torch.stack([imgs_l[:, i::self.crops, ...][:, :frames // self.gamma_tau, ...] for i in range(0, self.crops)], 0)
-                label = label[:, :(frames // self.gamma_tau) * self.gamma_tau]
-            else:
-                clips = imgs_l.unsqueeze(0)
-        else:
-            clips = imgs_l.unsqueeze(0)
+            step = int((n_decoded - 1 - per_view) // (self.crops - 1))
+            starts = [0] * self.crops if step == 0 else list(range(0, step * self.crops, step))
+            return [list(range(s0, min(s0 + per_view, n_decoded))) for s0 in starts]
+        if self.task == "loc":
+            keep = frame_count // self.gamma_tau
+            return [list(range(i, n_decoded, self.crops))[:keep] for i in range(self.crops)]
+        return everything
+
+    def views(self, imgs_l, label, frame_count):
+        """[3,T,S,S] -> clips [N,3,T',S,S]; localisation labels are cut to whole strides (charades_fine.py:189)."""
+        picks = self.view_indices(imgs_l.shape[1], frame_count)
+        clips = torch.stack([imgs_l[:, torch.as_tensor(p, device=imgs_l.device)] for p in picks], 0)
+        if self.split == "testing" and self.task == "loc":
+            label = label[:, :(frame_count // self.gamma_tau) * self.gamma_tau]
         return clips, label
 
     def __getitem__(self, index):

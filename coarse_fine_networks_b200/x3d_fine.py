@@ -161,77 +161,76 @@ class ResNet(nn.Module):
                  shortcut_type='B', widen_factor=1.0, dropout=0.5, n_classes=400, base_bn_splits=8, task='class',
                  extract_feat=False, global_tower=False, t_downsample=False, aux_losses=None):
         super().__init__()
-        block_inplanes = [(int(a * widen_factor), int(b * widen_factor)) for a, b in block_inplanes]
-        self.index = 0
-        self.base_bn_splits = base_bn_splits
-        self.task = task
-        self.extract_feat = extract_feat
-        self.global_tower = global_tower
-        self.t_downsample = t_downsample
-        self.in_planes = block_inplanes[0][1]
+        widths = [tuple(int(c * widen_factor) for c in pair) for pair in block_inplanes]     # (expanded, out) per stage
+        stem_c, head_in, head_c = widths[0][1], widths[-1][1], widths[-1][0]
+        self.base_bn_splits, self.task, self.t_downsample = base_bn_splits, task, t_downsample
+        self.extract_feat, self.global_tower = extract_feat, global_tower
+        self.index, self.in_planes = 0, stem_c
+        bn = lambda c: SubBatchNorm3d(num_splits=base_bn_splits, num_features=c, affine=True)
+        holder = lambda cin, cout, k, s, p, g=1: nn.Conv3d(cin, cout, kernel_size=k, stride=s, padding=p, groups=g, bias=False)
 
-        self.conv1_s = nn.Conv3d(n_input_channels, self.in_planes, kernel_size=(1, 3, 3), stride=(1, 2, 2),
-                                 padding=(0, 1, 1), bias=False)
-        self.conv1_t = nn.Conv3d(self.in_planes, self.in_planes, kernel_size=(5, 1, 1), stride=(1, 1, 1),
-                                 padding=(2, 0, 0), bias=False, groups=self.in_planes)
-        self.bn1 = SubBatchNorm3d(num_splits=base_bn_splits, num_features=self.in_planes, affine=True)
+        # parameter holders, registered under the reference's names (state-dict compatibility, x3d_fine.py:210-258)
+        self.conv1_s = holder(n_input_channels, stem_c, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        self.conv1_t = holder(stem_c, stem_c, (5, 1, 1), 1, (2, 0, 0), stem_c)
+        self.bn1 = bn(stem_c)
         self.relu = nn.ReLU(inplace=True)
-        for i in range(4):
-            setattr(self, f"layer{i + 1}", self._make_layer(block, block_inplanes[i], layers[i], shortcut_type, stride=2))
-        self.conv5 = nn.Conv3d(block_inplanes[3][1], block_inplanes[3][0], kernel_size=1, stride=1, padding=0, bias=False)
-        self.bn5 = SubBatchNorm3d(num_splits=base_bn_splits, num_features=block_inplanes[3][0], affine=True)
-        if task == 'class':
-            self.avgpool = nn.AdaptiveAvgPool3d((1, 1, 1))
-        elif task == 'loc':
-            self.avgpool = nn.AdaptiveAvgPool3d((None, 1, 1))
-        self.fc1 = nn.Conv3d(block_inplanes[3][0], 2048, bias=False, kernel_size=1, stride=1)
+        c_in = stem_c
+        for stage, (pair, depth) in enumerate(zip(widths, layers), start=1):
+            self.add_module(f"layer{stage}", self._make_layer(block, pair, depth, shortcut_type, stride=2, c_in=c_in))
+            c_in = pair[1]
+        self.in_planes = c_in
+        self.conv5 = holder(head_in, head_c, 1, 1, 0)
+        self.bn5 = bn(head_c)
+        pooled_t = {"class": 1, "loc": None}
+        if task in pooled_t:
+            self.avgpool = nn.AdaptiveAvgPool3d((pooled_t[task], 1, 1))
+        self.fc1 = holder(head_c, 2048, 1, 1, 0)
         self.fc2 = nn.Linear(2048, n_classes)
         self.dropout = nn.Dropout(dropout)
-        for m in self.modules():
-            if isinstance(m, nn.Conv3d):
-                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+        for conv in (m for m in self.modules() if isinstance(m, nn.Conv3d)):
+            nn.init.kaiming_normal_(conv.weight, mode="fan_out", nonlinearity="relu")
 
-    def _make_layer(self, block, planes, blocks, shortcut_type, stride=1):
-        downsample = None
-        if stride != 1 or self.in_planes != planes[1]:
-            if shortcut_type == 'A':
-                downsample = partial(self._downsample_basic_block, planes=planes[1], stride=stride)
+    def _make_layer(self, block, planes, blocks, shortcut_type, stride=1, c_in=None):
+        """One stage (x3d_fine.py:268-300): block 0 carries the stride and the projection shortcut, SE in every even block."""
+        c_in = self.in_planes if c_in is None else c_in
+        common = dict(base_bn_splits=self.base_bn_splits, t_downsample=self.t_downsample)
+        shortcut = None
+        if stride != 1 or c_in != planes[1]:
+            if shortcut_type == "A":
+                shortcut = partial(self._downsample_basic_block, planes=planes[1], stride=stride)
             else:
-                downsample = nn.Sequential(
-                    conv1x1x1(self.in_planes, planes[1], stride, t_downsample=self.t_downsample),
-                    SubBatchNorm3d(num_splits=self.base_bn_splits, num_features=planes[1], affine=True))
-        seq = [block(in_planes=self.in_planes, planes=planes, stride=stride, downsample=downsample, index=self.index,
-                     base_bn_splits=self.base_bn_splits, t_downsample=self.t_downsample)]
+                shortcut = nn.Sequential(conv1x1x1(c_in, planes[1], stride, t_downsample=self.t_downsample),
+                                         SubBatchNorm3d(num_splits=self.base_bn_splits, num_features=planes[1], affine=True))
+        stage = [block(c_in if i == 0 else planes[1], planes, stride=stride if i == 0 else 1,
+                       downsample=shortcut if i == 0 else None, index=i, **common) for i in range(blocks)]
         self.in_planes = planes[1]
-        self.index += 1
-        for _ in range(1, blocks):
-            seq.append(block(self.in_planes, planes, index=self.index, base_bn_splits=self.base_bn_splits,
-                             t_downsample=self.t_downsample))
-            self.index += 1
-        self.index = 0
-        return nn.Sequential(*seq)
+        return nn.Sequential(*stage)
 
     def _downsample_basic_block(self, x, planes, stride):
         raise NotImplementedError("shortcut_type 'A' is not built (unused by the reference scripts)")
 
     # -- reference helper surface (x3d_fine.py:309-328)
+    def _sub_bns(self):
+        return [m for m in self.modules() if isinstance(m, SubBatchNorm3d)]
+
     def replace_logits(self, n_classes):
-        self.fc2 = nn.Linear(2048, n_classes).to(self.fc1.weight.device)
+        """New classification layer on the device of the old one (x3d_fine.py:309-310)."""
+        self.fc2 = nn.Linear(self.fc2.in_features, n_classes).to(self.fc1.weight.device)
 
     def update_bn_splits_long_cycle(self, long_cycle_bn_scale):
-        for m in self.modules():
-            if isinstance(m, SubBatchNorm3d):
-                m.num_splits = self.base_bn_splits * long_cycle_bn_scale
-                m.split_bn = nn.BatchNorm3d(num_features=m.num_features * m.num_splits, affine=False).to(m.weight.device)
-        return self.base_bn_splits * long_cycle_bn_scale
+        """Multigrid long cycle: rebuild every split BatchNorm for base_bn_splits * scale splits; returns that count."""
+        splits = self.base_bn_splits * long_cycle_bn_scale
+        for sbn in self._sub_bns():
+            sbn.num_splits = splits
+            sbn.split_bn = nn.BatchNorm3d(sbn.num_features * splits, affine=False).to(sbn.weight.device)
+        return splits
 
     def aggregate_sub_bn_stats(self):
-        count = 0
-        for m in self.modules():
-            if isinstance(m, SubBatchNorm3d):
-                m.aggregate_stats()
-                count += 1
-        return count
+        """Fold the split statistics into the eval-mode BatchNorm of every SubBatchNorm3d; returns how many were folded."""
+        sbns = self._sub_bns()
+        for sbn in sbns:
+            sbn.aggregate_stats()
+        return len(sbns)
 
     # -- pieces shared with the coarse stream
     def _stem(self, x):
@@ -280,14 +279,19 @@ class ResNet(nn.Module):
         return self._head(pooled)
 
 
+# X3D variants: per stage (expanded width, output width) and block counts; 'S' and 'M' are the same network (they differ by
+# input size only, train_fine.py:59).  x3d_fine.py:388-402
+_X3D_M = dict(widths=((54, 24), (108, 48), (216, 96), (432, 192)), depths=(3, 5, 11, 7))
+_X3D_XL = dict(widths=((72, 32), (162, 72), (306, 136), (630, 280)), depths=(5, 10, 25, 15))
+_VARIANTS = {"S": _X3D_M, "M": _X3D_M, "XL": _X3D_XL}
+
+
 def get_inplanes(version):
-    return {'S': [(54, 24), (108, 48), (216, 96), (432, 192)],
-            'M': [(54, 24), (108, 48), (216, 96), (432, 192)],
-            'XL': [(72, 32), (162, 72), (306, 136), (630, 280)]}[version]
+    return [tuple(w) for w in _VARIANTS[version]["widths"]]
 
 
 def get_blocks(version):
-    return {'S': [3, 5, 11, 7], 'M': [3, 5, 11, 7], 'XL': [5, 10, 25, 15]}[version]
+    return list(_VARIANTS[version]["depths"])
 
 
 def generate_model(x3d_version, **kwargs):
