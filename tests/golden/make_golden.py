@@ -440,6 +440,36 @@ def gen_charades_loader():
         b = ref_cf.mt_collate_fn([dv[0], dv[1]])
         out.update({"collate/shape": np.array(b[0].shape), "collate/sha256": digest(b[0]), "collate/labels": b[1], "collate/masks": b[2],
                     "collate/vids": np.array(list(b[3]))})
+
+        # ---- coarse-stream loader (charades_coarse_fineFEAT.py) on the same videos + fine-feature files in the layout
+        # extract_fineFEAT.py:172-173 writes (torch.save of a [1,C,Tf,7,7] tensor under <dir>/<layer>/<video id>)
+        import charades_coarse_fineFEAT as ref_cc
+        feat_dir = os.path.join(tmp, "feat")
+        fkeys = ["layer1", "conv5"]
+        gen = torch.Generator().manual_seed(77)
+        for vid, tf in (("VIDA", 150), ("VIDB", 90)):                      # 150 > the collate cap of 128
+            for k, c in zip(fkeys, (2, 3)):
+                os.makedirs(os.path.join(feat_dir, k), exist_ok=True)
+                f = torch.randn(1, c, tf, 7, 7, generator=gen)
+                torch.save(f.data.cpu(), os.path.join(feat_dir, k, vid))
+                out[f"feat_file/{k}/{vid}"] = f
+        dc = ref_cc.Charades(split_file, "training", root, feat_dir, fkeys, train_tr, task="loc", frames=80, gamma_tau=5, crops=1)
+        random.seed(21)
+        items = [dc[0], dc[1]]
+        for i, (clips, label, feat, meta, vid, dur) in enumerate(items):
+            put(f"coarse_item{i}", clips, label, vid)
+            out[f"coarse_item{i}/meta"] = meta
+            out[f"coarse_item{i}/dur"] = np.array(dur)
+            for k in fkeys:
+                out[f"coarse_item{i}/feat_sha256/{k}"] = digest(torch.from_numpy(feat[k]))
+                out[f"coarse_item{i}/feat_shape/{k}"] = np.array(feat[k].shape)
+        cb = ref_cc.mt_collate_fn(items)
+        out.update({"ccollate/clips_shape": np.array(cb[0].shape), "ccollate/clips_sha256": digest(cb[0]), "ccollate/labels": cb[1],
+                    "ccollate/masks": cb[2], "ccollate/feat_masks": cb[4], "ccollate/meta": cb[5], "ccollate/vids": np.array(list(cb[6])),
+                    "ccollate/dur": cb[7]})
+        for k in fkeys:
+            out[f"ccollate/feat_sha256/{k}"] = digest(cb[3][k])
+            out[f"ccollate/feat_shape/{k}"] = np.array(cb[3][k].shape)
     finally:
         np.save = real_save
     save("charades_loader", **out)

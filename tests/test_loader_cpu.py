@@ -109,3 +109,57 @@ def test_collate_padding(env):
     assert tuple(b[0].shape) == tuple(g["collate/shape"]) and sha(b[0]) == str(g["collate/sha256"])
     assert np.array_equal(b[1].numpy(), g["collate/labels"]) and np.array_equal(b[2].numpy(), g["collate/masks"])
     assert list(b[3]) == [str(v) for v in g["collate/vids"]]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# coarse-stream loader + the on-disk fine-feature layout (charades_coarse_fineFEAT.py, extract_fineFEAT.py:172-173)
+# ---------------------------------------------------------------------------------------------------------------------------
+FKEYS = ["layer1", "conv5"]
+
+
+@pytest.fixture(scope="module")
+def coarse_items(env, tmp_path_factory):
+    from coarse_fine_networks_b200 import charades_coarse_fineFEAT as LC
+    g = env.g
+    feat_dir = str(tmp_path_factory.mktemp("feat"))
+    for vid in ("VIDA", "VIDB"):                               # written with OUR writer, in the reference's layout
+        LC.save_fine_features({k: torch.from_numpy(g[f"feat_file/{k}/{vid}"]) for k in FKEYS}, feat_dir, vid)
+    dc = LC.Charades(env.split_file, "training", env.root, feat_dir, FKEYS, env.train_tr, task="loc", frames=80, gamma_tau=5,
+                     crops=1, device="cpu", cache=False)
+    random.seed(21)
+    return LC, feat_dir, [dc[0], dc[1]]
+
+
+def test_feature_files_round_trip_in_reference_layout(env, coarse_items):
+    LC, feat_dir, _ = coarse_items
+    for vid in ("VIDA", "VIDB"):
+        assert sorted(os.listdir(feat_dir)) == sorted(FKEYS) and os.path.isfile(os.path.join(feat_dir, "conv5", vid))
+        raw = torch.load(os.path.join(feat_dir, "layer1", vid), weights_only=False)      # what the reference's loader does
+        assert raw.dtype == torch.float32 and raw.dim() == 5 and raw.shape[0] == 1
+        back = LC.load_fine_features(feat_dir, FKEYS, vid)
+        for k in FKEYS:
+            assert np.array_equal(back[k], env.g[f"feat_file/{k}/{vid}"][0])
+
+
+def test_coarse_items_match_reference(env, coarse_items):
+    _, _, items = coarse_items
+    g = env.g
+    for i, (clips, label, feat, meta, vid, dur) in enumerate(items):
+        check(env, f"coarse_item{i}", clips, label, vid)
+        assert meta.tolist() == g[f"coarse_item{i}/meta"].tolist() and float(dur) == float(g[f"coarse_item{i}/dur"])
+        for k in FKEYS:
+            assert tuple(feat[k].shape) == tuple(g[f"coarse_item{i}/feat_shape/{k}"])
+            assert sha(torch.from_numpy(feat[k])) == str(g[f"coarse_item{i}/feat_sha256/{k}"])
+
+
+def test_coarse_collate_caps_features_at_128(env, coarse_items):
+    LC, _, items = coarse_items
+    g = env.g
+    b = LC.mt_collate_fn(items)
+    assert tuple(b[0].shape) == tuple(g["ccollate/clips_shape"]) and sha(b[0]) == str(g["ccollate/clips_sha256"])
+    assert np.array_equal(b[1].numpy(), g["ccollate/labels"]) and np.array_equal(b[2].numpy(), g["ccollate/masks"])
+    assert np.array_equal(b[4].numpy(), g["ccollate/feat_masks"]) and b[4].shape[1] == 128
+    assert np.array_equal(b[5].numpy(), g["ccollate/meta"]) and list(b[6]) == [str(v) for v in g["ccollate/vids"]]
+    assert np.array_equal(b[7].numpy(), g["ccollate/dur"]) and b[7].dtype == torch.float64
+    for k in FKEYS:
+        assert tuple(b[3][k].shape) == tuple(g[f"ccollate/feat_shape/{k}"]) and sha(b[3][k]) == str(g[f"ccollate/feat_sha256/{k}"])
