@@ -88,6 +88,7 @@ class FlatTrainer:
             p._cf_grad = self.flat_g[off:off + n].view(p.shape)
             p.grad = p._cf_grad
         self.lr, self.momentum, self.weight_decay, self.fusion_lr_mult = lr, momentum, weight_decay, fusion_lr_mult
+        self.fusion_lr = None          # explicit learning rate of the fusion group (set by lr_warmup); None = lr * fusion_lr_mult
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.n_params = sum(p.numel() for p in self.params)
@@ -97,10 +98,14 @@ class FlatTrainer:
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
 
+    def lrs(self):
+        """(base-group lr, fusion-group lr) the next update uses."""
+        return float(self.lr), float(self.lr * self.fusion_lr_mult if self.fusion_lr is None else self.fusion_lr)
+
     def sgd(self):
-        call("cf_sgd_flat", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_v), self.n, self.n_split, float(self.lr),
-             float(self.lr * self.fusion_lr_mult), float(self.momentum), float(self.weight_decay), 1.0 / self.world,
-             stream_ptr())
+        lr0, lr1 = self.lrs()
+        call("cf_sgd_flat", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_v), self.n, self.n_split, lr0, lr1,
+             float(self.momentum), float(self.weight_decay), 1.0 / self.world, stream_ptr())
 
     def step(self):
         self.allreduce()
@@ -108,6 +113,47 @@ class FlatTrainer:
 
     def zero_grad(self):
         self.flat_g.zero_()
+
+
+class MultiStepSchedule:
+    """optim.lr_scheduler.MultiStepLR(optimizer, milestones, gamma) as the scripts use it (train_fine.py:72,131,256;
+    train_coarse_fineFEAT.py: lr_schedule [15,20,25], one step() per epoch) for a FlatTrainer: at every milestone epoch both
+    groups' CURRENT learning rates are multiplied by gamma (PyTorch's chainable form), so the fusion group keeps its ratio."""
+
+    def __init__(self, trainer, milestones, gamma=0.1, last_epoch=0):
+        self.trainer, self.milestones, self.gamma, self.last_epoch = trainer, sorted(milestones), gamma, last_epoch
+
+    def step(self):
+        self.last_epoch += 1
+        hits = self.milestones.count(self.last_epoch)
+        if hits:
+            self.trainer.lr *= self.gamma ** hits
+            if self.trainer.fusion_lr is not None:
+                self.trainer.fusion_lr *= self.gamma ** hits
+
+    def get_last_lr(self):
+        return list(self.trainer.lrs())
+
+    def state_dict(self):
+        return {"milestones": list(self.milestones), "gamma": self.gamma, "last_epoch": self.last_epoch,
+                "_last_lr": self.get_last_lr()}
+
+    def load_state_dict(self, sd):
+        self.milestones, self.gamma, self.last_epoch = sorted(sd["milestones"]), sd["gamma"], sd["last_epoch"]
+        if "_last_lr" in sd:
+            self.trainer.lr = sd["_last_lr"][0]
+            self.trainer.fusion_lr = sd["_last_lr"][1] if len(sd["_last_lr"]) > 1 else None
+
+
+def lr_warmup(init_lr, cur_steps, warmup_steps, trainer):
+    """train_fine.py:258-264 / train_coarse_fineFEAT.py: linear warm-up over the first steps.  As in the reference EVERY
+    parameter group is set to lr_scale * init_lr while it is active (the fusion group loses its 10x until the schedule or
+    the caller sets it again); outside the window nothing is touched."""
+    start_after = 1
+    if cur_steps < warmup_steps and cur_steps > start_after:
+        lr_scale = min(1., float(cur_steps + 1) / warmup_steps)
+        trainer.lr = lr_scale * init_lr
+        trainer.fusion_lr = lr_scale * init_lr
 
 
 def coarse_fine_forward(fine_net, coarse_net, x_fine, start, n_coarse, feat_masks, detach_fine=False, meta=None):

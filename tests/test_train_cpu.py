@@ -66,3 +66,39 @@ def test_gloo_world2_flat_allreduce():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert res[0][2] == res[1][2]                     # identical reduced buffers on both ranks
+
+
+def test_lr_schedule_and_warmup_match_torch_and_the_reference_rule():
+    """MultiStepSchedule against torch's MultiStepLR on an SGD with the scripts' two parameter groups (base lr, fusion 10x:
+    train_coarse_fineFEAT.py:137-141) with the scripts' milestones [15,20,25]; lr_warmup against the reference's rule
+    (train_fine.py:258-264: every group set to lr_scale * init_lr inside the window, untouched outside)."""
+    from coarse_fine_networks_b200 import train
+    m = _model()
+    tr = train.FlatTrainer([m], lr=0.02)
+    ref_params = [torch.nn.Parameter(torch.zeros(1)), torch.nn.Parameter(torch.zeros(1))]
+    opt = torch.optim.SGD([{"params": [ref_params[0]]}, {"params": [ref_params[1]], "lr": 0.02 * 10}], lr=0.02, momentum=0.9)
+    ref_sched = torch.optim.lr_scheduler.MultiStepLR(opt, [15, 20, 25])
+    sched = train.MultiStepSchedule(tr, [15, 20, 25])
+    assert tr.lrs() == (0.02, 0.02 * train.FUSION_LR_MULT) and train.FUSION_LR_MULT == 10
+    for epoch in range(30):
+        opt.step()
+        ref_sched.step()
+        sched.step()
+        want = [g["lr"] for g in opt.param_groups]
+        assert all(abs(a - b) <= 1e-12 * b for a, b in zip(tr.lrs(), want)), (epoch, tr.lrs(), want)
+    sd = sched.state_dict()
+    tr2 = train.FlatTrainer([_model()], lr=0.02)
+    s2 = train.MultiStepSchedule(tr2, [1])
+    s2.load_state_dict(sd)
+    assert s2.last_epoch == 30 and tr2.lrs() == tr.lrs()
+
+    def ref_lr_warmup(init_lr, cur_steps, warmup_steps, o):            # restated from train_fine.py:258-264
+        if cur_steps < warmup_steps and cur_steps > 1:
+            for pg in o.param_groups:
+                pg["lr"] = min(1., float(cur_steps + 1) / warmup_steps) * init_lr
+    tr3 = train.FlatTrainer([_model()], lr=0.02)
+    opt3 = torch.optim.SGD([{"params": [ref_params[0]]}, {"params": [ref_params[1]], "lr": 0.2}], lr=0.02)
+    for step in range(0, 14):
+        ref_lr_warmup(0.02, step, 10, opt3)
+        train.lr_warmup(0.02, step, 10, tr3)
+        assert list(tr3.lrs()) == [g["lr"] for g in opt3.param_groups], step
