@@ -87,6 +87,7 @@ class FlatTrainer:
             p.data = self.flat_p[off:off + n].view(p.shape)
             p._cf_grad = self.flat_g[off:off + n].view(p.shape)
             p.grad = p._cf_grad
+        self._offs, self._n_base = offs, len(base)
         self.lr, self.momentum, self.weight_decay, self.fusion_lr_mult = lr, momentum, weight_decay, fusion_lr_mult
         self.fusion_lr = None          # explicit learning rate of the fusion group (set by lr_warmup); None = lr * fusion_lr_mult
         self.group = process_group
@@ -113,6 +114,40 @@ class FlatTrainer:
 
     def zero_grad(self):
         self.flat_g.zero_()
+
+    # -- checkpoints in torch.optim.SGD's layout: what the scripts save as 'optimizer_state_dict' and load back on resume
+    #    (train_fine.py:132-134,245-249; train_coarse_fineFEAT.py:143-145,289-293).  Parameter indices follow the scripts'
+    #    group order: base parameters in named_parameters() order, then the 'rw'/'mix' group.
+    def _momentum_view(self, i):
+        p, off = self.params[i], self._offs[i]
+        return self.flat_v[off:off + p.numel()].view(p.shape)
+
+    def state_dict(self):
+        lr0, lr1 = self.lrs()
+        common = dict(momentum=self.momentum, dampening=0, weight_decay=self.weight_decay, nesterov=False)
+        groups = [dict(common, lr=lr0, params=list(range(self._n_base)))]
+        if len(self.params) > self._n_base:
+            groups.append(dict(common, lr=lr1, params=list(range(self._n_base, len(self.params)))))
+        return {"state": {i: {"momentum_buffer": self._momentum_view(i).detach().clone()} for i in range(len(self.params))},
+                "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        n = sum(len(g["params"]) for g in groups)
+        if n != len(self.params):
+            raise ValueError(f"optimizer state holds {n} parameters, this trainer {len(self.params)}")
+        order = [i for g in groups for i in g["params"]]               # saved index of our i-th parameter
+        for i, saved in enumerate(order):
+            buf = sd["state"].get(saved, {}).get("momentum_buffer")
+            if buf is None:
+                self._momentum_view(i).zero_()                          # no step taken yet: torch starts from v = g
+            else:
+                if tuple(buf.shape) != tuple(self.params[i].shape):
+                    raise ValueError(f"momentum buffer {saved}: shape {tuple(buf.shape)} != {tuple(self.params[i].shape)} ({self.names[i]})")
+                self._momentum_view(i).copy_(buf)
+        self.lr = groups[0]["lr"]
+        self.momentum, self.weight_decay = groups[0].get("momentum", self.momentum), groups[0].get("weight_decay", self.weight_decay)
+        self.fusion_lr = groups[1]["lr"] if len(groups) > 1 else None
 
 
 class MultiStepSchedule:

@@ -102,3 +102,41 @@ def test_lr_schedule_and_warmup_match_torch_and_the_reference_rule():
         ref_lr_warmup(0.02, step, 10, opt3)
         train.lr_warmup(0.02, step, 10, tr3)
         assert list(tr3.lrs()) == [g["lr"] for g in opt3.param_groups], step
+
+
+def test_optimizer_checkpoint_round_trip_with_torch_sgd():
+    """FlatTrainer.state_dict() / load_state_dict() speak torch.optim.SGD's layout, so a run resumes from the scripts'
+    'optimizer_state_dict' (train_coarse_fineFEAT.py:143-145,289-293) and the scripts can resume from ours."""
+    from coarse_fine_networks_b200 import train
+
+    def torch_sgd(model, lr=0.05):
+        rw = [p for n, p in model.named_parameters() if "rw" in n or "mix" in n]
+        base = [p for n, p in model.named_parameters() if not ("rw" in n or "mix" in n)]
+        return torch.optim.SGD([{"params": base}, {"params": rw, "lr": lr * 10}], lr=lr, momentum=0.9, weight_decay=1e-5)
+
+    ref_model = _model()
+    opt = torch_sgd(ref_model)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        for p in ref_model.parameters():
+            p.grad = torch.randn(p.shape, generator=g)
+        opt.step()
+    sd = opt.state_dict()
+
+    tr = train.FlatTrainer([_model()], lr=0.01)
+    tr.load_state_dict(sd)
+    assert tr.lrs() == (0.05, 0.5)
+    torch_order = [p for grp in opt.param_groups for p in grp["params"]]
+    assert [tuple(p.shape) for p in tr.params] == [tuple(p.shape) for p in torch_order]
+    for i, p in enumerate(torch_order):
+        assert torch.equal(tr._momentum_view(i), opt.state[p]["momentum_buffer"])
+    back = tr.state_dict()
+    opt2 = torch_sgd(_model(), lr=0.123)
+    opt2.load_state_dict(back)                                           # torch accepts our layout
+    assert [grp["lr"] for grp in opt2.param_groups] == [0.05, 0.5]
+    for p2, p in zip([q for grp in opt2.param_groups for q in grp["params"]], torch_order):
+        assert torch.equal(opt2.state[p2]["momentum_buffer"], opt.state[p]["momentum_buffer"])
+    fresh = train.FlatTrainer([_model()], lr=0.01)                       # a state saved before the first step has no buffers
+    fresh.flat_v.fill_(7.0)
+    fresh.load_state_dict(torch_sgd(_model()).state_dict())
+    assert all(float(fresh._momentum_view(i).abs().sum()) == 0.0 for i in range(len(fresh.params)))   # (alignment gaps are not parameters)
