@@ -30,6 +30,23 @@ def save_fine_features(feat, save_dir, name):
         torch.save(t.detach().to("cpu", torch.float32), os.path.join(save_dir, layer, name))
 
 
+def extract_fine_features(fine_net, loader, save_dir, log=None):
+    """The loop of extract_fineFEAT.py:152-173: every video of `loader` (batch size 1, items of charades_fine.mt_collate_fn:
+    clips [1,N,3,T,S,S], labels, masks, names) through the fine stream built with global_tower=True, features written in the
+    layout the coarse loader reads.  -> number of videos written."""
+    fine_net.train(False)                                                 # extract_fineFEAT.py:137
+    done = 0
+    with torch.no_grad():
+        for clips, _labels, masks, names in loader:
+            b, n = clips.shape[:2]
+            feat, _ = fine_net([clips.reshape((b * n,) + tuple(clips.shape[2:])), masks])
+            save_fine_features(feat, save_dir, names[0])
+            done += 1
+            if log is not None:
+                log(done, names[0], {k: tuple(v.shape) for k, v in feat.items()})
+    return done
+
+
 def load_fine_features(fine_feat, feature_keys, vid):
     """-> {layer: numpy [C,Tf,h,w]}; the 'gx' entry (a CDF saved as a vector) is viewed as [1,Tf,1,1] like the reference does."""
     out = {}

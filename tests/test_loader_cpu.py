@@ -163,3 +163,28 @@ def test_coarse_collate_caps_features_at_128(env, coarse_items):
     assert np.array_equal(b[7].numpy(), g["ccollate/dur"]) and b[7].dtype == torch.float64
     for k in FKEYS:
         assert tuple(b[3][k].shape) == tuple(g[f"ccollate/feat_shape/{k}"]) and sha(b[3][k]) == str(g[f"ccollate/feat_sha256/{k}"])
+
+
+def test_extract_loop_writes_what_the_coarse_loader_reads(env, tmp_path):
+    """extract_fine_features (extract_fineFEAT.py:152-173) with a stand-in for the fine stream: one file per layer and video,
+    batch and view dimensions merged before the call, read back by load_fine_features."""
+    from coarse_fine_networks_b200 import charades_coarse_fineFEAT as LC
+    seen = []
+
+    class Tower(torch.nn.Module):
+        def forward(self, inp):
+            x, masks = inp
+            seen.append((tuple(x.shape), self.training, torch.is_grad_enabled()))
+            t = x.shape[2]
+            return {"layer1": x.mean(dim=(3, 4), keepdim=True)[:, :2].expand(-1, -1, t, 7, 7) + 0.0,
+                    "conv5": torch.ones(x.shape[0], 3, t, 7, 7)}, masks
+
+    dv = env.L.Charades(env.split_file, "training", env.root, env.val_tr, task="loc", frames=80, gamma_tau=5, crops=1,
+                        extract_feat=True, device="cpu", cache=False)
+    loader = [env.L.mt_collate_fn([dv[i]]) for i in range(2)]
+    net = Tower().train()
+    n = LC.extract_fine_features(net, loader, str(tmp_path))
+    assert n == 2 and [s[0][:3] for s in seen] == [(1, 3, 17), (1, 3, 18)] and all(not s[1] and not s[2] for s in seen)
+    for vid, t in (("VIDA", 17), ("VIDB", 18)):
+        f = LC.load_fine_features(str(tmp_path), ["layer1", "conv5"], vid)
+        assert f["layer1"].shape == (2, t, 7, 7) and f["conv5"].shape == (3, t, 7, 7) and f["conv5"].dtype == np.float32
