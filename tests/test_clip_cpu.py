@@ -98,3 +98,24 @@ def test_compose_rejects_chains_the_scripts_never_build():
     import torch
     with pytest.raises(RuntimeError):                      # no CPU fallback
         tr.clip(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))
+
+
+def test_clip_entry_point_rejects_bad_arguments_before_touching_the_gpu():
+    """Argument validation of cf_clip_preprocess happens on the host, ahead of any CUDA call, so it can be exercised here:
+    non-multiple-of-4 size, crop box outside the frame, coefficient tables built for another crop/size pair, short channel stride."""
+    import ctypes
+    from coarse_fine_networks_b200 import _lib
+    f = _lib.lib.cf_clip_preprocess
+    p = ctypes.c_void_p(0x1000)                                # never dereferenced: every call below fails validation first
+
+    def call(T=2, H=40, W=60, x1=0, y1=0, crop=40, size=32, ks=None, rows_max=30, flip=0, t_out=2, stride=None):
+        ks = _lib.lib.cf_resample_ksize(crop, size) if ks is None else ks
+        stride = t_out * size * size if stride is None else stride
+        rc = f(p, p, p, p, p, p, p, T, H, W, x1, y1, crop, size, ks, ks, rows_max, flip, t_out, stride, None)
+        return rc, _lib.lib.cf_last_error().decode()
+
+    for kw, msg in ((dict(size=30), "multiple of 4"), (dict(x1=30), "crop box outside"), (dict(y1=1), "crop box outside"),
+                    (dict(ks=7), "do not match"), (dict(stride=100), "channel stride"), (dict(t_out=1), "T <= t_out"),
+                    (dict(rows_max=0), "rows_max")):
+        rc, err = call(**kw)
+        assert rc != 0 and msg in err, (kw, rc, err)
