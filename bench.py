@@ -28,6 +28,74 @@ import torch  # noqa: E402
 
 DEPTH = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
 N_CLASSES = 157
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+# compulsory conv traffic (each conv reads its input and writes its output once, fp32) of the X3D-M fine
+# stream = 730.4 MB per clip at T=16 (scales with T); coarse stream (stem + layer1 at T=64, the rest at Tl=17) ~ 1.75 GB
+# per clip; forward + backward ~ 3x the forward.
+FINE_FWD_BYTES_PER_CLIP_T16 = 730.4e6
+COARSE_FWD_BYTES_PER_CLIP = 1.75e9
+
+
+def state_template(which):
+    """Zero tensors with the shapes of the reference's state dict ('fine_M' / 'coarse_M'), from the fixture written by
+    tests/golden/make_golden.py:gen_param_order -- lets the CPU arms build weights without importing the product."""
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "param_order.json")))[which]["shapes"]
+    return {k: torch.zeros(shape, dtype=getattr(torch, dt.split(".")[1])) for k, (shape, dt) in d.items()}
+
+
+def import_reference():
+    """The unmodified reference model files staged in baseline/_ref by __graft_entry__.stage_reference(); None if absent."""
+    if not os.path.exists(os.path.join(REF_DIR, "x3d_coarse.py")):
+        return None
+    import importlib
+    sys.path.insert(0, REF_DIR)
+    try:
+        return importlib.import_module("x3d_fine"), importlib.import_module("x3d_coarse")
+    finally:
+        sys.path.remove(REF_DIR)
+
+
+def reference_models(which, ref):
+    """The reference's nets at the benchmarked configuration with the key-hashed synthetic weights of the parity goldens."""
+    from synth import fill_state_dict
+    rf, rc = ref
+    fine = rf.generate_model("M", n_classes=N_CLASSES, task="loc", base_bn_splits=1, dropout=0.0, global_tower=(which != "fine"))
+    fill_state_dict(fine, seed=1)
+    coarse = None
+    if which != "fine":
+        coarse = rc.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0,
+                                   t_pool="grid", learnedMixing=True, isMixing=True)
+        coarse.replace_logits(N_CLASSES)
+        coarse.rw6.dropout.p = 0.0
+        fill_state_dict(coarse, seed=2)
+    return fine, coarse
+
+
+def script_loss(logits, labels, masks, align_corners):
+    """train_fine.py:199-212,226 (align_corners=True) / train_coarse_fineFEAT.py:226-247 (default grid), torch calls."""
+    import torch.nn.functional as F
+    tl = labels.shape[2]
+    pl = F.interpolate(logits, tl, mode="linear", align_corners=True) if align_corners else F.interpolate(logits, tl, mode="linear")
+    probs = torch.sigmoid(pl) * masks.unsqueeze(1)
+    cls = F.binary_cross_entropy(torch.max(probs, dim=2)[0], torch.max(labels, dim=2)[0], reduction="mean")
+    loc = F.binary_cross_entropy(probs, labels, reduction="sum") / (torch.sum(masks) * labels.shape[1])
+    return (cls + loc) / 2
+
+
+def reference_step(which, fine, coarse, x, labels, masks, fmask, meta, start, n_coarse):
+    """One fwd + script loss + bwd of the reference modules (joint: gradients through both streams, like our step)."""
+    for m in (fine, coarse):
+        if m is not None:
+            m.zero_grad(set_to_none=True)
+    if which == "fine":
+        logits = fine([x, None])
+    else:
+        feat, _ = fine([x, None])
+        logits = coarse([x[:, :, start:start + n_coarse].contiguous(), feat, fmask, 0, meta])
+    loss = script_loss(logits, labels, masks, which == "fine")
+    loss.backward()
+    return loss.detach()
 
 
 # ----------------------------------------------------------------------------------------
@@ -195,7 +263,7 @@ class GridPoolWorkload:
         gout = torch.randn(n, 24, 17, 56, 56, generator=g)
         t0 = time.perf_counter()
         O.temporal_lerp(x, O.gridpool_cdf(conf)).backward(gout)
-        return n, time.perf_counter() - t0, f"{n} of 32 clips of the same workload per step"
+        return n, time.perf_counter() - t0, f"{n} of 32 clips of the same workload per step", "port"
 
 
 # ----------------------------------------------------------------------------------------
@@ -221,18 +289,20 @@ class TrainWorkload:
     """fwd + Charades loss + bwd (+ all-reduce) + fused SGD; the fwd/loss/bwd part replayed from a CUDA graph."""
     dtype = "f32"
 
-    def __init__(self, device, rank=0, which="coarse_fine", batch=None):
-        from coarse_fine_networks_b200 import train
-        self.train = train
-        self.which, self.device = which, device
+    @staticmethod
+    def describe(which, batch=None):
+        """-> (B, Tf, Tc, start, name) of a workload, without touching the product or allocating anything."""
         if which == "fine":
-            self.B, self.Tf, self.Tc, self.start = batch or 8, 16, 16, 0
-            self.name = f"cfg2 X3D-M fine stream train step, synthetic [{self.B},3,16,224,224] fp32, 157 classes"
-        else:
-            self.B, self.Tf, self.Tc, self.start = batch or 4, 256, 64, 96
-            self.name = (f"cfg4 joint Coarse-Fine X3D-M two-stream + Multi-stage Fusion train step: fine [{self.B},3,256,224,224] "
-                         f"(global tower) -> coarse window [{self.B},3,64,224,224] -> Grid Pool Tl=17 -> logits [{self.B},157,64], "
-                         "gradients through BOTH streams, fp32")
+            B = batch or 8
+            return B, 16, 16, 0, f"cfg2 X3D-M fine stream train step, synthetic [{B},3,16,224,224] fp32, 157 classes"
+        B = batch or 4
+        return B, 256, 64, 96, (f"cfg4 joint Coarse-Fine X3D-M two-stream + Multi-stage Fusion train step: fine [{B},3,256,224,224] "
+                                f"(global tower) -> coarse window [{B},3,64,224,224] -> Grid Pool Tl=17 -> logits [{B},157,64], "
+                                "gradients through BOTH streams, fp32")
+
+    def __init__(self, device, rank=0, which="coarse_fine", batch=None):
+        self.which, self.device = which, device
+        self.B, self.Tf, self.Tc, self.start, self.name = self.describe(which, batch)
         self.TL = self.Tc * 10                                   # labels at the raw-frame rate (stride-10 clips)
         g = torch.Generator().manual_seed(1000 + rank)           # a distinct shard of clips per rank
         self.host_x = torch.randn(self.B, 3, self.Tf, 224, 224, generator=g)
@@ -244,6 +314,8 @@ class TrainWorkload:
         self.graphed = False
         if device.type != "cuda":
             return
+        from coarse_fine_networks_b200 import train
+        self.train = train
         self.host_x, self.host_labels = self.host_x.pin_memory(), self.host_labels.pin_memory()
         self.x = self.host_x.to(device)
         self.labels = self.host_labels.to(device)
@@ -260,9 +332,50 @@ class TrainWorkload:
         else:
             logits = self.train.coarse_fine_forward(self.fine, self.coarse, self.x, self.start, self.Tc, self.fmask,
                                                     meta=self.meta)
-        loss, _ = self.train.charades_loss(logits, self.labels, self.lmask)
+        # train_fine.py:199 resamples with align_corners=True, train_coarse_fineFEAT.py:226 on the default grid
+        loss, _ = self.train.charades_loss(logits, self.labels, self.lmask, align_corners=(self.which == "fine"))
         loss.backward()
         self.loss = loss.detach()
+
+    def parity_check(self):
+        """Outside the timed region: the nets of THIS benchmark, given the key-hashed synthetic weights of the goldens, must
+        reproduce the logits the unmodified reference wrote for the same input (tests/golden/cfg4_synth.npz: cfg-4 geometry,
+        B=1, train-mode BatchNorm; cfg2_synth.npz: [2,3,16,224,224]).  The benchmark's own weights are restored after."""
+        import numpy as np
+        from synth import synth_state_dict, synth_tensor
+        mods = [m for m in (self.fine, self.coarse) if m is not None]
+        saved = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in mods]
+        try:
+            for m, seed in zip(mods, (1, 2)):
+                m.load_state_dict(synth_state_dict(m.state_dict(), seed), strict=True)
+            with torch.no_grad():
+                if self.which == "fine":
+                    gold = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "cfg2_synth.npz"))["out_train"])
+                    x = synth_tensor((2, 3, 16, 224, 224), seed=402).to(self.device)
+                    out = self.fine([x, None])
+                    what = "cfg2_synth.npz out_train [2,157,16]"
+                else:
+                    gold = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "cfg4_synth.npz"))["train/logits"])
+                    x = synth_tensor((1, 3, 256, 224, 224), seed=401).to(self.device)
+                    out = self.train.coarse_fine_forward(self.fine, self.coarse, x, 96, 64, torch.ones(1, 256, device=self.device))
+                    what = "cfg4_synth.npz train/logits [1,157,64] (fine [1,3,256,224,224] -> window [96:160] -> Tl=17)"
+            err = float((out.cpu() - gold).abs().max() / gold.abs().max())
+        finally:
+            for m, sd in zip(mods, saved):
+                m.load_state_dict(sd, strict=True)
+            self.trainer.zero_grad()
+        res = {"golden": what, "written_by": "the unmodified reference on CPU (tests/golden/make_golden.py)", "rel_linf": err,
+               "tol": 1e-3, "ok": bool(err <= 1e-3)}
+        if not res["ok"]:
+            raise RuntimeError(f"bench parity check failed: {res}")
+        return res
+
+    def step_algorithmic_bytes(self):
+        """SURVEY 8(d) compulsory conv traffic of one training step (fwd + bwd ~ 3x fwd), all clips of this rank."""
+        per_clip = FINE_FWD_BYTES_PER_CLIP_T16 * self.Tf / 16.0
+        if self.which != "fine":
+            per_clip += COARSE_FWD_BYTES_PER_CLIP
+        return 3.0 * per_clip * self.B
 
     def prepare(self, use_graph):
         if not use_graph:
@@ -355,25 +468,17 @@ class TrainWorkload:
                 "traffic_basis": "ncu --set full, r01_full_pw_tc2.md, per-row figure x rows of this launch",
                 "peak_basis": peaks["basis"], "algorithmic_bytes": alg, "kernel_ms": ms}
 
-    # ---- the reference algorithm on the host CPU (oracle port), one bounded sample per step
+    # ---- the reference on the host CPU, one bounded sample per step
     _cpu_state = {}
 
     @classmethod
     def cpu_step(cls, budget_s, which="coarse_fine", full=True):
-        """One fwd + loss + bwd of the oracle on ONE clip.  `full`: the workload's own shapes (Tf=256, T=64);
-        otherwise a quarter-length clip (Tf=64, T=16: a quarter of the conv work), reported as 0.25 clip."""
-        from oracle import cf_oracle as O
-        from synth import synth_state_dict
+        """One fwd + script loss + bwd on ONE clip on the host cores.  With baseline/_ref staged this is the UNMODIFIED
+        reference (kind "reference": its modules imported from baseline/_ref, `.cuda()` patched to the identity for the
+        duration so the hard-coded device moves of x3d_coarse.py stay on the CPU); otherwise the oracle port (kind
+        "port").  `full`: the workload's own shapes (Tf=256, T=64); else a quarter-length clip counted as 0.25 clip."""
         import torch.nn.functional as F
         st = cls._cpu_state
-        if "sd_f" not in st:
-            from coarse_fine_networks_b200 import x3d_coarse, x3d_fine   # shapes of the state dicts only
-            f = x3d_fine.generate_model("M", n_classes=N_CLASSES, task="loc", base_bn_splits=1, dropout=0.0)
-            st["sd_f"] = synth_state_dict(f.state_dict(), 1)
-            c = x3d_coarse.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0,
-                                          t_pool="grid", learnedMixing=True, isMixing=True)
-            c.replace_logits(N_CLASSES)
-            st["sd_c"] = synth_state_dict(c.state_dict(), 2)
         if which == "fine":
             Tf, Tc, start, frac = 16, 16, 0, 1.0
         else:
@@ -381,26 +486,46 @@ class TrainWorkload:
         g = torch.Generator().manual_seed(0)
         x = torch.randn(1, 3, Tf, 224, 224, generator=g)
         labels = (torch.rand(1, N_CLASSES, Tc * 10, generator=g) < 0.05).float()
-        req = lambda sd: {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
-                          for k, v in sd.items()}
-        t0 = time.perf_counter()
-        sd_f = req(st["sd_f"])
-        if which == "fine":
-            logits = O.fine_forward(sd_f, x, True)
+        masks = torch.ones(1, Tc * 10)
+        meta = torch.tensor([[float(start), float(Tc), float(Tf), 1.0]])
+        if "ref" not in st:
+            st["ref"] = import_reference()
+        if st["ref"] is not None:
+            kind = "reference"
+            if ("models", which) not in st:
+                st[("models", which)] = reference_models(which, st["ref"])
+            fine, coarse = st[("models", which)]
+            real_cuda = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda self, *a, **k: self
+            try:
+                t0 = time.perf_counter()
+                reference_step(which, fine.train(), coarse.train() if coarse is not None else None, x, labels, masks,
+                               torch.ones(1, Tf), meta, start, Tc)
+                dt = time.perf_counter() - t0
+            finally:
+                torch.Tensor.cuda = real_cuda
         else:
-            sd_c = req(st["sd_c"])
-            feat = O.fine_forward(sd_f, x, True, global_tower=True)
-            meta = torch.tensor([[float(start), float(Tc), float(Tf), 1.0]])
-            logits = O.coarse_forward(sd_c, x[:, :, start:start + Tc], feat, torch.ones(1, Tf), meta, True)
-        pl = F.interpolate(logits, labels.shape[2], mode="linear", align_corners=True)
-        probs = torch.sigmoid(pl)
-        loss = (F.binary_cross_entropy(probs.max(dim=2)[0], labels.max(dim=2)[0]) +
-                F.binary_cross_entropy(probs, labels, reduction="sum") / (labels.shape[2] * N_CLASSES)) / 2
-        loss.backward()
-        dt = time.perf_counter() - t0
+            kind = "port"
+            from oracle import cf_oracle as O
+            from synth import synth_state_dict
+            if "sd_f" not in st:
+                st["sd_f"] = synth_state_dict(state_template("fine_M"), 1)
+                st["sd_c"] = synth_state_dict(state_template("coarse_M"), 2)
+            req = lambda sd: {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+                              for k, v in sd.items()}
+            t0 = time.perf_counter()
+            sd_f = req(st["sd_f"])
+            if which == "fine":
+                logits = O.fine_forward(sd_f, x, True)
+            else:
+                sd_c = req(st["sd_c"])
+                feat = O.fine_forward(sd_f, x, True, global_tower=True)
+                logits = O.coarse_forward(sd_c, x[:, :, start:start + Tc], feat, torch.ones(1, Tf), meta, True)
+            script_loss(logits, labels, masks, which == "fine").backward()
+            dt = time.perf_counter() - t0
         what = ("1 clip of the same workload (full shapes) per step" if frac == 1.0 else
                 "a quarter-length clip (fine Tf=64, coarse T=16 -> Tl=5) per step, counted as 0.25 clip")
-        return frac, dt, what + "; fwd + loss + bwd through both streams, no optimizer step"
+        return frac, dt, what + "; fwd + script loss + bwd through both streams, no optimizer step", kind
 
 
 WORKLOADS = {"gridpool": GridPoolWorkload, "fine": TrainWorkload, "coarse_fine": TrainWorkload}
@@ -422,10 +547,72 @@ def cpu_step_fn(name):
 
 
 # ----------------------------------------------------------------------------------------
+def gpu_eager_baseline(which, device, steps=5, warmup=3):
+    """The competitor SURVEY 2.1 names: the UNMODIFIED reference modules (baseline/_ref) in PyTorch eager mode (cuDNN /
+    ATen kernels) on the SAME B200, same workload shapes, same step content as ours minus the optimizer (fwd + script loss
+    + bwd through both streams), CUDA-event timed.  fp32 with TF32 off (the precision our 3xTF32 path is held to) and, for
+    information, with PyTorch's stock cuDNN setting (allow_tf32=True for convolutions).  The per-GPU batch is ours (4, or 8
+    for cfg 2); if the reference's 6-D fusion temporaries do not fit, the batch is halved until it does (reported)."""
+    ref = import_reference()
+    if ref is None:
+        return {"unavailable": "baseline/_ref not staged (build() copies it from /root/reference)"}
+    B0, Tf, Tc, start, _ = TrainWorkload.describe(which)
+    out = {"impl": "reference modules (baseline/_ref), torch eager " + torch.__version__ + ", cudnn " + str(torch.backends.cudnn.version()),
+           "step": "fwd + script loss + bwd through both streams, no optimizer step", "unit": "clips/s"}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        fine, coarse = reference_models(which, ref)
+        fine = fine.to(device).train()
+        coarse = coarse.to(device).train() if coarse is not None else None
+        B = B0
+        while B >= 1:
+            try:
+                g = torch.Generator().manual_seed(7)
+                x = torch.randn(B, 3, Tf, 224, 224, generator=g).to(device)
+                labels = (torch.rand(B, N_CLASSES, Tc * 10, generator=g) < 0.05).float().to(device)
+                masks = torch.ones(B, Tc * 10, device=device)
+                fmask = torch.ones(B, Tf, device=device)
+                meta = torch.tensor([[float(start), float(Tc), float(Tf), 1.0]]).repeat(B, 1).to(device)
+                for tag, tf32 in (("fp32", False), ("tf32_conv_default", True)):
+                    torch.backends.cudnn.allow_tf32 = tf32
+                    torch.backends.cuda.matmul.allow_tf32 = False
+                    for _ in range(warmup):
+                        reference_step(which, fine, coarse, x, labels, masks, fmask, meta, start, Tc)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        reference_step(which, fine, coarse, x, labels, masks, fmask, meta, start, Tc)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / steps
+                    out[tag] = {"value": B / (ms * 1e-3), "ms_per_step": ms}
+                out.update({"per_gpu_batch": B, "steps": steps, "warmup": warmup, "value": out["fp32"]["value"],
+                            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30})
+                break
+            except torch.cuda.OutOfMemoryError:
+                for m in (fine, coarse):
+                    if m is not None:
+                        m.zero_grad(set_to_none=True)
+                x = labels = None
+                torch.cuda.empty_cache()
+                out.setdefault("oom_at_batch", []).append(B)
+                B //= 2
+        if "value" not in out:
+            out["unavailable"] = "out of memory even at batch 1"
+    except Exception as e:                                        # a broken competitor must not take the bench line down
+        out["unavailable"] = repr(e)[:300]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 def run_reference(args, rank):
-    """--impl reference: the reference's algorithm for this path on the host CPU.  The reference is pure
-    Python/PyTorch (nothing to compile into oracle/_ref) and /root/reference does not exist on the GPU box,
-    so this is the oracle port (pinned to the reference's outputs by tests/golden), with all host threads.
+    """--impl reference: the reference's own implementation of this path on the host CPU, all host threads: the unmodified
+    reference modules staged in baseline/_ref (kind "reference"; the reference is pure Python/PyTorch, pip cannot install
+    it -- no setup.py -- so build() copies its three model files there); the oracle port only if that staging is absent.
+    Nothing of the product (package or .so) is imported by this arm.
     Each step is a bounded sample of the workload; the run is additionally bounded in wall time
     (--ref-budget seconds): at least one timed step, at most --steps."""
     if rank != 0:
@@ -434,25 +621,26 @@ def run_reference(args, rank):
     name = "coarse_fine" if args.workload == "auto" else args.workload
     fn = cpu_step_fn(name)
     t_start = time.perf_counter()
-    units, dt, sample = fn(args.ref_budget, False)               # probe / warm-up on the small sample
+    units, dt, sample, kind = fn(args.ref_budget, False)         # probe / warm-up on the small sample
     full = name != "coarse_fine" or dt * 5.0 < args.ref_budget / 3
     times, n_units = [], 0.0
     for i in range(max(args.warmup - 1, 0) + args.steps):
         if times and time.perf_counter() - t_start > args.ref_budget:
             break
-        units, dt, sample = fn(args.ref_budget, full)
+        units, dt, sample, kind = fn(args.ref_budget, full)
         if i >= max(args.warmup - 1, 0) or time.perf_counter() - t_start > args.ref_budget:
             times.append(dt)
             n_units = units
     ms = 1e3 * sum(times) / len(times)
     val = n_units / (ms * 1e-3)
-    wl_name = make_workload(name, torch.device("cpu"), 0)[0].name
+    wl_name = GridPoolWorkload.name if name == "gridpool" else TrainWorkload.describe(name)[4]
     line = {"impl": "reference", "metric": "clips/sec fwd+bwd", "value": val, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": len(times), "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "sample": sample, "time_budget_s": args.ref_budget},
-            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "product_imported": any(m.startswith("coarse_fine_networks_b200") for m in sys.modules)}
     print(json.dumps(line), flush=True)
 
 
@@ -465,6 +653,8 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "coarse_fine", "fine", "gridpool"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden-logits check before the timed region")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager reference on the same GPU")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="wall-time bound (s) of the CPU reference arm")
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="wall-time bound (s) of the cpu_baseline leg")
     args = ap.parse_args()
@@ -509,6 +699,7 @@ def main():
         wl.step()
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - n0
+    parity = wl.parity_check() if (rank == 0 and isinstance(wl, TrainWorkload) and not args.no_parity) else None
     wl.prepare(use_graph=not args.no_graph)
 
     def sync():
@@ -552,16 +743,33 @@ def main():
         roof = wl.roofline(peaks, flush)
         if wl_key != "gridpool":
             gp = gridpool_gather_roofline(device, peaks, flush)
+            # the honest whole-step figure next to the best-launch one: compulsory conv bytes of the step / step time
+            alg = wl.step_algorithmic_bytes()
+            ach = alg / (ms_step * 1e-3) / 1e9
+            roof["step"] = {"bound": "hbm", "algorithmic_bytes": alg, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": ach / peaks["hbm_gbs"],
+                            "basis": "SURVEY 8(d): fine 730.4 MB/clip fwd at T=16 (x T/16) + coarse 1.75 GB/clip, x3 for fwd+bwd"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         fn = cpu_step_fn(wl_key)
-        units, dt, sample = fn(args.cpu_budget, False)              # quarter-length probe (also the warm-up)
+        units, dt, sample, kind = fn(args.cpu_budget, False)        # quarter-length probe (also the warm-up)
         if wl_key == "coarse_fine" and dt * 5.0 < args.cpu_budget:  # the full clip fits the budget: time it
-            units, dt, sample = fn(args.cpu_budget, True)
+            units, dt, sample, kind = fn(args.cpu_budget, True)
         elif wl_key != "coarse_fine":
-            units, dt, sample = fn(args.cpu_budget, True)
-        cpu = {"value": units / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+            units, dt, sample, kind = fn(args.cpu_budget, True)
+        cpu = {"value": units / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample}
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline and isinstance(wl, TrainWorkload):
+        which = wl.which
+        wl_name, wl_cfg = wl.name, wl.config()
+        wl.graph = None
+        del wl
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        eager = gpu_eager_baseline(which, device)
+        wl = type("Done", (), {"name": wl_name, "config": lambda self: wl_cfg, "dtype": "f32"})()
     if rank == 0:
         cfg = {"workload": wl.name, "parallelism": f"dp{world}"}
         cfg.update(wl.config())
@@ -569,7 +777,7 @@ def main():
                 "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": cfg,
                 "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
-                "clocks": clocks, "roofline": roof, "gridpool_roofline": gp, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roof, "gridpool_roofline": gp, "cpu_baseline": cpu, "parity": parity, "gpu_eager_baseline": eager}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

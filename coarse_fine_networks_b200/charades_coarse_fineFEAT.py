@@ -35,6 +35,7 @@ def extract_fine_features(fine_net, loader, save_dir, log=None):
     clips [1,N,3,T,S,S], labels, masks, names) through the fine stream built with global_tower=True, features written in the
     layout the coarse loader reads.  -> number of videos written."""
     fine_net.train(False)                                                 # extract_fineFEAT.py:137
+    getattr(fine_net, "module", fine_net).aggregate_sub_bn_stats()        # :138-139 -- eval-mode BN reads bn.running_*
     done = 0
     with torch.no_grad():
         for clips, _labels, masks, names in loader:

@@ -32,6 +32,22 @@ void cf_set_error(const char* fmt, ...);
 extern unsigned long long g_cf_launches;
 #define CF_COUNT_LAUNCH(n) (g_cf_launches += (unsigned long long)(n))
 
+// "done once" flag for cudaFuncSetAttribute opt-ins: the attribute belongs to the device / context, so the flag is kept per
+// device (a process that touches a second GPU opts in there too) and is safe to race on from several host threads.
+struct CfOncePerDevice {
+    unsigned long long mask = 0;
+    bool need() const {
+        int d = 0;
+        cudaGetDevice(&d);
+        return !((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> (d & 63)) & 1ull);
+    }
+    void mark() {
+        int d = 0;
+        cudaGetDevice(&d);
+        __atomic_fetch_or(&mask, 1ull << (d & 63), __ATOMIC_RELEASE);
+    }
+};
+
 static inline int cf_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline long long cf_cdiv64(long long a, long long b) { return (a + b - 1) / b; }
 

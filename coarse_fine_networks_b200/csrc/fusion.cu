@@ -423,8 +423,8 @@ int cf_rewight_agg_fwd(const cf_rewight_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a->B > 0 && a->C > 0 && a->Tf > 0 && a->Tl > 0 && a->P > 0, "bad shape");
     size_t smem = ((size_t)a->Tf * a->Tl + ((a->Tl + 3) & ~3) + 8 * RW_KC * 32) * sizeof(float);
     CF_CHECK_ARG(smem <= 200 * 1024, "Tf*Tl too large for shared memory");
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(rewight_agg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; }
+    static CfOncePerDevice done;
+    if (done.need()) { cudaFuncSetAttribute(rewight_agg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done.mark(); }
     dim3 grid((unsigned)(a->B * a->P), (unsigned)cf_cdiv(a->C, 32));
     rewight_agg_fwd_kernel<<<grid, dim3(32, 8), smem, stream>>>(*a);
     CF_COUNT_LAUNCH(1);
@@ -438,8 +438,8 @@ int cf_rewight_agg_bwd(const cf_rewight_bwd_args* a, cudaStream_t stream) {
     int Tl4 = (a->Tl + 3) & ~3;
     size_t smem = ((size_t)a->Tl * a->C + 2 * Tl4 + 8 * Tl4) * sizeof(float);
     CF_CHECK_ARG(smem <= 200 * 1024, "Tl*C too large for shared memory");
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(rewight_agg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; }
+    static CfOncePerDevice done;
+    if (done.need()) { cudaFuncSetAttribute(rewight_agg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done.mark(); }
     rewight_agg_bwd_kernel<<<(unsigned)(a->B * a->P), 256, smem, stream>>>(*a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();

@@ -2,8 +2,10 @@
 // and a fused SGD-momentum update over the flat parameter / gradient buffers.
 //
 // Reference semantics:
-//   loss ........ train_fine.py:199-212,226 (same train_coarse_fineFEAT.py:226-247):
-//                 F.interpolate(logits, TL, 'linear', align_corners=True); probs = sigmoid * mask;
+//   loss ........ train_fine.py:199-212,226: F.interpolate(logits, TL, 'linear', align_corners=True);
+//                 train_coarse_fineFEAT.py:226-247: F.interpolate(logits, TL, 'linear') -- the DEFAULT
+//                 align_corners=False grid (half-pixel centres); the caller chooses with `align_corners`;
+//                 probs = sigmoid * mask;
 //                 cls = BCE_mean(max_t probs, max_t labels); loc = BCE_sum(probs, labels) / (sum(mask) * C);
 //                 loss = (cls + loc) / (2 * num_steps_per_update)
 //   optimiser ... optim.SGD(momentum=0.9, weight_decay=1e-5) (train_fine.py:130), fusion parameters
@@ -23,7 +25,7 @@ __device__ __forceinline__ float bce_grad(float p, float y) { return (p - y) / f
 __global__ void __launch_bounds__(128) charades_loss_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
                                                             const float* __restrict__ masks, float* __restrict__ loss,
                                                             float* __restrict__ dlogits, int B, int C, int T, int TL,
-                                                            float scale) {
+                                                            float scale, int align_corners) {
     extern __shared__ float dl[];
     __shared__ float red[4];
     __shared__ int redi[4];
@@ -41,11 +43,17 @@ __global__ void __launch_bounds__(128) charades_loss_kernel(const float* __restr
     __syncthreads();
     const float msum = red[0] + red[1] + red[2] + red[3];
     __syncthreads();
-    const float step = (TL > 1) ? (float)(T - 1) / (float)(TL - 1) : 0.f;
+    // ATen's area_pixel_compute_scale / _source_index (UpSample.cuh), evaluated in fp32 like upsample_linear1d
+    const float step = align_corners ? ((TL > 1) ? (float)(T - 1) / (float)(TL - 1) : 0.f) : (float)T / (float)TL;
+    auto source = [&](int u) -> float {
+        if (align_corners) return __fmul_rn(step, (float)u);
+        const float sidx = __fsub_rn(__fmul_rn(step, __fadd_rn((float)u, 0.5f)), 0.5f);
+        return sidx < 0.f ? 0.f : sidx;
+    };
     float loc = 0.f, pmax = -1.f, ymax = -INFINITY;
     int amax = 0;
     for (int u = tid; u < TL; u += 128) {
-        float src = __fmul_rn(step, (float)u);
+        float src = source(u);
         int j0 = min((int)src, T - 1), j1 = min(j0 + 1, T - 1);
         float lam = src - (float)j0;
         float z = (1.0f - lam) * lg[j0] + lam * lg[j1];
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(128) charades_loss_kernel(const float* __restr
     if (dlogits == nullptr) return;
     const float gcls = scale * bce_grad(pm, ym) / cls_den;
     for (int u = tid; u < TL; u += 128) {
-        float src = __fmul_rn(step, (float)u);
+        float src = source(u);
         int j0 = min((int)src, T - 1), j1 = min(j0 + 1, T - 1);
         float lam = src - (float)j0;
         float z = (1.0f - lam) * lg[j0] + lam * lg[j1];
@@ -118,11 +126,11 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float4* __restrict__ p, f
 extern "C" {
 
 int cf_charades_loss(const float* logits, const float* labels, const float* masks, float* loss2, float* dlogits, int B, int C,
-                     int T, int TL, float scale, cudaStream_t stream) {
+                     int T, int TL, float scale, int align_corners, cudaStream_t stream) {
     CF_CHECK_ARG(logits && labels && masks && loss2, "null pointer");
     CF_CHECK_ARG(B > 0 && C > 0 && T > 0 && TL > 0 && T <= 8192, "bad shape");
     charades_loss_kernel<<<(unsigned)(B * C), 128, (size_t)T * sizeof(float), stream>>>(logits, labels, masks, loss2, dlogits, B,
-                                                                                      C, T, TL, scale);
+                                                                                      C, T, TL, scale, align_corners);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

@@ -315,11 +315,11 @@ int cf_dense_s2_fwd_try(const cf_pw_args* a, cudaStream_t stream) {
     f.To = g.T; f.Ho = g.H; f.Wo = g.W; f.Ti = g.Ti; f.Hi = g.Hi; f.Wi = g.Wi;
     f.sample_stride = g.sample_stride; f.pro = a->pro_mode; f.tiles_per_sample = (int)tiles;
     const size_t smem = (27 * FW_TAPSTRIDE + 3 * 24 + (FW_THREADS / 32) * 2 * 24) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static CfOncePerDevice attr_done;
+    if (attr_done.need()) {
         cudaError_t e = cudaFuncSetAttribute(dense3_s2_fwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cf_set_error("cf_dense_s2_fwd: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
-        attr_done = true;
+        attr_done.mark();
     }
     dense3_s2_fwd_kernel<24><<<(unsigned)(tiles * a->B), FW_THREADS, smem, stream>>>(f);
     CF_COUNT_LAUNCH(1);
@@ -488,11 +488,11 @@ int cf_dense_s2_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     w.sample_stride = g.sample_stride; w.dy_affine2 = a->dy_mode == CF_PRO_AFFINE2; w.x_mode = a->x_mode;
     w.chunks_per_sample = (int)cps;
     const size_t smem = (size_t)(WG3_ROWS * 24 + WG3_ROWS * 27 * 24) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static CfOncePerDevice attr_done;
+    if (attr_done.need()) {
         cudaError_t e = cudaFuncSetAttribute(dense3_s2_wgrad_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cf_set_error("cf_dense_s2_wgrad: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
-        attr_done = true;
+        attr_done.mark();
     }
     long long ctas = cps * a->B;
     if (ctas > 148 * 2) ctas = 148 * 2;

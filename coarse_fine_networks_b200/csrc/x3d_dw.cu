@@ -585,8 +585,8 @@ static int launch_dw_fwd(const cf_dw_args* a, cudaStream_t stream) {
     dim3 grid((unsigned)cf_cdiv64(ntask, 256), (unsigned)a->B);
 #define CF_DW_LAUNCH(KW_, SW_)                                                          \
     do {                                                                                \
-        static bool done = false;                                                       \
-        if (!done) { set_smem(dw_fwd_kernel<V, KW_, SW_, TW>); done = true; }           \
+        static CfOncePerDevice done;                                                       \
+        if (done.need()) { set_smem(dw_fwd_kernel<V, KW_, SW_, TW>); done.mark(); }           \
         dw_fwd_kernel<V, KW_, SW_, TW><<<grid, 256, smem, stream>>>(*a);                \
     } while (0)
     if (g.kw == 3 && g.sw == 1) CF_DW_LAUNCH(3, 1);
@@ -606,8 +606,8 @@ static int launch_dw_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     size_t smem = (size_t)(taps + 2) * a->C * sizeof(float);
     long long ntask = (long long)g.Ti * g.Hi * g.Wi * (a->C / V);
     dim3 grid((unsigned)cf_cdiv64(ntask, 256), (unsigned)a->B);
-    static bool done = false;
-    if (!done) { set_smem(dw_dgrad_kernel<V>); done = true; }
+    static CfOncePerDevice done;
+    if (done.need()) { set_smem(dw_dgrad_kernel<V>); done.mark(); }
     dw_dgrad_kernel<V><<<grid, 256, smem, stream>>>(*a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
@@ -624,8 +624,8 @@ static int launch_dw_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     long long chunk = cf_cdiv64(R, want_ctas);
     if (chunk < 4LL * PY) chunk = 4LL * PY;
     dim3 grid((unsigned)cf_cdiv64(R, chunk), (unsigned)a->B);
-    static bool done = false;
-    if (!done) { set_smem(dw_wgrad_kernel<V, TAPS>); done = true; }
+    static CfOncePerDevice done;
+    if (done.need()) { set_smem(dw_wgrad_kernel<V, TAPS>); done.mark(); }
     dw_wgrad_kernel<V, TAPS><<<grid, 256, smem, stream>>>(*a, (int)chunk);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
@@ -643,8 +643,8 @@ static int launch_dw_dgrad3(const cf_dw_args* a, cudaStream_t stream) {
     size_t smem = (size_t)(27 + 2) * a->C * sizeof(float);
     long long ntask = (long long)g.Ti * g.Hi * ((g.Wi + DW3_TW - 1) / DW3_TW) * (a->C / V);
     dim3 grid((unsigned)cf_cdiv64(ntask, 256), (unsigned)a->B);
-    static bool done = false;
-    if (!done) { set_smem(dw_dgrad3_kernel<V, ST>); done = true; }
+    static CfOncePerDevice done;
+    if (done.need()) { set_smem(dw_dgrad3_kernel<V, ST>); done.mark(); }
     dw_dgrad3_kernel<V, ST><<<grid, 256, smem, stream>>>(*a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
@@ -661,8 +661,8 @@ static int launch_dw_wgrad3(const cf_dw_args* a, cudaStream_t stream) {
     long long chunk = cf_cdiv64(NG, want_ctas);
     if (chunk < 4LL * PY) chunk = 4LL * PY;
     dim3 grid((unsigned)cf_cdiv64(NG, chunk), (unsigned)a->B);
-    static bool done = false;
-    if (!done) { set_smem(dw_wgrad3_kernel<V, ST>); done = true; }
+    static CfOncePerDevice done;
+    if (done.need()) { set_smem(dw_wgrad3_kernel<V, ST>); done.mark(); }
     dw_wgrad3_kernel<V, ST><<<grid, 256, smem, stream>>>(*a, (int)chunk);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();

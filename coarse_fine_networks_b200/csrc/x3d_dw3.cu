@@ -365,11 +365,11 @@ static int d3_launch(const cf_dw_args* a, const D3Params& p, cudaStream_t stream
     constexpr int PLANE = D3_HH * HW * D3_CS;
     const int nstg = (MODE == D3_DGRAD && a->pro_mode == CF_PRO_AFFINE2) ? 2 : 1;
     const size_t smem = (size_t)((3 + nstg) * PLANE + 5 * D3_CS + 27 * D3_CS) * sizeof(float);
-    static bool done = false;
-    if (!done) {
+    static CfOncePerDevice done;
+    if (done.need()) {
         cudaError_t e = cudaFuncSetAttribute(dw3_kernel<MODE, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { cf_set_error("dw3: cannot opt in to shared memory: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
-        done = true;
+        done.mark();
     }
     dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
     dw3_kernel<MODE, NPW><<<grid, D3_LANES * 4 * NPW, smem, stream>>>(*a, p);

@@ -510,11 +510,11 @@ static int s2_launch_dgrad(const cf_dw_args* a, const S2Params& p, cudaStream_t 
     constexpr int OTW = S2_PW * NPW;
     constexpr int PLANE = (S2_OTH + 1) * (OTW + 1) * S2_CS;
     const size_t smem = (size_t)(5 * PLANE + 5 * S2_CS + 27 * S2_CS) * sizeof(float);
-    static bool done = false;
-    if (!done) {
+    static CfOncePerDevice done;
+    if (done.need()) {
         cudaError_t e = cudaFuncSetAttribute(dw3s2_dgrad_kernel<NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) { cf_set_error("dw3s2: cannot opt in to shared memory: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
-        done = true;
+        done.mark();
     }
     dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
     dw3s2_dgrad_kernel<NPW><<<grid, S2_LANES * S2_OTH * NPW, smem, stream>>>(*a, p);
@@ -529,11 +529,11 @@ static int s2_launch(const cf_dw_args* a, const S2Params& p, cudaStream_t stream
     constexpr int OTW = S2_PW * NPW, IW = 2 * OTW + 1;
     constexpr int PLANE = S2_IH * IW * S2_CS;
     const size_t smem = (size_t)(2 * PLANE + 5 * S2_CS + 27 * S2_CS) * sizeof(float);
-    static bool done = false;
-    if (!done) {
+    static CfOncePerDevice done;
+    if (done.need()) {
         cudaError_t e = cudaFuncSetAttribute(dw3s2_kernel<MODE, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) { cf_set_error("dw3s2: cannot opt in to shared memory: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
-        done = true;
+        done.mark();
     }
     dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
     dw3s2_kernel<MODE, NPW><<<grid, S2_LANES * S2_OTH * NPW, smem, stream>>>(*a, p);

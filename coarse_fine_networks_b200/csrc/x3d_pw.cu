@@ -352,10 +352,10 @@ static int launch_pw(const cf_pw_args* a, int R, cudaStream_t stream) {
     size_t smem = (size_t)(PW_BK * PW_LDA + PW_BK * (BN_ + 4) + 3 * cin) * sizeof(float);
     size_t red = (size_t)2 * 16 * BN_ * sizeof(float);
     if (smem < red) smem = red;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static CfOncePerDevice attr_done;
+    if (attr_done.need()) {
         cudaFuncSetAttribute(pw_conv_kernel<BN_, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     if (smem > 100 * 1024) { cf_set_error("cf_pw_conv: K too large for the table cache"); return CF_ERR_ARG; }
     dim3 grid((unsigned)(tps * a->B), (unsigned)cf_cdiv(a->N, BN_));

@@ -357,14 +357,12 @@ static size_t tc_smem_bytes(const TcTiling& t, int K) {
 
 template <int AV, int EV>
 static int launch_tc(const cf_pw_args* a, const TcTiling& t, int R, uint32_t tmem_cols, size_t smem, cudaStream_t stream) {
-    static size_t cur_max = 48 * 1024;       // opt in to more dynamic shared memory as larger problems show up
-    if (smem > cur_max) {
+    if (smem > 48 * 1024) {     // opt in per launch: the attribute is per device and the call is cheap
         cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<AV, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             cf_set_error("cf_pw_conv_tc: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
             return CF_ERR_CUDA;
         }
-        cur_max = smem;
     }
     int tps = cf_cdiv(R, TC_BM);
     dim3 grid((unsigned)(tps * a->B), (unsigned)t.ntiles);

@@ -238,15 +238,15 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < 2 * p.acc_stride) p.tmem_cols <<= 1;
     cf_pw_tc_pack_launch(a->w, a->w_sn, a->w_sk, a->wpack, K, N, p.NT, p.NTp, p.ntiles, p.nchunks, stream);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static CfOncePerDevice attr_done;
+    if (attr_done.need()) {
         cudaError_t e = cudaFuncSetAttribute(p2w8::pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(p2w16::pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
         if (e != cudaSuccess) {
             cf_set_error("cf_pw_conv_tc: cannot opt in to %d B of shared memory: %s", P2_SMEM_MAX, cudaGetErrorString(e));
             return CF_ERR_CUDA;
         }
-        attr_done = true;
+        attr_done.mark();
     }
     long long grid = p.total_tiles < p2_sm_count() ? p.total_tiles : p2_sm_count();
     p.timing = p2_timing();

@@ -478,10 +478,10 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     cudaError_t e = cudaSuccess;
 #define WG_LAUNCH(DYM_, XM_)                                                                                                  \
     do {                                                                                                                      \
-        static bool attr_done = false;                                                                                        \
-        if (!attr_done) {                                                                                                     \
+        static CfOncePerDevice attr_done;                                                                                        \
+        if (attr_done.need()) {                                                                                                     \
             e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<DYM_, XM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX); \
-            attr_done = e == cudaSuccess;                                                                                     \
+            if (e == cudaSuccess) attr_done.mark();                                                                                     \
         }                                                                                                                     \
         if (e == cudaSuccess) pw_wgrad_tc_kernel<DYM_, XM_><<<grid, WG_THREADS, smem, stream>>>(*a, p);                       \
     } while (0)

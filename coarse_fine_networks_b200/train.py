@@ -16,11 +16,12 @@ FUSION_LR_MULT = 10.0        # train_coarse_fineFEAT.py:141
 
 
 class CharadesLossFn(torch.autograd.Function):
-    """(cls_loss + loc_loss) * scale with scale = 1/(2*num_steps_per_update) (train_fine.py:199-212,226).
+    """(cls_loss + loc_loss) * scale with scale = 1/(2*num_steps_per_update) (train_fine.py:199-212,226;
+    train_coarse_fineFEAT.py:226-247).  align_corners selects the grid of the F.interpolate to the label length.
     Returns (loss, parts) with parts = [cls_loss, loc_loss] (not differentiable)."""
 
     @staticmethod
-    def forward(ctx, logits, labels, masks, scale):
+    def forward(ctx, logits, labels, masks, scale, align_corners):
         logits = logits.contiguous().float()
         labels = labels.contiguous().float()
         masks = masks.contiguous().float()
@@ -29,7 +30,7 @@ class CharadesLossFn(torch.autograd.Function):
         parts = torch.zeros(2, device=logits.device, dtype=torch.float32)
         dlogits = torch.empty_like(logits)
         call("cf_charades_loss", ptr(logits), ptr(labels), ptr(masks), ptr(parts), ptr(dlogits), B, C, T, TL, float(scale),
-             stream_ptr())
+             int(bool(align_corners)), stream_ptr())
         ctx.save_for_backward(dlogits)
         ctx.mark_non_differentiable(parts)
         return parts.sum() * float(scale), parts
@@ -37,11 +38,20 @@ class CharadesLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, _dparts):
         (dlogits,) = ctx.saved_tensors
-        return dlogits * dloss, None, None, None
+        return dlogits * dloss, None, None, None, None
 
 
-def charades_loss(logits, labels, masks, num_steps_per_update=1):
-    return CharadesLossFn.apply(logits, labels, masks, 1.0 / (2.0 * num_steps_per_update))
+def charades_loss(logits, labels, masks, num_steps_per_update=1, align_corners=True):
+    """Loss of the scripts' hot loop.  The two scripts resample the logits to the label length on DIFFERENT grids:
+    train_fine.py:199 passes align_corners=True (the default here), train_coarse_fineFEAT.py:226 calls
+    F.interpolate(per_frame_logits, tl, mode='linear') with PyTorch's default align_corners=False -- use
+    ``coarse_charades_loss`` (or align_corners=False) for the coarse script."""
+    return CharadesLossFn.apply(logits, labels, masks, 1.0 / (2.0 * num_steps_per_update), align_corners)
+
+
+def coarse_charades_loss(logits, labels, masks, num_steps_per_update=1):
+    """train_coarse_fineFEAT.py:226-247: the same loss on F.interpolate's default (align_corners=False) grid."""
+    return charades_loss(logits, labels, masks, num_steps_per_update, align_corners=False)
 
 
 def is_fusion_param(name):

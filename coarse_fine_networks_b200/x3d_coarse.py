@@ -171,6 +171,10 @@ def GridUnpool(inp):
     return G.grid_unpool(x, gx, bool(is_logit), ratio=4)
 
 
+_REF_CHILD_ORDER = ('pool_1', 'conv1_s', 'conv1_t', 'bn1', 'relu', 'layer1', 'layer2', 'layer3', 'layer4', 'conv5', 'bn5',
+                    'rw2', 'rw3', 'rw4', 'rw5', 'rw6', 'mix2', 'mix3', 'mix4', 'mix5', 'gauss', 'avgpool', 'fc1', 'fc2', 'dropout')
+
+
 # ----------------------------------------------------------------------------------------
 class ResNet(_FineResNet):
     """Coarse-stream X3D with Grid Pool after layer1, Multi-stage Fusion of the fine features
@@ -201,6 +205,10 @@ class ResNet(_FineResNet):
             for i in range(4):
                 setattr(self, f"mix{i + 2}", MixingLayer(depth=planes[i][1], learned=learnedMixing, index=i))
         self.gauss = Gaussian(ratio=1)
+        # registration order of the reference's constructor (x3d_coarse.py:489-555): named_parameters() order is what
+        # torch.optim.SGD checkpoints index by, so resuming from / saving to the scripts' optimizer_state_dict needs it
+        first = [k for k in _REF_CHILD_ORDER if k in self._modules]
+        self._modules = {k: self._modules[k] for k in first + [k for k in self._modules if k not in first]}
         for m in self.modules():                             # same init rule as the reference (:557-561)
             if isinstance(m, nn.Conv3d):
                 nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')

@@ -472,12 +472,14 @@ int cf_block_maxpool_bwd(const float* dout, const int32_t* idx, float* dx, int B
 /* Training-step glue                                                                       */
 /* ====================================================================================== */
 /* Charades localisation loss of the scripts (train_fine.py:199-212,226; train_coarse_fineFEAT.py:226-247):
- * logits [B,C,T] are linearly interpolated to the label length TL (align_corners=True),
+ * logits [B,C,T] are linearly interpolated to the label length TL -- align_corners != 0: the
+ * align_corners=True grid of train_fine.py:199; align_corners == 0: F.interpolate's default half-pixel grid
+ * (src = max((u+0.5)*T/TL - 0.5, 0)), which is what train_coarse_fineFEAT.py:226 calls --,
  * probs = sigmoid * mask; loss2[0] += BCE_mean(max_t probs, max_t labels), loss2[1] += BCE_sum(probs,
  * labels)/(sum(mask)*C) (caller zero-fills loss2); dlogits [B,C,T] = d(scale*(loss2[0]+loss2[1]))/dlogits,
  * i.e. scale = 1/(2*num_steps_per_update) reproduces the scripts.  dlogits may be NULL (evaluation). */
 int cf_charades_loss(const float* logits, const float* labels, const float* masks, float* loss2, float* dlogits, int B, int C,
-                     int T, int TL, float scale, cudaStream_t stream);
+                     int T, int TL, float scale, int align_corners, cudaStream_t stream);
 
 /* fused SGD with momentum over flat fp32 buffers (optim.SGD, train_fine.py:130): g = grad_scale*g + wd*p;
  * v = momentum*v + g; p -= lr*v; g = 0.  Elements [0,n_split) use lr0, the rest lr1 (the 'rw'/'mix'

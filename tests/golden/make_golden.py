@@ -475,8 +475,172 @@ def gen_charades_loader():
     save("charades_loader", **out)
 
 
+# ---------------------------------------------------------------------------- benchmarked shapes (BASELINE cfg 2 / cfg 4)
+DEPTH = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
+FEAT_FRAMES = (0, 95, 96, 128, 159, 255)             # frames of the [1,C,256,7,7] fine features kept in the fixture
+
+
+def shipped(name):
+    """model_state_dict of a shipped checkpoint (/root/reference/models), or None."""
+    p = os.path.join(REF, "models", name)
+    if not os.path.exists(p):
+        return None
+    return torch.load(p, weights_only=False, map_location="cpu")["model_state_dict"]
+
+
+def _ref_models(weights):
+    """(fine global-tower net, coarse net) of the reference at the cfg-4 configuration (SURVEY 8(d) cfg 4)."""
+    fine = ref_fine.generate_model("M", n_classes=157, task="loc", base_bn_splits=1, dropout=0.0, global_tower=True)
+    coarse = ref_coarse.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0,
+                                       t_pool="grid", learnedMixing=True, isMixing=True)
+    coarse.replace_logits(157)
+    coarse.rw6.dropout.p = 0.0
+    if weights == "shipped":
+        fine.load_state_dict(shipped("fine_charades_039000_SAVE.pt"), strict=True)
+        coarse.load_state_dict(shipped("coarse_fineFEAT_charades_019000_SAVE.pt"), strict=True)
+    else:
+        fill_state_dict(fine, seed=1)                 # the seeds bench.py's CPU leg and parity check use
+        fill_state_dict(coarse, seed=2)
+    return fine, coarse
+
+
+def gen_cfg4():
+    """cfg 4 geometry at B=1 through the unmodified reference: fine global tower on [1,3,256,224,224] -> coarse stream on
+    the window [96:160] with meta=[96,64,256,1] -> Grid Pool Tl=17 -> logits [1,157,64]; eval and train mode; key-hashed
+    synthetic weights and the shipped Charades checkpoints."""
+    x = synth_tensor((1, 3, 256, 224, 224), seed=401)
+    mask = torch.ones(1, 256)
+    for weights in ("synth", "shipped"):
+        if weights == "shipped" and shipped("fine_charades_039000_SAVE.pt") is None:
+            continue
+        out = {}
+        for mode in ("eval", "train"):
+            fine, coarse = _ref_models(weights)
+            fine.train(mode == "train")
+            coarse.train(mode == "train")
+            cap = {}
+            h = coarse.pool_1.register_forward_hook(lambda mod, i, o: cap.__setitem__("pool", o))
+            with torch.no_grad():
+                feat, _ = fine([x, None])
+                meta = torch.tensor([[96., 64., 256., 1.]])
+                logits = coarse([x[:, :, 96:160].contiguous(), feat, mask, 0, meta])
+            h.remove()
+            pooled, cdf = cap["pool"]
+            z = ((((cdf - 0.5) * 2) + 1) / 2) * 63
+            out.update({f"{mode}/logits": logits, f"{mode}/cdf": cdf, f"{mode}/bins": torch.floor(z).long(),
+                        f"{mode}/pooled_mean": pooled.mean(dim=(3, 4))})
+            for k, v in feat.items():
+                out[f"{mode}/feat/{k}"] = v[:, :, list(FEAT_FRAMES)]
+            print(weights, mode, "logits", tuple(logits.shape), float(logits.abs().max()), "bins", out[f"{mode}/bins"][0].tolist())
+        save(f"cfg4_{weights}", feat_frames=np.array(FEAT_FRAMES), **out)
+
+
+def gen_cfg2():
+    """cfg 2 shape at B=2 through the unmodified reference fine stream: [2,3,16,224,224] -> [2,157,16], train and eval."""
+    x = synth_tensor((2, 3, 16, 224, 224), seed=402)
+    for weights in ("synth", "shipped"):
+        if weights == "shipped" and shipped("fine_charades_039000_SAVE.pt") is None:
+            continue
+        m = ref_fine.generate_model("M", n_classes=157, task="loc", base_bn_splits=1, dropout=0.0)
+        if weights == "shipped":
+            m.load_state_dict(shipped("fine_charades_039000_SAVE.pt"), strict=True)
+        else:
+            fill_state_dict(m, seed=1)
+        m.eval()
+        with torch.no_grad():
+            out_eval = m([x, None])
+        m.train()
+        xg = x.clone().requires_grad_(True)
+        out = m([xg, None])
+        gout = synth_tensor(tuple(out.shape), seed=403)
+        (out * gout).sum().backward()
+        print(weights, "cfg2 logits", float(out.abs().max()), float(out_eval.abs().max()))
+        save(f"cfg2_{weights}", out_eval=out_eval, out_train=out, dx_sum=xg.grad.sum(dim=(2, 3, 4)))
+
+
+GRAD_KEYS_B4 = ["pool_1.conv1.weight", "pool_1.conv2.weight", "pool_1.conv3.weight", "pool_1.conv3.bias", "rw2.at1.weight",
+                "rw2.fc2.weight", "rw3.fc4.weight", "rw5.at2.weight", "rw6.fc4.weight", "mix2.conv_at.weight",
+                "mix5.conv_at2.weight", "conv1_s.weight", "conv1_t.weight", "layer1.0.conv1.weight", "layer1.0.conv2.weight",
+                "layer1.2.fc1.weight", "layer2.0.conv1.weight", "layer2.0.downsample.0.weight", "layer3.5.conv2.weight",
+                "layer3.10.bn2.weight", "layer4.6.conv3.weight", "layer4.6.bn3.bias", "conv5.weight", "fc2.weight",
+                "fc2.bias"]
+
+
+def gen_coarse_b4():
+    """Whole coarse net at B=4 (BatchNorm over 4 clips: the conditioning of the benchmarked batch), default
+    (kaiming) initialisation scaled through the key-hashed fill, train mode: logits and parameter gradients of the
+    reference in fp32 AND of the oracle restatement in fp64 (the referee of SURVEY 8(a) finding 3)."""
+    B, T, Tf = 4, 8, 12
+    x = synth_tensor((B, 3, T, 224, 224), seed=501)
+    feat = {k: synth_tensor((B, c, Tf, 7, 7), seed=502 + i).abs() for i, (k, c) in enumerate(DEPTH.items())}
+    mask = torch.ones(B, Tf)
+    mask[2, 9:] = 0
+    meta = torch.tensor([[2., 8., 12., 1.], [0., 8., 12., 1.], [4., 8., 12., 1.], [1., 8., 12., 1.]])
+    res = {}
+    m = ref_coarse.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0,
+                                  t_pool="grid", learnedMixing=True, isMixing=True)
+    m.replace_logits(12)
+    m.rw6.dropout.p = 0.0
+    fill_state_dict(m, seed=82)
+    with torch.no_grad():
+        m.pool_1.conv3.weight.mul_(8.0)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.train()
+    out = m([x, feat, mask, 0, meta])
+    gout = synth_tensor(tuple(out.shape), seed=510)
+    (out * gout).sum().backward()
+    params = dict(m.named_parameters())
+    res["f32/out"] = out
+    for k in GRAD_KEYS_B4:
+        res[f"f32/grad/{k}"] = params[k].grad
+    # the referee: the oracle restatement (pinned to the reference by tests/test_oracle.py) evaluated in fp64 -- the
+    # reference module itself cannot run in fp64 (its grids are built with .float(), x3d_coarse.py:396-399)
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import cf_oracle as O
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    p64 = {k: v.clone().requires_grad_(True) for k, v in sd64.items() if v.is_floating_point() and "running" not in k}
+    out64 = O.coarse_forward({**sd64, **p64}, x.double(), {k: v.double() for k, v in feat.items()}, mask.double(),
+                             meta.double(), True)
+    (out64 * gout.double()).sum().backward()
+    res["f64/out"] = out64
+    for k in GRAD_KEYS_B4:
+        res[f"f64/grad/{k}"] = p64[k].grad
+    print("coarse_b4 logits fp32 vs fp64 rel-Linf %.2e" % float((out.double() - out64).abs().max() / out64.abs().max()))
+    e = [float((res[f"f32/grad/{k}"].double() - res[f"f64/grad/{k}"]).abs().max() / res[f"f64/grad/{k}"].abs().max()) for k in GRAD_KEYS_B4]
+    print("coarse_b4: reference fp32 vs fp64 grads rel-Linf: median %.2e max %.2e" % (sorted(e)[len(e) // 2], max(e)))
+    save("coarse_b4", **res)
+
+
+def gen_param_order():
+    """named_parameters() / state_dict() order of the reference modules (what torch.optim.SGD checkpoints index by), and
+    the parameter shapes in the index order of the shipped checkpoints' optimizer_state_dict."""
+    import json
+    out = {}
+    for v in ("M", "XL"):
+        m = ref_fine.generate_model(v, n_classes=157, task="loc", base_bn_splits=1)
+        out[f"fine_{v}"] = {"params": [n for n, _ in m.named_parameters()], "state": list(m.state_dict().keys())}
+        if v == "M":
+            out["fine_M"]["shapes"] = {k: [list(t.shape), str(t.dtype)] for k, t in m.state_dict().items()}
+    m = ref_coarse.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, t_pool="grid",
+                                  learnedMixing=True, isMixing=True)
+    m.replace_logits(157)
+    out["coarse_M"] = {"params": [n for n, _ in m.named_parameters()], "state": list(m.state_dict().keys()),
+                       "shapes": {k: [list(t.shape), str(t.dtype)] for k, t in m.state_dict().items()}}
+    for tag, f in (("fine", "fine_charades_039000_SAVE.pt"), ("coarse", "coarse_fineFEAT_charades_019000_SAVE.pt")):
+        p = os.path.join(REF, "models", f)
+        if os.path.exists(p):
+            osd = torch.load(p, weights_only=False, map_location="cpu")["optimizer_state_dict"]
+            out[f"shipped_{tag}_optimizer"] = {
+                "groups": [{"lr": g["lr"], "n": len(g["params"]), "first": g["params"][0]} for g in osd["param_groups"]],
+                "shapes": {str(i): list(st["momentum_buffer"].shape) for i, st in osd["state"].items()}}
+    with open(os.path.join(HERE, "param_order.json"), "w") as f:
+        json.dump(out, f)
+    print("param_order.json", os.path.getsize(os.path.join(HERE, "param_order.json")) // 1024, "KB")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["interp1d", "gridpool", "gridpool_cfgshape", "gridunpool", "gaussian", "rewight",
-                             "mixing", "bottleneck", "fine_net", "coarse_net", "apmeter", "clip_pipeline", "charades_loader"]
+                             "mixing", "bottleneck", "fine_net", "coarse_net", "apmeter", "clip_pipeline", "charades_loader", "cfg4", "cfg2",
+                             "coarse_b4", "param_order"]
     for w in which:
         globals()["gen_" + w]()

@@ -50,3 +50,17 @@ def test_reference_arm_is_silent_on_other_ranks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_does_not_import_the_product():
+    """`bench.py --impl reference` must run the reference (baseline/_ref, else the oracle port) on the host cores without
+    importing the product package or loading libcfnet_b200.so (the gridpool workload is the quick one)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "gridpool", "--steps", "1",
+                        "--warmup", "1"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["product_imported"] is False and d["value"] > 0
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    ref_fn = src[src.index("def run_reference"):src.index("def main")]
+    assert "import coarse_fine_networks_b200" not in ref_fn and "from coarse_fine_networks_b200" not in ref_fn

@@ -172,6 +172,12 @@ def test_extract_loop_writes_what_the_coarse_loader_reads(env, tmp_path):
     seen = []
 
     class Tower(torch.nn.Module):
+        aggregated = 0
+
+        def aggregate_sub_bn_stats(self):              # extract_fineFEAT.py:138-139: called once, right after train(False)
+            assert not self.training
+            self.aggregated += 1
+
         def forward(self, inp):
             x, masks = inp
             seen.append((tuple(x.shape), self.training, torch.is_grad_enabled()))
@@ -184,6 +190,7 @@ def test_extract_loop_writes_what_the_coarse_loader_reads(env, tmp_path):
     loader = [env.L.mt_collate_fn([dv[i]]) for i in range(2)]
     net = Tower().train()
     n = LC.extract_fine_features(net, loader, str(tmp_path))
+    assert net.aggregated == 1
     assert n == 2 and [s[0][:3] for s in seen] == [(1, 3, 17), (1, 3, 18)] and all(not s[1] and not s[2] for s in seen)
     for vid, t in (("VIDA", 17), ("VIDB", 18)):
         f = LC.load_fine_features(str(tmp_path), ["layer1", "conv5"], vid)

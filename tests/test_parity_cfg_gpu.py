@@ -1,0 +1,266 @@
+"""Parity AT THE BENCHMARKED SHAPES (BASELINE cfg 2 and cfg 4 / 5):
+
+* against committed goldens written by the UNMODIFIED reference on CPU (tests/golden/cfg2_*.npz, cfg4_*.npz,
+  coarse_b4.npz; make_golden.py gen_cfg2 / gen_cfg4 / gen_coarse_b4) -- key-hashed synthetic weights and, when the build
+  container staged them (baseline/_ref/models, git-ignored, travels with the snapshot), the shipped Charades checkpoints;
+* against the reference's own PyTorch path run LIVE on the same GPU (baseline/_ref/*.py, fp32 with TF32 off) at the full
+  cfg 2 ([8,3,16,224,224]) and cfg 4 ([4,3,256,224,224] -> window [96:160] -> Tl=17 -> [4,157,64]) shapes.
+
+Tolerances: logits <= 1e-3 relative L-infinity (north_star); frame-index bins bit-exact given the identical cdf; bins
+from OUR cdf equal wherever the reference's sample point is not within 2e-4 of a frame boundary."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from synth import synth_state_dict, synth_tensor
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+REF_DIR = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+DEPTH = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
+
+
+def load(name):
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    return {k: torch.from_numpy(d[k]) for k in d.files}
+
+
+def relmax(a, b, tol, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= tol * ref + 1e-7, f"{what}: rel-Linf {err / max(ref, 1e-30):.3e} > {tol:.1e}"
+    return err / max(ref, 1e-30)
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import __graft_entry__ as ge
+    ge.build()
+    from coarse_fine_networks_b200 import gridpool_ops, train, x3d_coarse, x3d_fine
+    return type("P", (), dict(T=train, C=x3d_coarse, F=x3d_fine, G=gridpool_ops))
+
+
+def shipped_sd(which):
+    p = os.path.join(REF_DIR, "models", f"{which}_sd.pt")
+    if not os.path.exists(p):
+        pytest.skip(f"{p} not staged (the build container copies it from /root/reference/models)")
+    return torch.load(p, map_location="cpu")
+
+
+def our_models(pk, weights, global_tower=True):
+    fine = pk.F.generate_model("M", n_classes=157, task="loc", base_bn_splits=1, dropout=0.0, global_tower=global_tower)
+    coarse = pk.C.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0,
+                                 t_pool="grid", learnedMixing=True, isMixing=True)
+    coarse.replace_logits(157)
+    coarse.rw6.dropout.p = 0.0
+    if weights == "shipped":
+        fine.load_state_dict(shipped_sd("fine"), strict=True)            # the shipped checkpoints load strict=True
+        coarse.load_state_dict(shipped_sd("coarse"), strict=True)
+    else:
+        fine.load_state_dict(synth_state_dict(fine.state_dict(), 1), strict=True)
+        coarse.load_state_dict(synth_state_dict(coarse.state_dict(), 2), strict=True)
+    return fine.cuda(), coarse.cuda()
+
+
+# ---------------------------------------------------------------------------- cfg 2 vs the committed golden
+@pytest.mark.parametrize("weights", ["synth", "shipped"])
+def test_cfg2_shape_golden(pk, weights):
+    g = load(f"cfg2_{weights}")
+    fine, _ = our_models(pk, weights, global_tower=False)
+    x = synth_tensor((2, 3, 16, 224, 224), seed=402).cuda()
+    fine.eval()
+    with torch.no_grad():
+        relmax(fine([x, None]), g["out_eval"], 1e-3, "eval logits")
+    fine.train()
+    xg = x.clone().requires_grad_(True)
+    out = fine([xg, None])
+    relmax(out, g["out_train"], 1e-3, "train logits")
+    (out * synth_tensor(tuple(out.shape), seed=403).cuda()).sum().backward()
+    relmax(xg.grad.sum(dim=(2, 3, 4)), g["dx_sum"], 5e-2, "dx summed over (T,H,W)")
+
+
+# ---------------------------------------------------------------------------- cfg 4 geometry vs the committed golden
+@pytest.mark.parametrize("weights", ["synth", "shipped"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_cfg4_geometry_golden(pk, weights, mode):
+    g = load(f"cfg4_{weights}")
+    fine, coarse = our_models(pk, weights)
+    fine.train(mode == "train")
+    coarse.train(mode == "train")
+    x = synth_tensor((1, 3, 256, 224, 224), seed=401).cuda()
+    mask = torch.ones(1, 256, device="cuda")
+    cap = {}
+    h = coarse.pool_1.register_forward_hook(lambda m, i, o: cap.__setitem__("pool", o))
+    with torch.no_grad():
+        feat, _ = fine([x, None])
+        logits = pk.T.coarse_fine_forward(fine, coarse, x, 96, 64, mask)
+    h.remove()
+    frames = [int(f) for f in g["feat_frames"]]
+    for k in DEPTH:
+        relmax(feat[k][:, :, frames], g[f"{mode}/feat/{k}"], 1e-3, f"fine feature {k}")
+    pooled, cdf = cap["pool"]
+    gcdf = g[f"{mode}/cdf"]
+    assert float((cdf.cpu() - gcdf).abs().max()) <= 2e-5, "cdf"
+    # bins: bit-exact given the identical cdf ...
+    i0, _ = pk.G.sample_bins(gcdf.cuda(), 64)
+    assert torch.equal(i0.cpu().long(), g[f"{mode}/bins"]), "bins from the reference's cdf"
+    # ... and from our own cdf wherever the reference's sample point is not on a frame boundary
+    z = ((((gcdf.double() - 0.5) * 2) + 1) / 2) * 63
+    safe = (z - z.round()).abs() > 2e-4
+    i0o, _ = pk.G.sample_bins(cdf, 64)
+    assert torch.equal(i0o.cpu().long()[safe], g[f"{mode}/bins"][safe]), "bins from our cdf"
+    relmax(pooled.mean(dim=(3, 4)), g[f"{mode}/pooled_mean"], 1e-3, "Grid Pool output (spatial mean)")
+    assert logits.shape == (1, 157, 64)
+    # eval mode with the key-hashed synthetic running statistics is a 1e10-magnitude, badly scaled net: 5e-3 there
+    relmax(logits, g[f"{mode}/logits"], 5e-3 if (weights, mode) == ("synth", "eval") else 1e-3, "logits")
+
+
+# ---------------------------------------------------------------------------- B=4 gradients, fp64 referee
+def test_coarse_b4_gradients_against_the_fp64_referee(pk):
+    """Whole coarse net, B=4 (the benchmarked per-GPU batch), train-mode BatchNorm: our parameter gradients and the
+    reference's fp32 gradients are both compared with the fp64 referee (oracle restatement in fp64; golden coarse_b4.npz).
+    Bound: per tensor err(ours) <= 3 x err(reference-fp32) (floor 1 %), median over tensors <= 2 x the reference's median."""
+    g = load("coarse_b4")
+    m = pk.C.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0, t_pool="grid",
+                            learnedMixing=True, isMixing=True)
+    m.replace_logits(12)
+    m.rw6.dropout.p = 0.0
+    sd = synth_state_dict(m.state_dict(), 82)
+    sd["pool_1.conv3.weight"] = sd["pool_1.conv3.weight"] * 8.0
+    m.load_state_dict(sd, strict=True)
+    m.cuda().train()
+    B, T, Tf = 4, 8, 12
+    x = synth_tensor((B, 3, T, 224, 224), seed=501).cuda()
+    feat = {k: synth_tensor((B, c, Tf, 7, 7), seed=502 + i).abs().cuda() for i, (k, c) in enumerate(DEPTH.items())}
+    mask = torch.ones(B, Tf)
+    mask[2, 9:] = 0
+    meta = torch.tensor([[2., 8., 12., 1.], [0., 8., 12., 1.], [4., 8., 12., 1.], [1., 8., 12., 1.]]).cuda()
+    out = m([x, feat, mask.cuda(), 0, meta])
+    relmax(out, g["f32/out"], 1e-3, "train logits vs the reference")
+    relmax(out, g["f64/out"].float(), 1e-3, "train logits vs the fp64 referee")
+    (out * synth_tensor(tuple(out.shape), seed=510).cuda()).sum().backward()
+    params = dict(m.named_parameters())
+    rl = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    e_ref, e_new = [], []
+    for k in [k[len("f64/grad/"):] for k in g if k.startswith("f64/grad/")]:
+        g64 = g[f"f64/grad/{k}"]
+        er, en = rl(g[f"f32/grad/{k}"], g64), rl(params[k].grad.detach().cpu(), g64)
+        e_ref.append(er)
+        e_new.append(en)
+        assert en <= max(3.0 * er, 1e-2), f"{k}: ours {en:.3e} vs reference-fp32 {er:.3e} (both against fp64)"
+        cos = torch.nn.functional.cosine_similarity(params[k].grad.detach().cpu().double().flatten(), g64.flatten(), dim=0).item()
+        assert cos >= 0.99, f"{k}: cosine {cos}"
+    e_ref.sort()
+    e_new.sort()
+    n = len(e_new)
+    assert e_new[n // 2] <= 2.0 * e_ref[n // 2], (e_new[n // 2], e_ref[n // 2])
+
+
+# ---------------------------------------------------------------------------- live: the reference's own PyTorch path on this GPU
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(os.path.join(REF_DIR, "x3d_coarse.py")):
+        pytest.skip("baseline/_ref not staged")
+    sys.path.insert(0, REF_DIR)
+    try:
+        mods = {n: importlib.import_module(n) for n in ("x3d_fine", "x3d_coarse")}
+    finally:
+        sys.path.remove(REF_DIR)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return type("R", (), dict(F=mods["x3d_fine"], C=mods["x3d_coarse"]))
+
+
+def ref_models(ref, sd_f, sd_c, global_tower=True):
+    fine = ref.F.generate_model("M", n_classes=157, task="loc", base_bn_splits=1, dropout=0.0, global_tower=global_tower)
+    coarse = ref.C.generate_model("M", n_classes=400, feat_depth=DEPTH, task="loc", base_bn_splits=1, dropout=0.0,
+                                  t_pool="grid", learnedMixing=True, isMixing=True)
+    coarse.replace_logits(157)
+    coarse.rw6.dropout.p = 0.0
+    fine.load_state_dict(sd_f, strict=True)
+    coarse.load_state_dict(sd_c, strict=True)
+    return fine.cuda(), coarse.cuda()
+
+
+def script_loss(logits, labels, masks, align_corners):
+    """train_fine.py:199-212,226 / train_coarse_fineFEAT.py:226-247 with the reference's own torch calls."""
+    import torch.nn.functional as F
+    tl = labels.shape[2]
+    pl = F.interpolate(logits, tl, mode="linear", align_corners=True) if align_corners else F.interpolate(logits, tl, mode="linear")
+    probs = torch.sigmoid(pl) * masks.unsqueeze(1)
+    cls = F.binary_cross_entropy(torch.max(probs, dim=2)[0], torch.max(labels, dim=2)[0], reduction="mean")
+    loc = F.binary_cross_entropy(probs, labels, reduction="sum") / (torch.sum(masks) * labels.shape[1])
+    return (cls + loc) / 2
+
+
+def test_live_reference_cfg2_full_shape(pk, ref):
+    """BASELINE cfg 2: X3D-M fine stream, [8,3,16,224,224], train mode: logits, script loss, input gradient and a spread
+    of parameter gradients against the reference modules running on the same GPU."""
+    fine, _ = our_models(pk, "synth", global_tower=False)
+    sd = {k: v.detach().cpu().clone() for k, v in fine.state_dict().items()}
+    rfine, _ = ref_models(ref, sd, synth_state_dict(our_models(pk, "synth")[1].state_dict(), 2), global_tower=False)
+    x = synth_tensor((8, 3, 16, 224, 224), seed=601).cuda()
+    labels = (torch.rand(8, 157, 160, generator=torch.Generator().manual_seed(602)) < 0.05).float().cuda()
+    masks = torch.ones(8, 160, device="cuda")
+    fine.train()
+    rfine.train()
+    xo, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    out = fine([xo, None])
+    rout = rfine([xr, None])
+    relmax(out, rout, 1e-3, "cfg2 train logits (B=8)")
+    loss, _ = pk.T.charades_loss(out, labels, masks)
+    rloss = script_loss(rout, labels, masks, True)
+    assert abs(loss.item() - rloss.item()) <= 1e-4 * abs(rloss.item()), (loss.item(), rloss.item())
+    loss.backward()
+    rloss.backward()
+    relmax(xo.grad.sum(dim=(2, 3, 4)), xr.grad.sum(dim=(2, 3, 4)), 5e-2, "dx summed over (T,H,W)")
+    rp = dict(rfine.named_parameters())
+    coss = []
+    for k, p in fine.named_parameters():
+        a, b = p.grad.detach().flatten().double(), rp[k].grad.detach().flatten().double()
+        if float(b.abs().max()) == 0.0:
+            continue
+        coss.append(float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-300)))
+    coss.sort()
+    assert coss[len(coss) // 2] >= 0.9999 and coss[len(coss) // 20] >= 0.995, (coss[:5], coss[len(coss) // 2])
+
+
+@pytest.mark.parametrize("weights", ["synth", "shipped"])
+def test_live_reference_cfg4_full_shape(pk, ref, weights):
+    """BASELINE cfg 4 at the benchmarked batch: fine global tower on [4,3,256,224,224] -> coarse on the window [96:160],
+    meta = [96,64,256,1] -> Tl=17 -> logits [4,157,64], train-mode BatchNorm, through train.coarse_fine_forward, against the
+    reference modules (fine -> features -> coarse, extract_fineFEAT.py:168 / train_coarse_fineFEAT.py:217) on the same GPU."""
+    fine, coarse = our_models(pk, weights)
+    sd_f = {k: v.detach().cpu().clone() for k, v in fine.state_dict().items()}
+    sd_c = {k: v.detach().cpu().clone() for k, v in coarse.state_dict().items()}
+    rfine, rcoarse = ref_models(ref, sd_f, sd_c)
+    B = 4
+    x = synth_tensor((B, 3, 256, 224, 224), seed=611).cuda()
+    mask = torch.ones(B, 256, device="cuda")
+    meta = torch.tensor([[96., 64., 256., 1.]]).repeat(B, 1).cuda()
+    for m in (fine, coarse, rfine, rcoarse):
+        m.train()
+    cap, rcap = {}, {}
+    h1 = coarse.pool_1.register_forward_hook(lambda m, i, o: cap.__setitem__("pool", o))
+    h2 = rcoarse.pool_1.register_forward_hook(lambda m, i, o: rcap.__setitem__("pool", o))
+    with torch.no_grad():
+        logits = pk.T.coarse_fine_forward(fine, coarse, x, 96, 64, mask)
+        rfeat, _ = rfine([x, None])
+        rlogits = rcoarse([x[:, :, 96:160].contiguous(), rfeat, mask, 0, meta])
+    h1.remove()
+    h2.remove()
+    assert logits.shape == rlogits.shape == (B, 157, 64)
+    relmax(logits, rlogits, 1e-3, "cfg4 train logits (B=4)")
+    cdf, rcdf = cap["pool"][1], rcap["pool"][1]
+    assert float((cdf - rcdf).abs().max()) <= 2e-5
+    i0, _ = pk.G.sample_bins(rcdf, 64)
+    z = ((((rcdf - 0.5) * 2) + 1) / 2) * 63
+    assert torch.equal(i0.long(), torch.floor(z).long()), "bins bit-exact given the reference's cdf"
+    relmax(cap["pool"][0], rcap["pool"][0], 1e-3, "Grid Pool output")

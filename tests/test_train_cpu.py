@@ -140,3 +140,47 @@ def test_optimizer_checkpoint_round_trip_with_torch_sgd():
     fresh.flat_v.fill_(7.0)
     fresh.load_state_dict(torch_sgd(_model()).state_dict())
     assert all(float(fresh._momentum_view(i).abs().sum()) == 0.0 for i in range(len(fresh.params)))   # (alignment gaps are not parameters)
+
+
+def _golden_order():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "param_order.json")))
+
+
+def test_parameter_and_state_dict_order_match_the_reference():
+    """named_parameters() order is what torch.optim.SGD checkpoints index by (train_coarse_fineFEAT.py:137-145): it has
+    to equal the reference's for fine M / XL and for the coarse net (fixture written by make_golden.py:gen_param_order
+    from the unmodified reference)."""
+    from coarse_fine_networks_b200 import x3d_coarse, x3d_fine
+    gold = _golden_order()
+    for v in ("M", "XL"):
+        m = x3d_fine.generate_model(v, n_classes=157, task="loc", base_bn_splits=1)
+        assert [n for n, _ in m.named_parameters()] == gold[f"fine_{v}"]["params"], v
+        assert list(m.state_dict().keys()) == gold[f"fine_{v}"]["state"], v
+    depth = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
+    m = x3d_coarse.generate_model("M", n_classes=400, feat_depth=depth, task="loc", base_bn_splits=1, t_pool="grid",
+                                  learnedMixing=True, isMixing=True)
+    m.replace_logits(157)
+    assert [n for n, _ in m.named_parameters()] == gold["coarse_M"]["params"]
+    assert list(m.state_dict().keys()) == gold["coarse_M"]["state"]
+
+
+def test_flat_trainer_indices_line_up_with_the_shipped_optimizer_checkpoints():
+    """FlatTrainer's parameter index i (base group in named_parameters() order, then the 'rw'/'mix' group) must carry the
+    shape of momentum buffer i of the shipped optimizer_state_dict, for both streams -- resuming maps by position."""
+    from coarse_fine_networks_b200 import train, x3d_coarse, x3d_fine
+    gold = _golden_order()
+    depth = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
+    fine = x3d_fine.generate_model("M", n_classes=157, task="loc", base_bn_splits=1)
+    coarse = x3d_coarse.generate_model("M", n_classes=400, feat_depth=depth, task="loc", base_bn_splits=1, t_pool="grid",
+                                       learnedMixing=True, isMixing=True)
+    coarse.replace_logits(157)
+    for tag, net in (("fine", fine), ("coarse", coarse)):
+        if f"shipped_{tag}_optimizer" not in gold:
+            continue
+        o = gold[f"shipped_{tag}_optimizer"]
+        tr = train.FlatTrainer([net], lr=0.01)
+        assert len(tr.params) == sum(g["n"] for g in o["groups"])
+        assert tr._n_base == o["groups"][0]["n"]
+        for i, p in enumerate(tr.params):
+            assert list(p.shape) == o["shapes"][str(i)], (tag, i, tr.names[i])

@@ -19,18 +19,20 @@ def pk():
     return type("P", (), dict(T=train, C=x3d_coarse, F=x3d_fine))
 
 
-def ref_loss(logits, labels, masks):
-    """train_fine.py:199-212,226 restated with the same torch calls."""
+def ref_loss(logits, labels, masks, align_corners=True):
+    """train_fine.py:199-212,226 (align_corners=True) / train_coarse_fineFEAT.py:226-247 (F.interpolate's default grid)
+    restated with the same torch calls."""
     tl = labels.shape[2]
-    pl = F.interpolate(logits, tl, mode="linear", align_corners=True)
+    pl = F.interpolate(logits, tl, mode="linear", align_corners=True) if align_corners else F.interpolate(logits, tl, mode="linear")
     probs = torch.sigmoid(pl) * masks.unsqueeze(1)
     cls = F.binary_cross_entropy(torch.max(probs, dim=2)[0], torch.max(labels, dim=2)[0], reduction="mean")
     loc = F.binary_cross_entropy(probs, labels, reduction="sum") / (torch.sum(masks) * labels.shape[1])
     return (cls + loc) / 2, cls, loc
 
 
-@pytest.mark.parametrize("B,C,T,TL", [(2, 7, 16, 160), (3, 157, 64, 640), (1, 5, 8, 8)])
-def test_charades_loss_vs_torch(pk, B, C, T, TL):
+@pytest.mark.parametrize("align", [True, False])
+@pytest.mark.parametrize("B,C,T,TL", [(2, 7, 16, 160), (3, 157, 64, 640), (1, 5, 8, 8), (2, 9, 64, 37)])
+def test_charades_loss_vs_torch(pk, B, C, T, TL, align):
     g = torch.Generator().manual_seed(B * 100 + T)
     logits = (torch.randn(B, C, T, generator=g) * 2).cuda()
     labels = (torch.rand(B, C, TL, generator=g) < 0.05).float().cuda()
@@ -38,11 +40,14 @@ def test_charades_loss_vs_torch(pk, B, C, T, TL):
     masks[0, TL - TL // 4:] = 0
     labels = labels * masks.unsqueeze(1)
     a = logits.clone().requires_grad_(True)
-    loss, parts = pk.T.charades_loss(a, labels, masks)
+    loss, parts = pk.T.charades_loss(a, labels, masks, align_corners=align)
     (loss * 3.0).backward()
     b = logits.clone().requires_grad_(True)
-    rl, rc, rloc = ref_loss(b, labels, masks)
+    rl, rc, rloc = ref_loss(b, labels, masks, align)
     (rl * 3.0).backward()
+    if not align:
+        l2, _ = pk.T.coarse_charades_loss(logits, labels, masks)
+        assert abs(l2.item() - rl.item()) <= 1e-5 * abs(rl.item()) + 1e-7
     assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item()) + 1e-7
     assert abs(parts[0].item() - rc.item()) <= 1e-5 * abs(rc.item()) + 1e-7
     assert abs(parts[1].item() - rloc.item()) <= 1e-5 * abs(rloc.item()) + 1e-7
