@@ -20,8 +20,9 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
 
 
-def _digest(path):
+def _digest(path, extra=()):
     h = hashlib.sha1()
+    h.update(" ".join(extra).encode())
     for f in [path] + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "cfnet_b200.h")]:
         with open(f, "rb") as fh:
             h.update(fh.read())
@@ -29,13 +30,13 @@ def _digest(path):
     return h.hexdigest()
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+def _compile(src, verbose, obj_dir=OBJ_DIR, extra=()):
+    obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
     stamp = obj + ".sha1"
-    dig = _digest(src)
+    dig = _digest(src, extra)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -46,22 +47,27 @@ def _compile(src, verbose):
     return obj, True
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build(force=False, verbose=False, ab=False):
+    """ab=True builds libcfnet_b200_ab.so with -DCFNET_AB: the same library with its experiment switches (environment
+    variables) compiled in -- select it with CFNET_LIB=<path> for same-box A/B runs; the shipped library reads no environment."""
+    obj_dir = OBJ_DIR + ("_ab" if ab else "")
+    lib = LIB.replace(".so", "_ab.so") if ab else LIB
+    extra = ("-DCFNET_AB",) if ab else ()
+    os.makedirs(obj_dir, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     if force:
-        for f in glob.glob(os.path.join(OBJ_DIR, "*.sha1")):
+        for f in glob.glob(os.path.join(obj_dir, "*.sha1")):
             os.remove(f)
     with ThreadPoolExecutor(max_workers=8) as ex:
-        res = list(ex.map(lambda s: _compile(s, verbose), srcs))
+        res = list(ex.map(lambda s: _compile(s, verbose, obj_dir, extra), srcs))
     objs = [o for o, _ in res]
-    if any(ch for _, ch in res) or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    if any(ch for _, ch in res) or not os.path.exists(lib):
+        cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ab="--ab" in sys.argv))

@@ -26,12 +26,15 @@
 #include "cf_common.cuh"
 #include "../../include/cfnet_b200.h"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 #define P2_A_STAGE (2 * TC_BM * TC_KC * 4) /* hi + lo: 32 KB */
 #define P2_CS_LD 36
 #define P2_CS_FLOATS (TC_BM * P2_CS_LD)
 #define P2_MAX_STAGES 4
+#define P2_MAX_RAW 8
 #define P2_RED_N 512
 #define P2_NT_MAX 224
 #define P2_SMEM_MAX (210 * 1024) /* dynamic; + ~16.5 KB static (statistics table) stays under the 227 KB per-CTA limit */
@@ -58,25 +61,19 @@ struct P2Params {
     long long g_sample_stride;
     uint32_t tmem_cols, b_chunk_bytes, stage_bytes;
     long long total_tiles;
+    // TMA-fed producers: raw activation tiles land in a ring of nraw stages (raw_stage_bytes each = raw_in_bytes per input
+    // tensor) at raw_off from the 1024-aligned base; fold = rows presented as one TMA row (tma_host.cuh)
+    int tma, fold, nraw;
+    uint32_t raw_in_bytes, raw_stage_bytes, raw_off;
 };
 
-// ---- role split A: 8 producer warps
+// ---- role split: 8 producer warps (the 16-warp split of round 1 lost every same-box A/B and is gone)
 #define P2_NS p2w8
 #define P2_PROD_WARPS 8
 #define P2_REGS_PROD 120
 #define P2_REGS_MMA 32
 #define P2_REGS_EPI 104
 #define P2_PROD_INC 1                  /* producers raise their register count (launch: 640 threads x 96) */
-#include "x3d_pw_tc2_roles.cuh"
-#include "x3d_pw_tc2_kernel.cuh"
-#include "x3d_pw_tc2_unroles.cuh"
-// ---- role split B: 16 producer warps
-#define P2_NS p2w16
-#define P2_PROD_WARPS 16
-#define P2_REGS_PROD 72
-#define P2_REGS_MMA 24
-#define P2_REGS_EPI 96
-#define P2_PROD_INC 0                  /* producers keep the launch count (896 threads x 72) */
 #include "x3d_pw_tc2_roles.cuh"
 #include "x3d_pw_tc2_kernel.cuh"
 #include "x3d_pw_tc2_unroles.cuh"
@@ -130,16 +127,16 @@ static int p2_sm_count() {
     return n;
 }
 
-static int p2_timing() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("CFNET_PW_TC_TIMING");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v;
+#ifdef CFNET_AB          /* A/B switches are compiled in only for experiments (-DCFNET_AB); the shipped library reads no environment */
+static int p2_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
+#else
+static int p2_env(const char*, int dflt) { return dflt; }
+#endif
 
-// debug: cycle counters of CTA 0 of the last persistent launch run with CFNET_PW_TC_TIMING=1 (16 values; see P2_ACC slots)
+// debug: cycle counters of CTA 0 of the last persistent launch (built with -DCFNET_P2_TIMING -DCFNET_AB, CFNET_PW_TC_TIMING=1)
 extern "C" int cf_pw_tc_debug_read(long long* out16) {
     long long zero[32] = {0};
     if (cudaMemcpyFromSymbol(out16, p2_dbg, 24 * sizeof(long long)) != cudaSuccess) return CF_ERR_CUDA;
@@ -147,18 +144,8 @@ extern "C" int cf_pw_tc_debug_read(long long* out16) {
     return CF_OK;
 }
 
-static bool p2_use_v1() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("CFNET_PW_TC_V1");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
-
 // called by cf_pw_conv (x3d_pw.cu) for dense problems when the caller supplied a weight-pack workspace
 int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
-    if (p2_use_v1()) return (a->gather_in || a->scatter_out) ? -1 : cf_pw_conv_tc_v1(a, stream);
     const int K = a->K, N = a->N;
     P2Params p;
     p2_tiling(K, N, p);
@@ -187,8 +174,33 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     p.g_sample_stride = a->g.sample_stride;
     if (av == 1 || ev == 1 || (a->accumulate && p.gmode != 2) || (a->stats_mode != CF_STATS_NONE && N > P2_RED_N))
         return p.gmode ? -1 : cf_pw_conv_tc_v1(a, stream);      // (-1: the caller falls back to the CUDA-core gather kernel)
-    // shared-memory plan: weights resident next to >= 3 A stages, else streamed with each stage; if even two stages
-    // of the widest channel tile do not fit (very long K: big prologue tables), narrow the channel tile
+
+    // ---- TMA-fed producers: dense rows (gathered rows keep the register-load producers), describable by a tensor map
+    const bool x2 = a->pro_mode == CF_PRO_AFFINE2;
+    CUtensorMap tmx, tmx2;
+    memset(&tmx, 0, sizeof(tmx));
+    memset(&tmx2, 0, sizeof(tmx2));
+    p.tma = 0; p.fold = 1; p.nraw = 0; p.raw_in_bytes = p.raw_stage_bytes = p.raw_off = 0;
+    if (p.gmode == 0 && p2_env("CFNET_P2_TMA", 1)) {
+        const int fold = (K % 4 == 0) ? 1 : ((K % 2 == 0) ? 2 : 4);
+        if ((fold == 1 || K <= 64) && cf_make_row_tmap(&tmx, a->x, a->B, p.R, K, fold) &&
+            (!x2 || cf_make_row_tmap(&tmx2, a->x2, a->B, p.R, K, fold))) {
+            p.tma = 1;
+            p.fold = fold;
+            p.raw_in_bytes = fold == 1 ? (uint32_t)(TC_BM * TC_KC * 4) : (uint32_t)(((size_t)TC_BM * K * 4 + 127) / 128 * 128);
+            p.raw_stage_bytes = p.raw_in_bytes * (x2 ? 2u : 1u);
+        }
+    }
+
+    // shared-memory plan.  Register-load producers (round 1): weights resident next to >= 3 A stages when they fit, else
+    // streamed with each stage (>= 2 stages); if even that does not fit (very long K), narrow the channel tile.
+    // TMA-fed producers: the operand stages only decouple producers from the MMA issuer (2-3 are enough) and the rest of the
+    // budget is raw stages (= bytes in flight); taken when the weights stay resident and >= 3 raw stages (2 for one input
+    // tensor) fit -- a second input (BatchNorm-backward prologue) doubles the raw stage and usually does not.
+    // Keep some L1 when the epilogue moves 8-byte vectors (N % 4 != 0): the unified L1/shared array is carved in steps
+    // (... 164, 196, 228 KB); above 196 KB per CTA (dynamic + 16.5 KB static + 1 KB reserved) no L1 is left and those
+    // loads / stores (two per 32-byte sector) go to L2 twice: measured -18 % .. -43 % on the layer-1 shapes.
+    const size_t l1_friendly = 196 * 1024 - 1024 - 17 * 1024;
     size_t smem = 0;
     static const int nt_try[] = {P2_NT_MAX, 160, 128, 96, 64, 32};
     bool planned = false;
@@ -197,11 +209,32 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
             p2_tiling(K, N, p, nt_try[ti]);
             p.total_tiles = (long long)a->B * p.tps * p.ntiles;
         }
-        const size_t fixed = 1024 + 2 * (size_t)P2_CS_FLOATS * 4 + 3 * (size_t)p.KP * 4;
+        const size_t fixed = 1024 + 2 * (size_t)P2_CS_FLOATS * 4 + 3 * (size_t)p.KP * 4 + 128;
         if (fixed + 2 * (size_t)P2_A_STAGE >= P2_SMEM_MAX) break;
         const size_t avail = P2_SMEM_MAX - fixed;
         const size_t wres_bytes = (size_t)p.nchunks * p.b_chunk_bytes;
         p.resident = (p.ntiles == 1 && wres_bytes + 3 * (size_t)P2_A_STAGE <= avail) ? 1 : 0;
+        if (p.tma && p.resident) {
+            const size_t cap = ev == 4 ? (size_t)P2_SMEM_MAX : l1_friendly;
+            const int raw_need = x2 ? 3 : 2;
+            size_t used = fixed + wres_bytes + 2 * (size_t)P2_A_STAGE;
+            if (used + raw_need * (size_t)p.raw_stage_bytes <= cap) {
+                p.stage_bytes = P2_A_STAGE;
+                p.nstages = 2;
+                if (used + P2_A_STAGE + 4 * (size_t)p.raw_stage_bytes <= cap) {      // room for a third operand stage
+                    p.nstages = 3;
+                    used += P2_A_STAGE;
+                }
+                p.nraw = (int)((cap - used) / p.raw_stage_bytes);
+                if (p.nraw > P2_MAX_RAW) p.nraw = P2_MAX_RAW;
+                p.raw_off = (uint32_t)((used - 1024 - 128 + 127) / 128 * 128);   // content ends 128 B (the slack in `fixed`) before `used`
+                smem = 1024 + p.raw_off + (size_t)p.nraw * p.raw_stage_bytes;
+                planned = true;
+                break;
+            }
+        }
+        p.tma = 0;
+        p.nraw = 0;
         if (p.resident) {
             p.stage_bytes = P2_A_STAGE;
             p.nstages = (int)((avail - wres_bytes) / P2_A_STAGE);
@@ -217,21 +250,15 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
                 planned = true;
             }
         }
-    }
-    CF_CHECK_ARG(planned, "K too large for the tensor-core path");
-    // Keep some L1: the unified L1/shared array is carved in steps (... 164, 196, 228 KB).  Above 196 KB per CTA (dynamic +
-    // 16.5 KB static + 1 KB reserved) no L1 is left and the 8-byte loads / stores of the 54-channel layers (two per
-    // 32-byte sector) go to L2 twice: measured -18 % .. -43 % on the layer-1 shapes.  A ring stage is worth less.
-    {
-        static int l1cap = -1;                                       // CFNET_P2_L1CAP=0: A/B switch
-        if (l1cap < 0) { const char* e = getenv("CFNET_P2_L1CAP"); l1cap = e ? atoi(e) : 1; }
-        const size_t l1_friendly = l1cap == 2 ? 164 * 1024 - 1024 - 17 * 1024 : (l1cap ? 196 * 1024 - 1024 - 17 * 1024 : (size_t)P2_SMEM_MAX);
-        const int min_stages = (p.resident && l1cap != 2) ? 3 : 2;
-        while (smem > l1_friendly && p.nstages > min_stages) {
-            --p.nstages;
-            smem -= p.stage_bytes;
+        if (planned) {
+            const int min_stages = p.resident ? 3 : 2;
+            while (smem > l1_friendly && p.nstages > min_stages) {
+                --p.nstages;
+                smem -= p.stage_bytes;
+            }
         }
     }
+    CF_CHECK_ARG(planned, "K too large for the tensor-core path");
     CF_CHECK_ARG(a->wpack_bytes >= (int64_t)((size_t)p.ntiles * p.nchunks * p.b_chunk_bytes), "weight-pack workspace too small");
     CF_CHECK_ARG(p.total_tiles < (1LL << 31), "too many tiles");
     p.acc_stride = (p.NTp + 31) / 32 * 32;
@@ -241,7 +268,6 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     static CfOncePerDevice attr_done;
     if (attr_done.need()) {
         cudaError_t e = cudaFuncSetAttribute(p2w8::pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(p2w16::pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
         if (e != cudaSuccess) {
             cf_set_error("cf_pw_conv_tc: cannot opt in to %d B of shared memory: %s", P2_SMEM_MAX, cudaGetErrorString(e));
             return CF_ERR_CUDA;
@@ -249,23 +275,11 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
         attr_done.mark();
     }
     long long grid = p.total_tiles < p2_sm_count() ? p.total_tiles : p2_sm_count();
-    p.timing = p2_timing();
-    {
-        static int one = -1;
-        if (one < 0) { const char* e = getenv("CFNET_PW_TC_1X"); one = (e && e[0] == '1') ? 1 : 0; }
-        p.dbg_1x = one;
-    }
+    p.timing = p2_env("CFNET_PW_TC_TIMING", 0);
+    p.dbg_1x = p2_env("CFNET_PW_TC_1X", 0);
     p.g_j = (int)(grid % p.ntiles);
     p.g_rt = (int)(grid / p.ntiles);
-    // Role split.  Same-box A/B runs (gpurun_out/s25_ab*.log; boxes of this pool differ by 10-25 %, so only runs inside one
-    // call compare): 8 producer warps (120 / 32 / 104 registers) win or tie on every shape of the step except the Swish
-    // prologues with K = 54 and K = 216 (16 producer warps 6 % faster there, 10-20 % slower on the BatchNorm-backward
-    // prologues: their 72-register producers spill).  Default: 8; CFNET_PW_TC_PROD=16 selects the other split.
-    static int force_pw = -1;
-    if (force_pw < 0) { const char* e = getenv("CFNET_PW_TC_PROD"); force_pw = e ? atoi(e) : 0; }
-    const bool few_producers = force_pw != 16;
-    if (few_producers) p2w8::pw_tc2_kernel<<<(unsigned)grid, (8 + 4 + 8) * 32, smem, stream>>>(*a, a->wpack, p, av, ev);
-    else p2w16::pw_tc2_kernel<<<(unsigned)grid, (16 + 4 + 8) * 32, smem, stream>>>(*a, a->wpack, p, av, ev);
+    p2w8::pw_tc2_kernel<<<(unsigned)grid, (8 + 4 + 8) * 32, smem, stream>>>(*a, a->wpack, p, av, ev, tmx, tmx2);
     CF_COUNT_LAUNCH(2);
     CF_CHECK_LAUNCH();
     return CF_OK;

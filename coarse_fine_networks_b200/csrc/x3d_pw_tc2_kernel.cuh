@@ -1,8 +1,5 @@
-// Device code of the persistent tcgen05 pointwise GEMM (x3d_pw_tc2.cu).  Included twice with different role splits:
-//   P2_NS = p2w8  :  8 producer warps (4 rows per thread and chunk), register budgets 120 / 32 / 104, 640 threads
-//   P2_NS = p2w16 : 16 producer warps (2 rows per thread and chunk), register budgets  72 / 24 /  96, 896 threads
-// The epilogue is the critical role when N > K with a cheap prologue (8 producer warps leave it more registers and
-// issue slots), the producers are when K >= N or the prologue is Swish / BatchNorm-backward (16 warps hide their latency).
+// Device code of the persistent tcgen05 pointwise GEMM (x3d_pw_tc2.cu): 8 producer warps (4 rows per thread and chunk),
+// one MMA-issuer warp + one TMA-loader lane in the same warpgroup, 8 epilogue warps; register budgets 120 / 32 / 104.
 namespace P2_NS {
 
 // sigmoid from ex2.approx / rcp.approx (2^-22 relative: at the 3xTF32 level, far inside the 1e-3 parity bar): 5 issue
@@ -252,6 +249,143 @@ __device__ __forceinline__ void p2_producer(const cf_pw_args& a, const P2Params&
         p2_dbg[7] = clock64() - tstart;
     }
 #endif
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA-fed producers.  One loader lane (in the MMA warpgroup) walks the same item list and keeps p.nraw raw activation
+// tiles in flight with cp.async.bulk.tensor (tensor maps of cf_make_row_tmap): the loads no longer live in producer
+// registers, so their latency is hidden by the depth of the raw ring instead of by 2-4 register sets per thread.  The
+// producers read a landed tile from shared memory, hand the raw stage straight back, and then do what they did before:
+// prologue -> hi/lo TF32 split -> SWIZZLE_128B operand stage.
+//   FOLD == 1: a raw stage is one [128 rows][32 floats] k-chunk (pitch 128 B);
+//   FOLD  > 1: (K not a multiple of 4, K <= 64) a raw stage is the whole [128 rows][K] tile (pitch K*4 B), read chunk by chunk.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void p2_loader(const cf_pw_args& a, const P2Params& p, uint8_t* raw, uint64_t* rfull, uint64_t* rempty,
+                                          const CUtensorMap* tmx, const CUtensorMap* tmx2) {
+    const bool x2 = a.pro_mode == CF_PRO_AFFINE2;
+    const uint32_t bytes = p.raw_in_bytes * (x2 ? 2u : 1u);
+    tma_prefetch_desc(tmx);
+    if (x2) tma_prefetch_desc(tmx2);
+    int rs = 0;
+    uint32_t rph = 0;
+    P2Item it;
+    for (p2_first(it, p); it.valid; p2_advance(it, p)) {
+        if (p.fold != 1 && it.c != 0) continue;
+        mbar_wait_b(&rempty[rs], rph ^ 1u);                  // every producer warp has read this raw stage
+        uint8_t* dst = raw + (size_t)rs * p.raw_stage_bytes;
+        mbar_expect_tx(&rfull[rs], bytes);
+        const int c0 = p.fold == 1 ? it.c * TC_KC : 0, c1 = it.r0 / p.fold;
+        tma_load_3d(dst, tmx, c0, c1, it.b, &rfull[rs]);
+        if (x2) tma_load_3d(dst + p.raw_in_bytes, tmx2, c0, c1, it.b, &rfull[rs]);
+        if (++rs == p.nraw) { rs = 0; rph ^= 1u; }
+    }
+}
+
+template <int FOLD>
+__device__ __forceinline__ void p2_raw_read(const uint8_t* rx, int row, int q, int k, int K, float* v) {
+    if (FOLD == 1) {
+        const float4 t = *reinterpret_cast<const float4*>(rx + row * 128 + q * 16);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if (FOLD == 2) {
+        const float* src = reinterpret_cast<const float*>(rx) + row * K + k;
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+            if (k + e < K) {
+                const float2 t = *reinterpret_cast<const float2*>(src + e);
+                v[e] = t.x; v[e + 1] = t.y;
+            } else {
+                v[e] = 0.f; v[e + 1] = 0.f;
+            }
+        }
+    } else {
+        const float* src = reinterpret_cast<const float*>(rx) + row * K + k;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (k + e < K) ? src[e] : 0.f;
+    }
+}
+
+template <int FOLD, int PRO>
+__device__ __forceinline__ void p2_producer_tma(const cf_pw_args& a, const P2Params& p, uint8_t* stages, float* tab, uint64_t* full,
+                                                uint64_t* empty, uint64_t* rfull, uint64_t* rempty, const uint8_t* raw,
+                                                const float* __restrict__ pack, int tid) {
+    constexpr bool X2 = PRO == CF_PRO_AFFINE2;
+    const int lane = tid & 31;
+    const int q = tid & 7, rr = tid >> 3;
+    const int K = a.K;
+    P2Item pr;
+    p2_first(pr, p);
+    int cur_b = -1, s = 0, rs = 0;
+    uint32_t ph = 0, rph = 0;
+    while (pr.valid) {
+        if (PRO != CF_PRO_NONE && pr.c == 0 && pr.b != cur_b) {  // prologue tables of this tile's sample
+            named_bar_sync(1, P2_PROD_THREADS);
+            for (int t = tid; t < p.KP; t += P2_PROD_THREADS) {
+                const bool kv = t < K;
+                tab[t] = kv ? a.pro_a[(size_t)pr.b * K + t] : 0.f;
+                tab[p.KP + t] = (kv && a.pro_b) ? a.pro_b[(size_t)pr.b * K + t] : 0.f;
+                tab[2 * p.KP + t] = (kv && a.pro_c) ? a.pro_c[(size_t)pr.b * K + t] : 0.f;
+            }
+            named_bar_sync(1, P2_PROD_THREADS);
+            cur_b = pr.b;
+        }
+        if (FOLD == 1 || pr.c == 0) mbar_wait_b(&rfull[rs], rph);        // the raw tile has landed
+        const uint8_t* rx = raw + (size_t)rs * p.raw_stage_bytes;
+        const int k = pr.c * TC_KC + q * 4;
+        float v[P2_PROD_PASSES][4], v2[X2 ? P2_PROD_PASSES : 1][4];
+#pragma unroll
+        for (int pp = 0; pp < P2_PROD_PASSES; ++pp) {
+            const int row = pp * (P2_PROD_WARPS * 4) + rr;
+            p2_raw_read<FOLD>(rx, row, q, k, K, v[pp]);
+            if (X2) p2_raw_read<FOLD>(rx + p.raw_in_bytes, row, q, k, K, v2[X2 ? pp : 0]);
+        }
+        if (FOLD == 1 || pr.c == p.nchunks - 1) {                        // values are in registers: give the raw stage back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rempty[rs]);
+            if (++rs == p.nraw) { rs = 0; rph ^= 1u; }
+        }
+        mbar_wait_b(&empty[s], ph ^ 1u);
+        uint8_t* stage = stages + (size_t)s * p.stage_bytes;
+        if (!p.resident && tid == 0) {
+            mbar_expect_tx(&full[s], p.b_chunk_bytes);
+            bulk_g2s(stage + P2_A_STAGE, pack + ((size_t)pr.j * p.nchunks + pr.c) * (p.b_chunk_bytes / 4), p.b_chunk_bytes, &full[s]);
+        }
+        float pa[4], pb[4], pc[4];
+        if (PRO != CF_PRO_NONE) {
+            const float4 ta = *reinterpret_cast<const float4*>(tab + k);
+            const float4 tb = *reinterpret_cast<const float4*>(tab + p.KP + k);
+            pa[0] = ta.x; pa[1] = ta.y; pa[2] = ta.z; pa[3] = ta.w;
+            pb[0] = tb.x; pb[1] = tb.y; pb[2] = tb.z; pb[3] = tb.w;
+            if (X2) {
+                const float4 tc = *reinterpret_cast<const float4*>(tab + 2 * p.KP + k);
+                pc[0] = tc.x; pc[1] = tc.y; pc[2] = tc.z; pc[3] = tc.w;
+            }
+        }
+        const int rows_valid = min(TC_BM, p.R - pr.r0);
+        uint8_t* a_hi = stage;
+        uint8_t* a_lo = stage + TC_BM * TC_KC * 4;
+#pragma unroll
+        for (int pp = 0; pp < P2_PROD_PASSES; ++pp) {
+            const int row = pp * (P2_PROD_WARPS * 4) + rr;
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float t = v[pp][e];
+                if (PRO != CF_PRO_NONE) {
+                    t = p2_pro<PRO>(t, X2 ? v2[X2 ? pp : 0][e] : 0.f, pa[e], pb[e], X2 ? pc[e] : 0.f);
+                    if (row >= rows_valid) t = 0.f;
+                }
+                tf32_split(t, hi[e], lo[e]);
+            }
+            const uint32_t off = sw128_off(row, q);
+            *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (++s == p.nstages) { s = 0; ph ^= 1u; }
+        p2_advance(pr, p);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -551,13 +685,16 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
 // kernel
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args a, const float* __restrict__ pack, const P2Params p,
-                                                               int av, int ev) {
+                                                               int av, int ev, const __grid_constant__ CUtensorMap tmx,
+                                                               const __grid_constant__ CUtensorMap tmx2) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full[P2_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty[P2_MAX_STAGES];
     __shared__ __align__(8) uint64_t tfull[2];
     __shared__ __align__(8) uint64_t tempty[2];
     __shared__ __align__(8) uint64_t wres_bar;
+    __shared__ __align__(8) uint64_t rfull[P2_MAX_RAW];
+    __shared__ __align__(8) uint64_t rempty[P2_MAX_RAW];
     __shared__ uint32_t tmem_addr_s;
     __shared__ float red[4 * 2 * P2_RED_N];                          // [epilogue warp in group][sum, sum2][channel]
 
@@ -566,6 +703,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
     uint8_t* wres = stages + (size_t)p.nstages * p.stage_bytes;
     float* Cs = reinterpret_cast<float*>(wres + (p.resident ? (size_t)p.nchunks * p.b_chunk_bytes : 0));
     float* tab = Cs + 2 * P2_CS_FLOATS;
+    uint8_t* raw = base + p.raw_off;                                                  // TMA landing ring (128-B aligned)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -581,6 +719,10 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
         mbar_init(&tempty[0], P2_EPI_WARPS); mbar_init(&tempty[1], P2_EPI_WARPS);
         mbar_init(&wres_bar, 1);
+        for (int s = 0; s < p.nraw; ++s) {
+            mbar_init(&rfull[s], 1);                                    // the loader's expect_tx arrival
+            mbar_init(&rempty[s], P2_PROD_WARPS);
+        }
         fence_mbar_init();
     }
     for (int i = tid; i < 4 * 2 * P2_RED_N; i += P2_THREADS) red[i] = 0.f;
@@ -608,13 +750,27 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
         case CF_PRO_AFFINE2: p2_producer<AV_, CF_PRO_AFFINE2>(P2_PARGS); break;  \
         default: p2_producer<AV_, CF_PRO_NONE>(P2_PARGS); break;                 \
     }
-        if (av == 4) { P2_PROD(4) } else { P2_PROD(2) }
+#define P2_TARGS a, p, stages, tab, full, empty, rfull, rempty, raw, pack, tid
+#define P2_PROD_T(F_)                                                                                            \
+    switch (a.pro_mode) {                                                                                        \
+        case CF_PRO_AFFINE: p2_producer_tma<F_, CF_PRO_AFFINE>(P2_TARGS); break;                                 \
+        case CF_PRO_AFFINE_RELU: p2_producer_tma<F_, CF_PRO_AFFINE_RELU>(P2_TARGS); break;                       \
+        case CF_PRO_AFFINE_SWISH: p2_producer_tma<F_, CF_PRO_AFFINE_SWISH>(P2_TARGS); break;                     \
+        case CF_PRO_AFFINE2: p2_producer_tma<F_, CF_PRO_AFFINE2>(P2_TARGS); break;                               \
+        default: p2_producer_tma<F_, CF_PRO_NONE>(P2_TARGS); break;                                              \
+    }
+        if (p.tma) {
+            if (p.fold == 1) { P2_PROD_T(1) } else if (p.fold == 2) { P2_PROD_T(2) } else { P2_PROD_T(4) }
+        } else if (av == 4) { P2_PROD(4) } else { P2_PROD(2) }
+#undef P2_PROD_T
+#undef P2_TARGS
 #undef P2_PROD
 #undef P2_PARGS
     } else if (warp < P2_EPI_WARP0) {
         // ================= MMA issuer (first warp of its warpgroup; the other three only give up their registers) =================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_REGS_MMA));
         if (warp == P2_MMA_WARP) p2_mma_warp(a, p, stages, wres, full, empty, tfull, tempty, &wres_bar, tmem);
+        else if (p.tma && warp == P2_MMA_WARP + 1 && lane == 0) p2_loader(a, p, raw, rfull, rempty, &tmx, &tmx2);
     } else {
         // ================= epilogue =================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_REGS_EPI));

@@ -218,7 +218,7 @@ class ResNet(_FineResNet):
         self.fc2 = nn.Linear(2048, n_classes).to(dev)
         self.rw6 = RewightLayer(n_classes, n_classes, self.feat_depth['conv5'], height=7, pool=True).to(dev)
 
-    def forward(self, inp):
+    def _forward(self, inp):
         x, feat, feat_masks, i, meta = inp
         t_in = x.shape[2]
         if self.t_pool != 'grid':

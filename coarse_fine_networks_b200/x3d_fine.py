@@ -95,7 +95,7 @@ def se_width(width, multiplier=0.0625, min_width=8, divisor=8):
 
 
 class _BlockCfg:
-    __slots__ = ("stride", "t_stride", "training", "bn1", "bn2", "bn3", "bnd")
+    __slots__ = ("stride", "t_stride", "training", "bn1", "bn2", "bn3", "bnd", "arena")
 
 
 class Bottleneck(nn.Module):
@@ -136,6 +136,7 @@ class Bottleneck(nn.Module):
         has_se = self.index % 2 == 0
         ds = self.downsample
         cfg.bnd = X.BNCfg(ds[1]) if ds is not None else None
+        cfg.arena = getattr(self, "_arena", None)               # set by the owning ResNet for the duration of a forward pass
         params = (self.conv1.weight, self.bn1.weight, self.bn1.bias,
                   self.conv2.weight, self.bn2.weight, self.bn2.bias,
                   self.conv3.weight, self.bn3.weight, self.bn3.bias,
@@ -147,8 +148,9 @@ class Bottleneck(nn.Module):
 
 
 class _SimpleCfg:
-    def __init__(self, training, **bns):
+    def __init__(self, training, arena=None, **bns):
         self.training = training
+        self.arena = arena
         for k, v in bns.items():
             setattr(self, k, X.BNCfg(v))
 
@@ -233,13 +235,31 @@ class ResNet(nn.Module):
         return len(sbns)
 
     # -- pieces shared with the coarse stream
+    def _open_arena(self, batch, device):
+        """One zero-filled fp64 arena for every BatchNorm statistic / backward sum of this pass (x3d_ops.StatsArena)."""
+        n = 0
+        blocks = [m for m in self.modules() if isinstance(m, Bottleneck)]
+        for blk in blocks:
+            n += 2 * 4 * batch * max(blk.conv1.weight.shape[0], blk.conv3.weight.shape[0]) * 2
+        n += 2 * batch * 2 * (self.conv1_s.weight.shape[0] + self.conv5.weight.shape[0])
+        arena = X.StatsArena(n, device)
+        for blk in blocks:
+            blk._arena = arena
+        self._arena = arena
+        return arena
+
+    def _close_arena(self):
+        for blk in (m for m in self.modules() if isinstance(m, Bottleneck)):
+            blk._arena = None
+        self._arena = None
+
     def _stem(self, x):
-        return X.StemFn.apply(x, _SimpleCfg(self.training, bn1=self.bn1), self.conv1_s.weight, self.conv1_t.weight,
-                              self.bn1.weight, self.bn1.bias)
+        return X.StemFn.apply(x, _SimpleCfg(self.training, getattr(self, "_arena", None), bn1=self.bn1), self.conv1_s.weight,
+                              self.conv1_t.weight, self.bn1.weight, self.bn1.bias)
 
     def _conv5_pool(self, x, rh, rw):
-        return X.ConvBNReluPoolFn.apply(x, _SimpleCfg(self.training, bn=self.bn5), self.conv5.weight, self.bn5.weight,
-                                        self.bn5.bias, rh, rw)
+        return X.ConvBNReluPoolFn.apply(x, _SimpleCfg(self.training, getattr(self, "_arena", None), bn=self.bn5), self.conv5.weight,
+                                        self.bn5.weight, self.bn5.bias, rh, rw)
 
     def _head(self, pooled):
         """pooled [B,432,T,1,1] (channels-last) -> logits [B,n_classes,T] (x3d_fine.py:370-380)."""
@@ -258,6 +278,13 @@ class ResNet(nn.Module):
         return X.AvgPoolFn.apply(x, H // 7, W // 7)
 
     def forward(self, inp):
+        self._open_arena(inp[0].shape[0], inp[0].device)
+        try:
+            return self._forward(inp)
+        finally:
+            self._close_arena()
+
+    def _forward(self, inp):
         x, masks = inp
         x = self._stem(x)
         feat_g = {}

@@ -78,6 +78,33 @@ def dw_call(fn, x, w, y, B, C, g, *, x2=None, pro=PRO_NONE, pro_tabs=(None, None
     return y
 
 
+class StatsArena:
+    """One zero-filled fp64 buffer for all the BatchNorm statistics / backward sums of a forward pass: ONE memset per
+    network pass instead of two per block (the fp64 atomics of the producer epilogues accumulate into slices of it).
+    A slice handed out for the backward pass is consumed once (no double backward through these Functions)."""
+
+    def __init__(self, n, device):
+        self.buf = torch.zeros(max(int(n), 1), device=device, dtype=torch.float64)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        if self.off + n > self.buf.numel():                    # sized from the module tree; never expected
+            return torch.zeros(shape, device=self.buf.device, dtype=torch.float64)
+        out = self.buf[self.off:self.off + n].view(shape)
+        self.off += n
+        return out
+
+
+def _zeros64(cfg, *shape, device=None):
+    arena = getattr(cfg, "arena", None)
+    if arena is not None:
+        return arena.take(*shape)
+    return torch.zeros(shape, device=device, dtype=torch.float64)
+
+
 class BNCfg:
     """What the kernels need to know about one SubBatchNorm3d (x3d_fine.py:13-62)."""
 
@@ -176,8 +203,9 @@ class BottleneckFn(torch.autograd.Function):
         has_se, has_ds = fw1 is not None, wd is not None
         Cmax = max(Ce, Co)
         need_stats = tr or has_se                      # eval: only the SE pool needs sum(y2)
-        stats = torch.zeros(4, B, Cmax, 2, device=dev, dtype=torch.float64) if need_stats else None
+        stats = _zeros64(cfg, 4, B, Cmax, 2, device=dev) if need_stats else None
         st = (lambda i, C: stats[i].view(-1)[: B * C * 2]) if need_stats else (lambda i, C: None)
+        ctx.sums = _zeros64(cfg, 4, B, Cmax, 2, device=dev) if getattr(cfg, "arena", None) is not None else None
         smode = STATS_SUM_SQ if tr else STATS_NONE
         g_in, g_out = geom(T, H, W), geom(To, Ho, Wo)
         g_dw = geom(To, Ho, Wo, T, H, W, k=(3, 3, 3), s=(ts, s, s), p=(1, 1, 1))
@@ -235,7 +263,8 @@ class BottleneckFn(torch.autograd.Function):
         grads, rets = _flat_grads(ctx.param_shapes, dev)
         (dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dfw1, dfb1, dfw2, dfb2, dwd, dgd, dbd) = grads
         Cmax = max(Ce, Co)
-        sums = torch.zeros(4, B, Cmax, 2, device=dev, dtype=torch.float64)
+        sums = ctx.sums if ctx.sums is not None else torch.zeros(4, B, Cmax, 2, device=dev, dtype=torch.float64)
+        ctx.sums = None
         sm = lambda i, C: sums[i].view(-1)[: B * C * 2]
         g_in, g_out = geom(T, H, W), geom(To, Ho, Wo)
         g_dw = geom(To, Ho, Wo, T, H, W, k=(3, 3, 3), s=(ts, s, s), p=(1, 1, 1))
@@ -305,7 +334,8 @@ class StemFn(torch.autograd.Function):
         y0 = new_act(B, C, T, Ho, Wo, dev)
         pw_conv(x, ws, y0, B, Ci * 9, C, g_s, gather_in=1)
         yt = new_act(B, C, T, Ho, Wo, dev)
-        stats = torch.zeros(B, C, 2, device=dev, dtype=torch.float64) if tr else None
+        stats = _zeros64(cfg, B, C, 2, device=dev) if tr else None
+        ctx.sums = _zeros64(cfg, B, C, 2, device=dev) if getattr(cfg, "arena", None) is not None else None
         dw_call("cf_dw_conv_fwd", y0, wt, yt, B, C, g_t, stats=stats, stats_mode=STATS_SUM_SQ if tr else STATS_NONE)
         a, b, m, i = bn_finalize(stats, cfg.bn1, B, C, R, tr, dev)
         out = new_act(B, C, T, Ho, Wo, dev)
@@ -325,7 +355,8 @@ class StemFn(torch.autograd.Function):
         R = T * Ho * Wo
         dout = cl(dout)
         (dws, dwt, dgam, dbet), rets = _flat_grads(ctx.params, dev)
-        sums = torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
+        sums = ctx.sums if ctx.sums is not None else torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
+        ctx.sums = None
         dz = torch.empty_like(out)
         residual_bwd(dout, out, yt, dz, sums, B, C, R)
         P, Q, Rr = bn_bwd_coeffs(sums, gamma, m, i, dgam, dbet, B, C, R, ctx.cfg.training)
@@ -355,7 +386,8 @@ class ConvBNReluPoolFn(torch.autograd.Function):
         R = T * H * W
         tr = cfg.training
         y = new_act(B, C, T, H, W, dev)
-        stats = torch.zeros(B, C, 2, device=dev, dtype=torch.float64) if tr else None
+        stats = _zeros64(cfg, B, C, 2, device=dev) if tr else None
+        ctx.sums = _zeros64(cfg, B, C, 2, device=dev) if getattr(cfg, "arena", None) is not None else None
         pw_conv(x, w, y, B, Cin, C, geom(T, H, W), stats=stats, stats_mode=STATS_SUM_SQ if tr else STATS_NONE)
         a, b, m, i = bn_finalize(stats, cfg.bn, B, C, R, tr, dev)
         out = new_act(B, C, T, H // rh, W // rw, dev)
@@ -374,7 +406,8 @@ class ConvBNReluPoolFn(torch.autograd.Function):
         R = T * H * W
         dout = cl(dout)
         (dw, dgam, dbet), rets = _flat_grads(ctx.params, dev)
-        sums = torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
+        sums = ctx.sums if ctx.sums is not None else torch.zeros(B, C, 2, device=dev, dtype=torch.float64)
+        ctx.sums = None
         dz = torch.empty_like(y)
         call_struct("cf_block_avgpool_bwd", make("cf_pool_bwd_args", dy=dout, x=y, tab_a=a, tab_b=b, dz=dz, sums=sums, B=B, C=C,
                                                  T=T, H=H, W=W, rh=rh, rw=rw, accumulate=0))

@@ -244,3 +244,28 @@ def test_dense_s2_wgrad_direct(X, Ti, Hi, Wi, modes):
     assert X.lib.cf_launch_count() - n0 == 1
     assert relerr(dw, 1.0 + w.grad.reshape(C, C * 27)) <= 1e-5
     assert relerr(db, 1.0 + bias.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("K,N,T,H,W", [(54, 24, 1, 7, 7), (54, 24, 3, 7, 7), (24, 54, 1, 5, 9), (108, 48, 5, 7, 7), (6, 10, 2, 9, 8),
+                                       (216, 96, 17, 7, 7), (432, 192, 17, 7, 7)])
+def test_tc_tma_edge_shapes(X, K, N, T, H, W):
+    """Shapes around the TMA-fed producers' eligibility rules: fewer rows than one tile, odd row counts (a 54-channel row
+    tensor with an odd number of rows cannot be folded into 16-byte-aligned TMA rows: register-load producers), sample
+    boundaries inside a tile-sized box (rows of the next sample must not leak in), k-chunks that end inside a box."""
+    B = 3
+    x, x2 = synth_tensor((B, K, T, H, W), 31), synth_tensor((B, K, T, H, W), 32)
+    w = synth_tensor((N, K), 33, 0.2)
+    ta, tb, tcc = synth_tensor((B, K), 34), synth_tensor((B, K), 35), synth_tensor((B, K), 36)
+    v = lambda t: t.double().view(B, -1, 1, 1, 1)
+    g = X.geom(T, H, W)
+    conv = lambda z: torch.einsum("nk,bkthw->bnthw", w.double(), z.double())
+    for mode, xin in ((X.PRO_NONE, x.double()), (X.PRO_AFFINE_RELU, F.relu(v(ta) * x.double() + v(tb))),
+                      (X.PRO_AFFINE2, v(ta) * x.double() + v(tb) * x2.double() + v(tcc))):
+        y = X.new_act(B, N, T, H, W, "cuda")
+        stats = torch.zeros(B, N, 2, device="cuda", dtype=torch.float64)
+        X.pw_conv(rows(x), w.cuda(), y, B, K, N, g, x2=rows(x2) if mode == X.PRO_AFFINE2 else None, pro=mode,
+                  pro_tabs=(ta.cuda(), tb.cuda(), tcc.cuda()) if mode != X.PRO_NONE else (None, None, None), stats=stats,
+                  stats_mode=X.STATS_SUM_SQ, tc=True)
+        ref = conv(xin)
+        assert relerr(y, ref) <= 1e-5, f"pro {mode}"
+        assert relerr(stats[..., 0], ref.sum(dim=(2, 3, 4))) <= 1e-4 and relerr(stats[..., 1], (ref ** 2).sum(dim=(2, 3, 4))) <= 3e-5
