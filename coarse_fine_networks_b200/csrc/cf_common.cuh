@@ -65,6 +65,16 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// Packed fp32x2 FMA (sm_100 FFMA2): c += a * b on both halves in ONE issue slot.  On Blackwell a scalar FFMA warp
+// instruction occupies the FMA pipe for two cycles per SM sub-partition (64 FMA/clk/SM); only the packed form reaches the
+// full 128 FMA/clk/SM, and the depthwise 3x3x3 stencils (27 FMA per output) are FMA-issue-bound at the scalar rate.
+__device__ __forceinline__ void ffma2(float2& c, const float2 a, const float2 b) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(c.x), "+f"(c.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+}
+
 // 128-bit streaming accessors: inputs read once go through the read-only path, outputs
 // written once bypass L1 so they do not evict the small tables / reused frames.
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }

@@ -212,18 +212,18 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_kernel(const cf
 #pragma unroll
                             for (int j = 0; j < S2_PW; ++j) {
                                 const float2 x = in[2 * j + dw];
-                                pC[j].x = fmaf(x.x, w0.x, pC[j].x); pC[j].y = fmaf(x.y, w0.y, pC[j].y);      // dt = 0 -> out(ti+1)
-                                pB[j].x = fmaf(x.x, w1.x, pB[j].x); pB[j].y = fmaf(x.y, w1.y, pB[j].y);      // dt = 1 -> out(ti)
-                                pA[j].x = fmaf(x.x, w2.x, pA[j].x); pA[j].y = fmaf(x.y, w2.y, pA[j].y);      // dt = 2 -> out(ti-1)
+                                ffma2(pC[j], x, w0);      // dt = 0 -> out(ti+1)
+                                ffma2(pB[j], x, w1);      // dt = 1 -> out(ti)
+                                ffma2(pA[j], x, w2);      // dt = 2 -> out(ti-1)
                             }
                         } else {
                             float2 g0 = wreg[(0 * 3 + dh) * 3 + dw], g1 = wreg[(1 * 3 + dh) * 3 + dw], g2 = wreg[(2 * 3 + dh) * 3 + dw];
 #pragma unroll
                             for (int j = 0; j < S2_PW; ++j) {
                                 const float2 x = in[2 * j + dw];
-                                g0.x = fmaf(pC[j].x, x.x, g0.x); g0.y = fmaf(pC[j].y, x.y, g0.y);
-                                g1.x = fmaf(pB[j].x, x.x, g1.x); g1.y = fmaf(pB[j].y, x.y, g1.y);
-                                g2.x = fmaf(pA[j].x, x.x, g2.x); g2.y = fmaf(pA[j].y, x.y, g2.y);
+                                ffma2(g0, pC[j], x);
+                                ffma2(g1, pB[j], x);
+                                ffma2(g2, pA[j], x);
                             }
                             wreg[(0 * 3 + dh) * 3 + dw] = g0; wreg[(1 * 3 + dh) * 3 + dw] = g1; wreg[(2 * 3 + dh) * 3 + dw] = g2;
                         }
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(co
                     in1[j] = *reinterpret_cast<const float2*>(pl + (RW + j) * S2_CS);
                 }
                 const float2* w = wreg + dt * 9;                   // w[dh * 3 + dw]
-#define S2_FMA(ACC, X, WV) do { ACC.x = fmaf(X.x, WV.x, ACC.x); ACC.y = fmaf(X.y, WV.y, ACC.y); } while (0)
+#define S2_FMA(ACC, X, WV) ffma2(ACC, X, WV)
 #pragma unroll
                 for (int j = 0; j < S2_PW; ++j) {
                     S2_FMA(acc[0][2 * j], in0[j], w[1 * 3 + 1]);                                   // even row, even col

@@ -19,11 +19,14 @@
 #include "cf_common.cuh"
 #include "../../include/cfnet_b200.h"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 #define WG_PROD_WARPS 16
 #define WG_PROD_THREADS (WG_PROD_WARPS * 32)
-#define WG_THREADS (WG_PROD_THREADS + 32)
+#define WG_THREADS (WG_PROD_THREADS + 64)        /* + MMA issuer warp + TMA loader warp */
+#define WG_MAX_RAW 8
 #define WG_MAX_STAGES 4
 #define WG_UB 2                                  /* units per batch; two batches (this one and the next) are in registers */
 #define WG_SMEM_MAX (220 * 1024)
@@ -45,6 +48,10 @@ struct WgParams {
     // strided 1x1x1 conv (downsample branch): the x rows are gathered from a [Ti,Hi,Wi] volume at (t*st, h*sh, w*sw)
     int gmode, gH, gW, gHi, gWi, gst, gsh, gsw;
     long long g_sample_stride;
+    // TMA-fed producers: per row block the loader lane lands dy (+ dy2) and x in a raw stage [dy | dy2 | x]; a tensor whose
+    // rows are not 16-byte multiples (54 channels) is presented with `fold` rows per TMA row (tma_host.cuh)
+    int tma, fold_dy, fold_x, nraw;
+    uint32_t raw_dy_bytes, raw_x_bytes, raw_stage_bytes, raw_off;
 };
 
 // MN-major descriptor.  32-bit (tf32) MN-major operands only exist in the SWIZZLE_128B_BASE32B layout (layout type 1;
@@ -104,10 +111,15 @@ __device__ __forceinline__ void wg_ld4(const float* p, int c, int C, int av, flo
 }
 
 template <int DYM, int XM>
-__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_wgrad_args a, const WgParams p) {
+__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_wgrad_args a, const WgParams p,
+                                                                    const __grid_constant__ CUtensorMap tm_dy,
+                                                                    const __grid_constant__ CUtensorMap tm_dy2,
+                                                                    const __grid_constant__ CUtensorMap tm_x) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full[WG_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty[WG_MAX_STAGES];
+    __shared__ __align__(8) uint64_t rfull[WG_MAX_RAW];
+    __shared__ __align__(8) uint64_t rempty[WG_MAX_RAW];
     __shared__ __align__(8) uint64_t done_bar;
     __shared__ uint32_t tmem_addr_s;
 
@@ -115,6 +127,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
     uint8_t* stages = base;
     float* tabA = reinterpret_cast<float*>(stages + (size_t)p.nstages * p.stage_bytes);      // dy tables [3][ndyc*32]
     float* tabB = tabA + 3 * p.ndyc * 32;                                                      // x tables  [2][nxc*32]
+    uint8_t* raw = base + p.raw_off;                                                           // TMA landing ring
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ms = blockIdx.y / p.nsplit, ns = blockIdx.y - ms * p.nsplit;
@@ -135,6 +148,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
             mbar_init(&empty[s], 1);
         }
         mbar_init(&done_bar, 1);
+        for (int s = 0; s < p.nraw; ++s) {
+            mbar_init(&rfull[s], 1);
+            mbar_init(&rempty[s], WG_PROD_WARPS);
+        }
         fence_mbar_init();
     }
     tc_fence_before();
@@ -240,7 +257,83 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
         int b = (int)(item0 / p.rbps);
         int rb = (int)(item0 - (long long)b * p.rbps);
         long long item = item0;
-        if (item0 < item1 && grp < nunits) load_batch(b, rb, grp, vA, wA);
+        if (p.tma) {
+            // ---- TMA-fed: the row block's dy (+ dy2) and x tiles are already in shared memory (raw ring, filled by the
+            // loader lane with cp.async.bulk.tensor); read -> prologue -> hi/lo split -> swizzled operand stage
+            int rs = 0;
+            uint32_t rph = 0;
+            auto raw4 = [&](const uint8_t* reg, int fold, int C, int u, float* v) {
+                if (fold == 1) {
+                    const float4 t = *reinterpret_cast<const float4*>(reg + (size_t)u * p.chunk_bytes + row * 128 + q8 * 16);
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+                    const int c = u * 32 + q8 * 4;
+                    const float* src = reinterpret_cast<const float*>(reg) + row * C + c;
+                    if (fold == 2) {
+#pragma unroll
+                        for (int e = 0; e < 4; e += 2) {
+                            if (c + e < C) {
+                                const float2 t = *reinterpret_cast<const float2*>(src + e);
+                                v[e] = t.x; v[e + 1] = t.y;
+                            } else {
+                                v[e] = 0.f; v[e + 1] = 0.f;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = (c + e < C) ? src[e] : 0.f;
+                    }
+                }
+            };
+            for (; item < item1; ++item) {
+                const bool rv = row < min(p.RB, p.R - rb * p.RB);
+                if (b != cur_b) {
+                    named_bar_sync(1, WG_PROD_THREADS);
+                    for (int t = tid; t < p.ndyc * 32; t += WG_PROD_THREADS) {
+                        const int n = n_base + t;
+                        const bool v = n < N && DYM != CF_PRO_NONE;
+                        tabA[t] = v ? a.dy_a[(size_t)b * N + n] : 0.f;
+                        tabA[p.ndyc * 32 + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
+                        tabA[2 * p.ndyc * 32 + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
+                    }
+                    for (int t = tid; t < p.nxc * 32; t += WG_PROD_THREADS) {
+                        const int k = k_base + t;
+                        const bool v = k < K && XM != CF_PRO_NONE;
+                        tabB[t] = v ? a.x_a[(size_t)b * K + k] : 0.f;
+                        tabB[p.nxc * 32 + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
+                    }
+                    named_bar_sync(1, WG_PROD_THREADS);
+                    cur_b = b;
+                }
+                mbar_wait_b(&rfull[rs], rph);
+                mbar_wait_b(&empty[s], ph ^ 1u);
+                const uint8_t* rst = raw + (size_t)rs * p.raw_stage_bytes;
+                uint8_t* stage = stages + (size_t)s * p.stage_bytes;
+                for (int u0 = grp; u0 < nunits; u0 += ustep) {
+#pragma unroll
+                    for (int i = 0; i < WG_UB; ++i) {
+                        const int u = u0 + i * groups;
+                        if (u >= nunits) break;
+                        if (u < p.ndyc) {
+                            raw4(rst, p.fold_dy, N, u, vA[i]);
+                            if (aff2) raw4(rst + p.raw_dy_bytes, p.fold_dy, N, u, wA[i]);
+                        } else {
+                            raw4(rst + (aff2 ? 2u : 1u) * p.raw_dy_bytes, p.fold_x, K, u - p.ndyc, vA[i]);
+                        }
+                    }
+                    store_batch(stage, u0, rv, vA, wA);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rempty[rs]);                 // raw stage read: the loader may refill it
+                if (++rs == p.nraw) { rs = 0; rph ^= 1u; }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+                if (++s == p.nstages) { s = 0; ph ^= 1u; }
+                if (++rb == p.rbps) { rb = 0; ++b; }
+            }
+        }
+        if (!p.tma && item0 < item1 && grp < nunits) load_batch(b, rb, grp, vA, wA);
 
         // One row block.  Its batches alternate between the two register sets starting with (cv, cw); which set a batch
         // uses is fixed in the code (a run-time "current set" flag made the compiler copy registers right after the
@@ -304,6 +397,41 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
             if (item < item1) item_body(vA, wA, vB, wB);
         } else {
             while (item < item1) item_body(vA, wA, vB, wB);
+        }
+    } else if (warp == WG_PROD_WARPS + 1) {
+        // ================= TMA loader (one lane) =================
+        if (p.tma && lane == 0) {
+            constexpr bool aff2 = DYM == CF_PRO_AFFINE2;
+            tma_prefetch_desc(&tm_dy);
+            tma_prefetch_desc(&tm_x);
+            if (aff2) tma_prefetch_desc(&tm_dy2);
+            int rs = 0;
+            uint32_t rph = 0;
+            int b = (int)(item0 / p.rbps);
+            int rb = (int)(item0 - (long long)b * p.rbps);
+            for (long long item = item0; item < item1; ++item) {
+                mbar_wait_b(&rempty[rs], rph ^ 1u);
+                uint8_t* dst = raw + (size_t)rs * p.raw_stage_bytes;
+                mbar_expect_tx(&rfull[rs], p.raw_stage_bytes);
+                const int r0 = rb * p.RB;
+                if (p.fold_dy == 1) {
+                    for (int u = 0; u < p.ndyc; ++u) {
+                        tma_load_3d(dst + (size_t)u * p.chunk_bytes, &tm_dy, n_base + u * 32, r0, b, &rfull[rs]);
+                        if (aff2) tma_load_3d(dst + p.raw_dy_bytes + (size_t)u * p.chunk_bytes, &tm_dy2, n_base + u * 32, r0, b, &rfull[rs]);
+                    }
+                } else {
+                    tma_load_3d(dst, &tm_dy, 0, r0 / p.fold_dy, b, &rfull[rs]);
+                    if (aff2) tma_load_3d(dst + p.raw_dy_bytes, &tm_dy2, 0, r0 / p.fold_dy, b, &rfull[rs]);
+                }
+                uint8_t* xd = dst + (aff2 ? 2u : 1u) * p.raw_dy_bytes;
+                if (p.fold_x == 1) {
+                    for (int u = 0; u < p.nxc; ++u) tma_load_3d(xd + (size_t)u * p.chunk_bytes, &tm_x, k_base + u * 32, r0, b, &rfull[rs]);
+                } else {
+                    tma_load_3d(xd, &tm_x, 0, r0 / p.fold_x, b, &rfull[rs]);
+                }
+                if (++rs == p.nraw) { rs = 0; rph ^= 1u; }
+                if (++rb == p.rbps) { rb = 0; ++b; }
+            }
         }
     } else {
         // ================= MMA issuer =================
@@ -377,6 +505,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
 }
 
 // ---------------------------------------------------------------------------------------
+#ifdef CFNET_AB          /* experiment switches exist only in the -DCFNET_AB build; the shipped library reads no environment */
+static int wg_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+#else
+static int wg_env(const char*, int dflt) { return dflt; }
+#endif
+
 static int wg_sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -390,12 +527,7 @@ static int wg_sm_count() {
 
 // returns CF_OK when launched, -1 when the problem is not eligible (the caller runs the CUDA-core kernel)
 int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
-    static int disabled = -1;
-    if (disabled < 0) {
-        const char* e = getenv("CFNET_PW_WGRAD_SIMT");
-        disabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (disabled) return -1;
+    if (wg_env("CFNET_PW_WGRAD_SIMT", 0)) return -1;
     const int N = a->N, K = a->K;
     if (a->dbias || (N & 1) || (K & 1) || N > 512 || K > 512) return -1;
     if (a->gather_in && !(a->g.kt == 1 && a->g.kh == 1 && a->g.kw == 1 && a->g.pt == 0 && a->g.ph == 0 && a->g.pw == 0 && a->g.ch_stride == 1 &&
@@ -404,9 +536,7 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     if (a->dy_mode != CF_PRO_NONE && a->dy_mode != CF_PRO_AFFINE2) return -1;
     if (a->x_mode == CF_PRO_AFFINE2) return -1;
     const long long R = (long long)a->g.T * a->g.H * a->g.W;
-    static long long min_rows = -1;                          // tiny problems: launch overhead dominates, keep the simple kernel
-    if (min_rows < 0) { const char* e = getenv("CFNET_WG_MINROWS"); min_rows = e ? atoll(e) : 4096; }
-    if (R * a->B < min_rows) return -1;
+    if (R * a->B < 4096) return -1;                          // tiny problems: launch overhead dominates, keep the simple kernel
     WgParams p;
     p.B = a->B; p.R = (int)R; p.N = N; p.K = K;
     p.gmode = a->gather_in ? 1 : 0;
@@ -422,9 +552,7 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     {
         const long long cost0 = (long long)((N + 127) / 128) * 128 * ((K + 31) / 32 * 32);
         const long long cost1 = (long long)((K + 127) / 128) * 128 * ((N + 31) / 32 * 32);
-        static int noswap = -1;                               // CFNET_WG_NOSWAP=1: A/B switch
-        if (noswap < 0) { const char* e = getenv("CFNET_WG_NOSWAP"); noswap = (e && e[0] == '1') ? 1 : 0; }
-        p.swap = (cost1 < cost0 && !noswap) ? 1 : 0;
+        p.swap = (cost1 < cost0 && !wg_env("CFNET_WG_NOSWAP", 0)) ? 1 : 0;
     }
     const int Msz = p.swap ? K : N, Csz = p.swap ? N : K;
     const int mtiles = (Msz + 127) / 128;
@@ -447,20 +575,57 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.mt_per * p.npad_per) p.tmem_cols <<= 1;
     const size_t tab_bytes = (size_t)(3 * p.ndyc + 2 * p.nxc) * 32 * 4;
-    static int rb0 = -1;                                      // CFNET_WG_RB=32|16: A/B switch
-    if (rb0 < 0) { const char* e = getenv("CFNET_WG_RB"); rb0 = e ? atoi(e) : 64; if (rb0 != 16 && rb0 != 32) rb0 = 64; }
-    p.RB = rb0;                                              // rows per stage: as many as leave >= 2 stages (per-stage overhead amortised)
-    for (;;) {
-        p.chunk_bytes = (uint32_t)p.RB * 128u;
-        p.stage_bytes = (uint32_t)(2 * (p.nchA_pad + p.nchB)) * p.chunk_bytes;
-        p.nstages = (int)((WG_SMEM_MAX - 1024 - tab_bytes) / p.stage_bytes);
-        if (p.nstages >= 2 || p.RB == 16) break;
-        p.RB >>= 1;
+    // ---- TMA-fed producers (dense rows; tensors describable by a tensor map): 2 operand stages + a ring of raw stages
+    CUtensorMap tm_dy, tm_dy2, tm_x;
+    memset(&tm_dy, 0, sizeof(tm_dy));
+    memset(&tm_dy2, 0, sizeof(tm_dy2));
+    memset(&tm_x, 0, sizeof(tm_x));
+    const bool aff2 = a->dy_mode == CF_PRO_AFFINE2;
+    p.tma = 0; p.fold_dy = p.fold_x = 1; p.nraw = 0; p.raw_dy_bytes = p.raw_x_bytes = p.raw_stage_bytes = p.raw_off = 0;
+    bool planned = false;
+    if (!p.gmode && wg_env("CFNET_WG_TMA", 1)) {
+        const int fdy = (N % 4 == 0) ? 1 : 2, fx = (K % 4 == 0) ? 1 : 2;
+        // 54-channel tensors (rows that are not 16-byte multiples) would need the folded whole-tile copies and 8-byte
+        // shared-memory reads: measured 2-4 % slower than the register-load producers on the layer-1 shapes (same-box A/B,
+        // profiles/r02_ab_same_box.md), 13-19 % faster on the 16-byte-row shapes of layers 2-4
+        if (fdy == 1 && fx == 1) {
+            for (int rb = 64; rb >= 16 && !planned; rb >>= 1) {
+                const uint32_t chunk = (uint32_t)rb * 128u;
+                const uint32_t stage = (uint32_t)(2 * (p.nchA_pad + p.nchB)) * chunk;
+                const uint32_t rdy = fdy == 1 ? (uint32_t)p.ndyc * chunk : (uint32_t)rb * N * 4u;
+                const uint32_t rx = fx == 1 ? (uint32_t)p.nxc * chunk : (uint32_t)rb * K * 4u;
+                const uint32_t rstage = (aff2 ? 2u : 1u) * rdy + rx;
+                const size_t used = 1024 + 2 * (size_t)stage + tab_bytes + 128;
+                if (used + 3 * (size_t)rstage > WG_SMEM_MAX) continue;
+                if (!cf_make_row_tmap(&tm_dy, a->dy, a->B, R, N, fdy, rb) || (aff2 && !cf_make_row_tmap(&tm_dy2, a->dy2, a->B, R, N, fdy, rb)) ||
+                    !cf_make_row_tmap(&tm_x, a->x, a->B, R, K, fx, rb))
+                    break;
+                p.tma = 1; p.fold_dy = fdy; p.fold_x = fx;
+                p.RB = rb; p.chunk_bytes = chunk; p.stage_bytes = stage; p.nstages = 2;
+                p.raw_dy_bytes = rdy; p.raw_x_bytes = rx; p.raw_stage_bytes = rstage;
+                p.nraw = (int)((WG_SMEM_MAX - used) / rstage);
+                if (p.nraw > WG_MAX_RAW) p.nraw = WG_MAX_RAW;
+                p.raw_off = (uint32_t)((2 * (size_t)stage + tab_bytes + 127) / 128 * 128);
+                planned = true;
+            }
+        }
     }
-    if (p.nstages < 2) return -1;
-    if (p.nstages > WG_MAX_STAGES) p.nstages = WG_MAX_STAGES;
-    // keep the shared-memory carve-out at <= 196 KB (some L1 left for the 8-byte loads of the 54-channel tensors: see x3d_pw_tc2.cu)
-    while (p.nstages > 2 && 1024 + (size_t)p.nstages * p.stage_bytes + tab_bytes > 193 * 1024) --p.nstages;
+    if (!planned) {
+        int rb0 = wg_env("CFNET_WG_RB", 64);
+        if (rb0 != 16 && rb0 != 32) rb0 = 64;
+        p.RB = rb0;                                          // rows per stage: as many as leave >= 2 stages (per-stage overhead amortised)
+        for (;;) {
+            p.chunk_bytes = (uint32_t)p.RB * 128u;
+            p.stage_bytes = (uint32_t)(2 * (p.nchA_pad + p.nchB)) * p.chunk_bytes;
+            p.nstages = (int)((WG_SMEM_MAX - 1024 - tab_bytes) / p.stage_bytes);
+            if (p.nstages >= 2 || p.RB == 16) break;
+            p.RB >>= 1;
+        }
+        if (p.nstages < 2) return -1;
+        if (p.nstages > WG_MAX_STAGES) p.nstages = WG_MAX_STAGES;
+        // keep the shared-memory carve-out at <= 196 KB (some L1 left for the 8-byte loads of the 54-channel tensors: see x3d_pw_tc2.cu)
+        while (p.nstages > 2 && 1024 + (size_t)p.nstages * p.stage_bytes + tab_bytes > 193 * 1024) --p.nstages;
+    }
     {
         const uint32_t m_lo = (uint32_t)p.nchA_pad * p.chunk_bytes, c_off = 2u * m_lo, c_lo = (uint32_t)p.nchB * p.chunk_bytes;
         if (p.swap) { p.x_off = 0; p.x_lo = m_lo; p.dy_off = c_off; p.dy_lo = c_lo; }
@@ -473,7 +638,8 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     if (gx > p.total_items) gx = (int)p.total_items;
     p.items_per_cta = (int)((p.total_items + gx - 1) / gx);
     gx = (int)((p.total_items + p.items_per_cta - 1) / p.items_per_cta);
-    const size_t smem = 1024 + (size_t)p.nstages * p.stage_bytes + tab_bytes;
+    const size_t smem = p.tma ? 1024 + (size_t)p.raw_off + (size_t)p.nraw * p.raw_stage_bytes
+                              : 1024 + (size_t)p.nstages * p.stage_bytes + tab_bytes;
     dim3 grid((unsigned)gx, (unsigned)(p.msplit * p.nsplit));
     cudaError_t e = cudaSuccess;
 #define WG_LAUNCH(DYM_, XM_)                                                                                                  \
@@ -483,7 +649,7 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
             e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<DYM_, XM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX); \
             if (e == cudaSuccess) attr_done.mark();                                                                                     \
         }                                                                                                                     \
-        if (e == cudaSuccess) pw_wgrad_tc_kernel<DYM_, XM_><<<grid, WG_THREADS, smem, stream>>>(*a, p);                       \
+        if (e == cudaSuccess) pw_wgrad_tc_kernel<DYM_, XM_><<<grid, WG_THREADS, smem, stream>>>(*a, p, tm_dy, tm_dy2, tm_x);                     \
     } while (0)
 #define WG_LAUNCH_X(DYM_)                                                              \
     switch (a->x_mode) {                                                               \
