@@ -227,6 +227,52 @@ __global__ void __launch_bounds__(256) residual_fwd_kernel(const cf_residual_arg
     stv<V>(a.out + off, o);
 }
 
+// the same join for a stage-final block of the global tower: a thread owns one (t, pooling block, channel vector), writes
+// the rh x rw outputs of its block and their average (x3d_fine.py:345-354) -- the features leave in the pass that produces
+// the stage output instead of in a second full read of it
+template <int V>
+__global__ void __launch_bounds__(256) residual_pool_fwd_kernel(const cf_residual_args a) {
+    const int b = blockIdx.y, C = a.C, CV = C / V;
+    const int Ho = a.H / a.rh, Wo = a.W / a.rw;
+    long long n = (long long)a.T * Ho * Wo * CV;
+    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n) return;
+    int c0 = (int)(idx % CV) * V;
+    long long q = idx / CV;
+    int wo = (int)(q % Wo); q /= Wo;
+    int ho = (int)(q % Ho);
+    int t = (int)(q / Ho);
+    const VecF<V> ta = ldtab<V>(a.tab_a + (size_t)b * C + c0), tb = ldtab<V>(a.tab_b + (size_t)b * C + c0);
+    VecF<V> ra, rb;
+    if (a.res && a.res_a) { ra = ldtab<V>(a.res_a + (size_t)b * C + c0); rb = ldtab<V>(a.res_b + (size_t)b * C + c0); }
+    VecF<V> acc;
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc.v[i] = 0.f;
+    for (int dh = 0; dh < a.rh; ++dh)
+        for (int dw = 0; dw < a.rw; ++dw) {
+            const long long off = ((((long long)b * a.T + t) * a.H + ho * a.rh + dh) * a.W + wo * a.rw + dw) * C + c0;
+            const VecF<V> y = ldv<V>(a.y + off);
+            VecF<V> o;
+#pragma unroll
+            for (int i = 0; i < V; ++i) o.v[i] = fmaf(ta.v[i], y.v[i], tb.v[i]);
+            if (a.res) {
+                const VecF<V> r = ldv<V>(a.res + off);
+#pragma unroll
+                for (int i = 0; i < V; ++i) o.v[i] += a.res_a ? fmaf(ra.v[i], r.v[i], rb.v[i]) : r.v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                o.v[i] = fmaxf(o.v[i], 0.f);
+                acc.v[i] += o.v[i];
+            }
+            stv<V>(a.out + off, o);
+        }
+    const float inv = 1.0f / (float)(a.rh * a.rw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc.v[i] *= inv;
+    stv<V>(a.pooled + ((((long long)b * a.T + t) * Ho + ho) * Wo + wo) * C + c0, acc);
+}
+
 // rows of one sample are split in chunks over grid.x; 256 threads = PY row lanes x CV channel vectors
 template <int V>
 __global__ void __launch_bounds__(256) residual_bwd_kernel(const cf_residual_bwd_args a, int chunk) {
@@ -244,7 +290,22 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const cf_residual_bwd
         for (int i = 0; i < V; ++i) { s0.v[i] = 0.f; s1.v[i] = 0.f; s2.v[i] = 0.f; }
         for (long long r = r0 + lane; r < r1; r += PY) {
             long long off = ((long long)b * a.rows_per_sample + r) * C + c0;
-            VecF<V> d = ldv<V>(a.dout + off), o = ldv<V>(a.out + off), y = ldv<V>(a.y + off);
+            VecF<V> d, o = ldv<V>(a.out + off), y = ldv<V>(a.y + off);
+            if (a.dout) d = ldv<V>(a.dout + off);
+            else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) d.v[i] = 0.f;
+            }
+            if (a.dpool) {                       // gradient of the pooled features, spread over their rh x rw block
+                const int w = (int)(r % a.W);
+                const long long q = r / a.W;
+                const int h = (int)(q % a.H), t = (int)(q / a.H);
+                const int Ho = a.H / a.rh, Wo = a.W / a.rw;
+                const VecF<V> dp = ldv<V>(a.dpool + ((((long long)b * a.T + t) * Ho + h / a.rh) * Wo + w / a.rw) * C + c0);
+                const float inv = 1.0f / (float)(a.rh * a.rw);
+#pragma unroll
+                for (int i = 0; i < V; ++i) d.v[i] = fmaf(dp.v[i], inv, d.v[i]);
+            }
             VecF<V> rs;
             if (a.res) rs = ldv<V>(a.res + off);
             VecF<V> dz;
@@ -427,6 +488,20 @@ extern "C" int cf_residual_fwd(const cf_residual_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->y && a->tab_a && a->tab_b && a->out, "null pointer");
     CF_CHECK_ARG(a->B > 0 && a->B <= 65535 && a->C > 0 && a->rows_per_sample > 0, "bad shape");
     int v = vec_for(a->C, a->y, a->out, a->res, nullptr);
+    if (a->pooled) {
+        CF_CHECK_ARG(a->T > 0 && a->H > 0 && a->W > 0 && a->rh > 0 && a->rw > 0 && a->H % a->rh == 0 && a->W % a->rw == 0 &&
+                         (int64_t)a->T * a->H * a->W == a->rows_per_sample,
+                     "pooled output: rows_per_sample must be T*H*W with H,W multiples of the pooling block");
+        if ((((uintptr_t)a->pooled) & 15) && v == 4) v = 2;
+        long long np = (long long)a->T * (a->H / a->rh) * (a->W / a->rw) * (a->C / v);
+        dim3 gp((unsigned)cf_cdiv64(np, 256), (unsigned)a->B);
+        if (v == 4) residual_pool_fwd_kernel<4><<<gp, 256, 0, stream>>>(*a);
+        else if (v == 2) residual_pool_fwd_kernel<2><<<gp, 256, 0, stream>>>(*a);
+        else residual_pool_fwd_kernel<1><<<gp, 256, 0, stream>>>(*a);
+        CF_COUNT_LAUNCH(1);
+        CF_CHECK_LAUNCH();
+        return CF_OK;
+    }
     long long n = a->rows_per_sample * (a->C / v);
     dim3 grid((unsigned)cf_cdiv64(n, 256), (unsigned)a->B);
     if (v == 4) residual_fwd_kernel<4><<<grid, 256, 0, stream>>>(*a);
@@ -438,10 +513,14 @@ extern "C" int cf_residual_fwd(const cf_residual_args* a, cudaStream_t stream) {
 }
 
 extern "C" int cf_residual_bwd(const cf_residual_bwd_args* a, cudaStream_t stream) {
-    CF_CHECK_ARG(a && a->dout && a->out && a->y && a->dz && a->sums_y, "null pointer");
+    CF_CHECK_ARG(a && (a->dout || a->dpool) && a->out && a->y && a->dz && a->sums_y, "null pointer");
     CF_CHECK_ARG(a->B > 0 && a->B <= 65535 && a->C > 0 && a->rows_per_sample > 0, "bad shape");
     CF_CHECK_ARG(!a->sums_res || a->res, "sums_res without res");
-    int v = vec_for(a->C, a->dout, a->out, a->y, a->dz);
+    CF_CHECK_ARG(!a->dpool || (a->T > 0 && a->rh > 0 && a->rw > 0 && a->H % a->rh == 0 && a->W % a->rw == 0 &&
+                               (int64_t)a->T * a->H * a->W == a->rows_per_sample),
+                 "dpool: rows_per_sample must be T*H*W with H,W multiples of the pooling block");
+    int v = vec_for(a->C, a->dout ? a->dout : a->out, a->out, a->y, a->dz);
+    if (a->dpool && (((uintptr_t)a->dpool) & 15) && v == 4) v = 2;
     if (a->res && (((uintptr_t)a->res) & 15) && v == 4) v = 2;
     if (a->C / v > 256) { cf_set_error("cf_residual_bwd: C/vec > 256"); return CF_ERR_ARG; }
     int chunk = chunk_for(a->rows_per_sample, a->B, 256 / (a->C / v));

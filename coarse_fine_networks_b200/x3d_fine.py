@@ -95,7 +95,7 @@ def se_width(width, multiplier=0.0625, min_width=8, divisor=8):
 
 
 class _BlockCfg:
-    __slots__ = ("stride", "t_stride", "training", "bn1", "bn2", "bn3", "bnd", "arena")
+    __slots__ = ("stride", "t_stride", "training", "bn1", "bn2", "bn3", "bnd", "arena", "pool")
 
 
 class Bottleneck(nn.Module):
@@ -126,7 +126,9 @@ class Bottleneck(nn.Module):
 
     round_width = staticmethod(se_width)
 
-    def forward(self, x):
+    def forward(self, x, pool=None):
+        """pool=(rh, rw): also return the (H/rh, W/rw) block average of the output, emitted by the residual-join kernel
+        (the global tower's adaptive_avg_pool3d(x, (None,7,7)) of a stage output, x3d_fine.py:345-354) -> (out, pooled)."""
         if self.downsample is not None and not isinstance(self.downsample, nn.Sequential):
             raise NotImplementedError("shortcut_type 'A' (zero-padded identity) is not built; the scripts use 'B'")
         cfg = _BlockCfg()
@@ -137,6 +139,7 @@ class Bottleneck(nn.Module):
         ds = self.downsample
         cfg.bnd = X.BNCfg(ds[1]) if ds is not None else None
         cfg.arena = getattr(self, "_arena", None)               # set by the owning ResNet for the duration of a forward pass
+        cfg.pool = pool
         params = (self.conv1.weight, self.bn1.weight, self.bn1.bias,
                   self.conv2.weight, self.bn2.weight, self.bn2.bias,
                   self.conv3.weight, self.bn3.weight, self.bn3.bias,
@@ -289,9 +292,16 @@ class ResNet(nn.Module):
         x = self._stem(x)
         feat_g = {}
         for name in ("layer1", "layer2", "layer3", "layer4"):
-            x = getattr(self, name)(x)
-            if self.global_tower:
-                feat_g[name] = self._pool7(x)                       # x3d_fine.py:345-354
+            stage = getattr(self, name)
+            if not self.global_tower:
+                x = stage(x)
+                continue
+            for blk in list(stage)[:-1]:
+                x = blk(x)
+            Ho, Wo = (x.shape[3] - 1) // stage[-1].stride + 1, (x.shape[4] - 1) // stage[-1].stride + 1
+            if Ho % 7 or Wo % 7:
+                raise NotImplementedError("global_tower needs spatial sizes that are multiples of 7 (224x224 clips)")
+            x, feat_g[name] = stage[-1](x, pool=(Ho // 7, Wo // 7))     # x3d_fine.py:345-354, fused into the residual join
         B, _, T, H, W = x.shape
         if self.global_tower:
             if H % 7 or W % 7:

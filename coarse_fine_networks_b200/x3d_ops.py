@@ -144,16 +144,18 @@ def bn_bwd_coeffs(sums, gamma, mean, invstd, dgamma, dbeta, B, C, rows, training
     return tabs[0], tabs[1], tabs[2]
 
 
-def residual_fwd(y, ta, tb, out, B, C, rows, res=None, ra=None, rb=None):
-    a = make("cf_residual_args", y=y, tab_a=ta, tab_b=tb, res=res, res_a=ra, res_b=rb, out=out, B=B, C=C,
-             rows_per_sample=rows)
+def residual_fwd(y, ta, tb, out, B, C, rows, res=None, ra=None, rb=None, pooled=None, pool_geom=(0, 0, 0, 0, 0)):
+    T, H, W, rh, rw = pool_geom
+    a = make("cf_residual_args", y=y, tab_a=ta, tab_b=tb, res=res, res_a=ra, res_b=rb, out=out, pooled=pooled, B=B, C=C,
+             T=T, H=H, W=W, rh=rh, rw=rw, rows_per_sample=rows)
     call_struct("cf_residual_fwd", a)
     return out
 
 
-def residual_bwd(dout, out, y, dz, sums_y, B, C, rows, res=None, sums_res=None):
-    a = make("cf_residual_bwd_args", dout=dout, out=out, y=y, res=res, dz=dz, sums_y=sums_y, sums_res=sums_res, B=B, C=C,
-             rows_per_sample=rows)
+def residual_bwd(dout, out, y, dz, sums_y, B, C, rows, res=None, sums_res=None, dpool=None, pool_geom=(0, 0, 0, 0, 0)):
+    T, H, W, rh, rw = pool_geom
+    a = make("cf_residual_bwd_args", dout=dout, out=out, y=y, res=res, dpool=dpool, dz=dz, sums_y=sums_y, sums_res=sums_res,
+             B=B, C=C, T=T, H=H, W=W, rh=rh, rw=rw, rows_per_sample=rows)
     call_struct("cf_residual_bwd", a)
     return dz
 
@@ -239,7 +241,14 @@ class BottleneckFn(torch.autograd.Function):
             pw_conv(x, wd, yd, B, Cin, Co, g_ds, gather_in=1, stats=st(3, Co) if tr else None, stats_mode=smode)
             ad, bbd, md, idd = bn_finalize(st(3, Co) if tr else None, cfg.bnd, B, Co, Rout, tr, dev)
         out = new_act(B, Co, To, Ho, Wo, dev)
-        residual_fwd(y3, a3, bb3, out, B, Co, Rout, res=yd if has_ds else x, ra=ad, rb=bbd)
+        pool = getattr(cfg, "pool", None)                     # (rh, rw): stage-final block of the global tower
+        pooled = None
+        if pool is not None:
+            pooled = new_act(B, Co, To, Ho // pool[0], Wo // pool[1], dev)
+            ctx.pool_geom = (To, Ho, Wo, pool[0], pool[1])
+        residual_fwd(y3, a3, bb3, out, B, Co, Rout, res=yd if has_ds else x, ra=ad, rb=bbd, pooled=pooled,
+                     pool_geom=ctx.pool_geom if pool is not None else (0, 0, 0, 0, 0))
+        ctx.has_pool = pool is not None
 
         ctx.cfg = cfg
         ctx.dims = (B, Cin, Ce, Co, T, H, W, To, Ho, Wo, s, ts)
@@ -247,10 +256,12 @@ class BottleneckFn(torch.autograd.Function):
         ctx.aux = (a1, bb1, m1, i1, a2, bb2, m2, i2, ga, gb, a3, bb3, m3, i3, ad, bbd, md, idd, st(1, Ce))
         ctx.save_for_backward(x, y1, y2, y3, yd, out, w1, g1, w2, g2, w3, g3, fw1, fw2, wd, gd)
         ctx.param_shapes = [p for p in (w1, g1, b1, w2, g2, b2, w3, g3, b3, fw1, fb1, fw2, fb2, wd, gd, bd)]
+        if pool is not None:
+            return out, pooled
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dpooled=None):
         x, y1, y2, y3, yd, out, w1, g1, w2, g2, w3, g3, fw1, fw2, wd, gd = ctx.saved_tensors
         (a1, bb1, m1, i1, a2, bb2, m2, i2, ga, gb, a3, bb3, m3, i3, ad, bbd, md, idd, stats2) = ctx.aux
         B, Cin, Ce, Co, T, H, W, To, Ho, Wo, s, ts = ctx.dims
@@ -259,7 +270,8 @@ class BottleneckFn(torch.autograd.Function):
         dev = x.device
         has_se, has_ds = fw1 is not None, wd is not None
         Rin, Rout = T * H * W, To * Ho * Wo
-        dout = cl(dout)
+        dout = cl(dout) if dout is not None else None
+        dpooled = cl(dpooled) if (ctx.has_pool and dpooled is not None) else None
         grads, rets = _flat_grads(ctx.param_shapes, dev)
         (dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3, dfw1, dfb1, dfw2, dfb2, dwd, dgd, dbd) = grads
         Cmax = max(Ce, Co)
@@ -272,7 +284,8 @@ class BottleneckFn(torch.autograd.Function):
 
         # join: dz3 = dout*[out>0]; sums vs y3 (bn3) and vs yd (downsample bn)
         dz3 = torch.empty_like(out)
-        residual_bwd(dout, out, y3, dz3, sm(0, Co), B, Co, Rout, res=yd, sums_res=sm(3, Co) if has_ds else None)
+        residual_bwd(dout, out, y3, dz3, sm(0, Co), B, Co, Rout, res=yd, sums_res=sm(3, Co) if has_ds else None, dpool=dpooled,
+                     pool_geom=ctx.pool_geom if dpooled is not None else (0, 0, 0, 0, 0))
         P3, Q3, R3 = bn_bwd_coeffs(sm(0, Co), g3, m3, i3, dg3, db3, B, Co, Rout, tr)
         # conv3
         pw_wgrad(dz3, y2, dw3, B, Ce, Co, g_out, dy2=y3, dy_mode=PRO_AFFINE2, dy_tabs=(P3, Q3, R3), x_mode=PRO_AFFINE_SWISH,

@@ -302,7 +302,10 @@ typedef struct {
 int cf_se_bwd(const cf_se_bwd_args* a, cudaStream_t stream);
 
 /* residual join (x3d_fine.py:169-173): out = relu(a3*y3 + b3 + res'),
- * res' = ar*res + br (downsample branch, tables) or res (identity) or 0 (res == NULL). */
+ * res' = ar*res + br (downsample branch, tables) or res (identity) or 0 (res == NULL).
+ * Stage-final blocks of the fine stream's global tower (x3d_fine.py:345-354) also emit the (H/rh, W/rw) block average
+ * of `out` -- F.adaptive_avg_pool3d(x, (None,7,7)) -- from the same pass: pooled [B,T,H/rh,W/rw,C] != NULL with
+ * rows_per_sample == T*H*W and H % rh == W % rw == 0 (one thread owns a pooling block: no atomics). */
 typedef struct {
     const float* y;          /* [B,R,C] */
     const float* tab_a;      /* [B,C] */
@@ -311,22 +314,28 @@ typedef struct {
     const float* res_a;      /* [B,C] or NULL */
     const float* res_b;
     float* out;              /* [B,R,C] */
+    float* pooled;           /* [B,T,H/rh,W/rw,C] or NULL */
     int B, C;
+    int T, H, W, rh, rw;     /* only read when pooled != NULL */
     int64_t rows_per_sample;
 } cf_residual_args;
 int cf_residual_fwd(const cf_residual_args* a, cudaStream_t stream);
 
-/* backward of the join: dz = dout * [out > 0]; sums_y[b,c] = (sum dz, sum dz*y);
- * sums_res likewise against `res` (downsample branch pre-BN tensor) when given. */
+/* backward of the join: dz = dout' * [out > 0]; sums_y[b,c] = (sum dz, sum dz*y);
+ * sums_res likewise against `res` (downsample branch pre-BN tensor) when given.
+ * dout' = dout + dpool[block of the row] / (rh*rw) when the forward also emitted the pooled features
+ * (dpool [B,T,H/rh,W/rw,C] != NULL; dout may then be NULL = no gradient from the next stage). */
 typedef struct {
-    const float* dout;
+    const float* dout;       /* [B,R,C] (or NULL with dpool) */
     const float* out;
     const float* y;
     const float* res;        /* or NULL */
+    const float* dpool;      /* [B,T,H/rh,W/rw,C] or NULL */
     float* dz;
     double* sums_y;          /* [B,C,2] */
     double* sums_res;        /* [B,C,2] or NULL */
     int B, C;
+    int T, H, W, rh, rw;     /* only read when dpool != NULL */
     int64_t rows_per_sample;
 } cf_residual_bwd_args;
 int cf_residual_bwd(const cf_residual_bwd_args* a, cudaStream_t stream);

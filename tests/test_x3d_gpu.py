@@ -340,6 +340,41 @@ def test_bottleneck_real_widths_vs_oracle():
             close(p.grad, params["b." + k].grad, rtol=1e-3, atol=5e-5, what=f"grad {k}")
 
 
+@pytest.mark.parametrize("stride,grad_out", [(1, True), (2, True), (1, False)])
+def test_bottleneck_fused_stage_pool_vs_oracle(stride, grad_out):
+    """Stage-final block of the global tower: the residual-join kernel also emits adaptive_avg_pool3d(out, (None,7,7))
+    (x3d_fine.py:345-354); forward and backward (gradient arriving through both outputs, or through the features only)
+    against the oracle's block followed by torch's pooling."""
+    import torch.nn.functional as F
+    from coarse_fine_networks_b200 import x3d_fine as M
+    cin, planes, index = 24, (54, 24), 0
+    down = None
+    if stride != 1:
+        down = torch.nn.Sequential(M.conv1x1x1(cin, planes[1], stride), M.SubBatchNorm3d(num_splits=1, num_features=planes[1], affine=True))
+    m = M.Bottleneck(cin, planes, stride=stride, downsample=down, index=index, base_bn_splits=1)
+    fill_state_dict(m, seed=17)
+    sd = {"b." + k: v.clone() for k, v in m.state_dict().items()}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    x = synth_tensor((2, cin, 3, 28 * stride, 28 * stride), 18)
+    xr = x.clone().requires_grad_(True)
+    ref = O.bottleneck(xr, sd, "b", stride, index, True, 1)
+    ref_p = F.adaptive_avg_pool3d(ref, (None, 7, 7))
+    gout, gp = synth_tensor(tuple(ref.shape), 19), synth_tensor(tuple(ref_p.shape), 20)
+    ((ref * gout).sum() * (1.0 if grad_out else 0.0) + (ref_p * gp).sum()).backward()
+    m.cuda().train()
+    xc = x.cuda().requires_grad_(True)
+    out, pooled = m(xc, pool=(4, 4))
+    close(out, ref, rtol=5e-5, atol=5e-5, what="out")
+    close(pooled, ref_p, rtol=5e-5, atol=5e-5, what="pooled")
+    loss = (pooled * gp.cuda()).sum()
+    if grad_out:
+        loss = loss + (out * gout.cuda()).sum()
+    loss.backward()
+    close(xc.grad, xr.grad, rtol=1e-3, atol=5e-5, what="dx")
+    for k, p in m.named_parameters():
+        close(p.grad, params["b." + k].grad, rtol=1e-3, atol=5e-5, what=f"grad {k}")
+
+
 def test_standalone_bn_and_swish():
     from coarse_fine_networks_b200 import x3d_fine as M
     bn = M.SubBatchNorm3d(num_splits=2, num_features=6, affine=True)
