@@ -62,7 +62,7 @@ def build(force=False, verbose=False, ab=False):
         res = list(ex.map(lambda s: _compile(s, verbose, obj_dir, extra), srcs))
     objs = [o for o, _ in res]
     if any(ch for _, ch in res) or not os.path.exists(lib):
-        cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -62,19 +62,26 @@ class Charades(_fine.Charades):
     (`split` is used as given: this loader has no extract_feat switch.)"""
 
     def __init__(self, split_file, split, root, fine_feat, feature_keys, spatial_transform=None, task="class", frames=80,
-                 gamma_tau=5, crops=1, device="cuda", cache=True):
+                 gamma_tau=5, crops=1, device="cuda", cache=True, decode="pil", host_items=False):
         super().__init__(split_file, split, root, spatial_transform, task=task, frames=frames, gamma_tau=gamma_tau, crops=crops,
-                         extract_feat=False, device=device, cache=cache)
+                         extract_feat=False, device=device, cache=cache, decode=decode, host_items=host_items)
         self.fine_feat, self.feature_keys = fine_feat, list(feature_keys)
 
-    def __getitem__(self, index):
-        """-> (clips [N,3,T,S,S] on `device`, label, feat {layer: numpy [C,Tf,7,7]}, meta int64 [4], vid, duration)."""
+    def host_item(self, index):
         s = self.sample(index)                                            # window draw first ...
-        feat = load_fine_features(self.fine_feat, self.feature_keys, s["vid"])
-        frames_u8 = torch.from_numpy(s["frames"]).to(self.device, non_blocking=True)
+        s["feat"] = load_fine_features(self.fine_feat, self.feature_keys, s["vid"])
         self.spatial_transform.randomize_parameters(224)                  # ... then the transform's draws (reference order)
-        clips, label = self.views(self.spatial_transform.clip(frames_u8), s["label"], s["frame_count"])
-        return clips, label, feat, s["meta"], s["vid"], self.data[index][2]
+        s["tstate"] = self.spatial_transform.get_state()
+        return s
+
+    def finish(self, s):
+        """-> (clips [N,3,T,S,S] on `device`, label, feat {layer: numpy [C,Tf,7,7]}, meta int64 [4], vid, duration)."""
+        self.spatial_transform.set_state(s["tstate"])
+        clips, label = self.views(self.spatial_transform.clip(self.frames_on_device(s)), s["label"], s["frame_count"])
+        return clips, label, s["feat"], s["meta"], s["vid"], self.data[s["index"]][2]
+
+    def device_collate(self, batch):
+        return mt_collate_fn([self.finish(s) for s in batch])
 
 
 def mt_collate_fn(batch):

@@ -10,7 +10,15 @@ the reference statement by statement, including the order of the draws from Pyth
 transform's parameters), so one seed selects the same clips on both sides.  What changes is where the pixels are processed:
 the decoded frames of a video go to the GPU as ONE uint8 tensor [T,H,W,3] and `spatial_transform.clip()` (one launch of
 cf_clip_preprocess) produces the normalised [3,T,S,S] clip -- bit-identical to `[transform(img) for img in imgs]` + stack +
-permute (charades_fine.py:170-172).  JPEG decoding stays on the host (PIL, as in the reference's pil_loader, 22-26).
+permute (charades_fine.py:170-172).  JPEG decoding: `decode="pil"` keeps the reference's host decode (pil_loader, 22-26);
+`decode="nvjpeg"` reads the files as bytes and decodes the whole clip on the GPU (jpeg.JpegDecoder, nvJPEG batched decode)
+straight into the uint8 tensor the clip kernel reads.
+
+DataLoader workers: CUDA cannot be used in forked workers and pinned-memory collation does not apply to CUDA tensors, so with
+`num_workers > 0` build the dataset with `host_items=True`: `__getitem__` then does only the host half (window draw, file
+reads / PIL decode, the transform's random draw) and returns a plain dict; pass `collate_fn=dataset.device_collate` (runs in
+the main process: GPU decode + clip kernel + the reference's zero-padding collate).  Without it (`host_items=False`, the
+default) items are CUDA tensors as before and the loader must run with num_workers=0, pin_memory=False.
 
 Differences, on purpose: the label cache `<split>_<split>labeldata_160.npy` is written as an object array (the reference's
 `np.save(list_of_tuples)` raises on numpy >= 1.24) and read back the way the reference reads it; the accimage backend is not
@@ -46,6 +54,12 @@ def video_loader(video_dir_path, vid, frame_indices, image_loader=pil_loader):
 def load_rgb_frames(image_dir, vid, start, num, stride, loader=video_loader):
     """charades_fine.py:73-80."""
     return loader(image_dir, vid, list(range(start, start + num, stride)))
+
+
+def bytes_loader(path):
+    """The undecoded JPEG stream of a frame (for decode="nvjpeg")."""
+    with open(path, "rb") as f:
+        return f.read()
 
 
 def make_dataset(split_file, split, root, num_classes=157, cache=True):
@@ -84,7 +98,10 @@ class Charades(torch.utils.data.Dataset):
     object with randomize_parameters(c_size) and clip(frames_u8)); `device` is where the frames are processed."""
 
     def __init__(self, split_file, split, root, spatial_transform=None, task="class", frames=80, gamma_tau=5, crops=1,
-                 extract_feat=False, device="cuda", cache=True):
+                 extract_feat=False, device="cuda", cache=True, decode="pil", host_items=False):
+        if decode not in ("pil", "nvjpeg"):
+            raise ValueError("decode must be 'pil' (host, as the reference) or 'nvjpeg' (GPU)")
+        self.decode, self.host_items, self._decoder = decode, host_items, None
         self.data = make_dataset(split_file, split, root, cache=cache)
         self.split_file = split_file
         self.root = root
@@ -114,14 +131,17 @@ class Charades(torch.utils.data.Dataset):
         -> dict(frames uint8 [T,H,W,3], label, vid, frame_count, start_f, stride_f, meta int64 [4])."""
         vid, full_label, _, nf = self.data[index]
         start, count, stride = self.plan(nf)
-        decoded = load_rgb_frames(self.root, vid, start, count, stride)
+        if self.decode == "nvjpeg":                                       # undecoded streams: the GPU decodes the whole clip at once
+            decoded = video_loader(self.root, vid, list(range(start, start + count, stride)), image_loader=bytes_loader)
+        else:
+            decoded = load_rgb_frames(self.root, vid, start, count, stride)
         window = torch.from_numpy(np.ascontiguousarray(full_label[:, start - 1:start - 1 + count]))
         if self.task == "class":
             window = window.max(dim=1).values                             # clip-level label: any frame positive
         g = self.gamma_tau
         meta = torch.tensor([start // g, count // g, nf // g, stride // g], dtype=torch.int64)      # charades_fine.py:193-194
-        return dict(frames=np.stack(decoded, 0), label=window, vid=vid, frame_count=count, start_f=start, stride_f=stride,
-                    meta=meta)
+        frames = list(decoded) if self.decode == "nvjpeg" else np.stack(decoded, 0)
+        return dict(frames=frames, label=window, vid=vid, frame_count=count, start_f=start, stride_f=stride, meta=meta, index=index)
 
     def view_indices(self, n_decoded, frame_count):
         """Frame positions (into the decoded clip) of every view of the item (charades_fine.py:174-191): one view holding all
@@ -148,14 +168,45 @@ class Charades(torch.utils.data.Dataset):
             label = label[:, :(frame_count // self.gamma_tau) * self.gamma_tau]
         return clips, label
 
-    def __getitem__(self, index):
-        """-> (clips [N,3,T,S,S] fp32 on `device`, label, vid), as the reference's (charades_fine.py:196)."""
+    def frames_on_device(self, s):
+        """Decoded frames of a sample as ONE uint8 CUDA tensor [T,H,W,3]: host->device copy of PIL's output, or the nvJPEG
+        batched decode of the undecoded streams."""
+        if isinstance(s["frames"], list):
+            if self._decoder is None:
+                from .jpeg import JpegDecoder
+                self._decoder = JpegDecoder()
+            return self._decoder.decode(s["frames"], device=self.device)
+        return torch.from_numpy(s["frames"]).to(self.device, non_blocking=True)
+
+    def host_item(self, index):
+        """Everything of __getitem__ that needs no GPU, with the reference's `random` draw order: the window first
+        (sample), then the transform's parameters (charades_fine.py:147-170) -- shipped as plain numbers."""
         s = self.sample(index)
-        frames_u8 = torch.from_numpy(s["frames"]).to(self.device, non_blocking=True)
         self.spatial_transform.randomize_parameters(224)                  # charades_fine.py:170 (224 is hard-coded there)
-        imgs_l = self.spatial_transform.clip(frames_u8)                   # [3,T,S,S]: 171-172 in one kernel
+        s["tstate"] = self.spatial_transform.get_state()
+        return s
+
+    def finish(self, s):
+        """Device half of an item: decode / upload -> clip kernel (171-172 in one launch) -> views."""
+        self.spatial_transform.set_state(s["tstate"])
+        imgs_l = self.spatial_transform.clip(self.frames_on_device(s))    # [3,T,S,S]
         clips, label = self.views(imgs_l, s["label"], s["frame_count"])
         return clips, label, s["vid"]
+
+    def __getitem__(self, index):
+        """-> (clips [N,3,T,S,S] fp32 on `device`, label, vid), as the reference's (charades_fine.py:196); with
+        host_items=True the host half only (a dict; finish it with device_collate in the main process)."""
+        s = self.host_item(index)
+        return s if self.host_items else self.finish(s)
+
+    def device_collate(self, batch):
+        """collate_fn for host_items=True: runs in the main process."""
+        return mt_collate_fn([self.finish(s) for s in batch])
+
+    def __getstate__(self):                                               # the nvJPEG decoder does not travel to worker processes
+        d = dict(self.__dict__)
+        d["_decoder"] = None
+        return d
 
 
 def mt_collate_fn(batch):

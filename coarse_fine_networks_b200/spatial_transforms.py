@@ -140,6 +140,24 @@ class Compose:
         for t in self.transforms:
             t.randomize_parameters(c_size, index)
 
+    def get_state(self):
+        """The current random draw as plain numbers: a loader WORKER draws (same `random` order as the reference) and ships
+        this with the undecoded frames; the main process restores it with set_state() before clip()."""
+        c, f = self._crop, self._flip
+        st = {"size": int(c.size)}
+        if isinstance(c, MultiScaleRandomCropMultigrid):
+            st.update(scale=float(c.scale), tl_x=float(c.tl_x), tl_y=float(c.tl_y))
+        if f is not None:
+            st["flip_p"] = float(f.p)
+        return st
+
+    def set_state(self, st):
+        c, f = self._crop, self._flip
+        if isinstance(c, MultiScaleRandomCropMultigrid):
+            c.size, c.scale, c.tl_x, c.tl_y = st["size"], st["scale"], st["tl_x"], st["tl_y"]
+        if f is not None:
+            f.p = st["flip_p"]
+
     # ------------------------------------------------------------------------------------------------------
     def _lut_on(self, device):
         key = str(device)

@@ -478,6 +478,21 @@ int cf_block_maxpool_bwd(const float* dout, const int32_t* idx, float* dx, int B
                          cudaStream_t stream);
 
 /* ====================================================================================== */
+/* GPU JPEG decode (loader input)                                        */
+/* ====================================================================================== */
+/* Replaces the per-frame host decode of the reference's loaders (charades_fine.py:22-27 pil_loader, :46-56
+ * video_loader, :78-101 load_rgb_frames): the JPEG streams of a clip are decoded by nvJPEG's batched decoder straight
+ * into the uint8 [n,H,W,3] device tensor cf_clip_preprocess reads.  The decoder object owns the nvJPEG handle / state
+ * (nvJPEG is dlopen'ed at creation; it allocates its own scratch memory); one decoder per host thread.
+ * `data[i]` / `lengths[i]` are HOST pointers to the i-th JPEG stream; every stream must decode to H x W.
+ * Decoded pixels follow the JPEG standard but are not bit-identical to libjpeg-turbo's (see tests/test_jpeg_gpu.py). */
+int cf_jpeg_create(void** decoder);
+int cf_jpeg_destroy(void* decoder);
+int cf_jpeg_image_info(void* decoder, const unsigned char* data, size_t length, int* height, int* width, int* components);
+int cf_jpeg_decode_batch(void* decoder, const unsigned char* const* data, const size_t* lengths, int n, unsigned char* out, int H,
+                         int W, cudaStream_t stream);
+
+/* ====================================================================================== */
 /* Training-step glue                                                                       */
 /* ====================================================================================== */
 /* Charades localisation loss of the scripts (train_fine.py:199-212,226; train_coarse_fineFEAT.py:226-247):

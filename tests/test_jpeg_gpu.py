@@ -1,0 +1,146 @@
+"""GPU JPEG decode (cf_jpeg_decode_batch, nvJPEG batched decoder) against PIL's host decode (the reference's pil_loader,
+charades_fine.py:22-26), and the loaders with decode="nvjpeg" / host_items=True behind a multi-worker DataLoader.
+
+Tolerance.  nvJPEG and libjpeg-turbo are both conforming baseline-JPEG decoders with different IDCT / chroma up-sampling /
+colour-conversion arithmetic, so decoded pixels are close but not bit-identical.  Stated and checked here, on 8-bit values:
+mean absolute difference <= 1.0, 99.9 % of the pixels within 6, every pixel within 32 (4:2:0 chroma edges are the tail)."""
+import io
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "charades_loader.npz")
+SCALES = [224 / 256., 224 / 320.]
+
+
+@pytest.fixture(scope="module")
+def J():
+    import __graft_entry__ as ge
+    ge.build()
+    from coarse_fine_networks_b200 import jpeg
+    return jpeg
+
+
+def pil_decode(blob):
+    from PIL import Image
+    with Image.open(io.BytesIO(blob)) as im:
+        return np.asarray(im.convert("RGB"))
+
+
+def smooth_frames(T, H, W, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    out = np.empty((T, H, W, 3), np.uint8)
+    for t in range(T):
+        for c in range(3):
+            ph = rng.uniform(0, 6.28, 3)
+            base = 127.5 + 80 * np.sin(xx * (0.05 + 0.03 * c) + ph[0] + 0.3 * t) * np.cos(yy * (0.04 + 0.02 * c) + ph[1]) \
+                + 40 * np.sin((xx + yy) * 0.21 + ph[2])
+            out[t, ..., c] = np.clip(base + rng.integers(-12, 13, (H, W)), 0, 255).astype(np.uint8)
+    return out
+
+
+def stats(a, b):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return float(d.mean()), float(np.quantile(d, 0.999)), int(d.max())
+
+
+@pytest.mark.parametrize("H,W,quality,subsampling", [(240, 320, 90, 2), (240, 320, 75, 2), (270, 480, 95, 0), (48, 64, 90, 1)])
+def test_decode_batch_vs_pil(J, H, W, quality, subsampling):
+    from PIL import Image
+    frames = smooth_frames(5, H, W, seed=H + quality)
+    blobs = []
+    for t in range(frames.shape[0]):
+        buf = io.BytesIO()
+        Image.fromarray(frames[t]).save(buf, format="JPEG", quality=quality, subsampling=subsampling)
+        blobs.append(buf.getvalue())
+    dec = J.JpegDecoder()
+    assert dec.image_size(blobs[0]) == (H, W)
+    out = dec.decode(blobs)
+    assert out.shape == (5, H, W, 3) and out.dtype == torch.uint8 and out.is_cuda
+    ref = np.stack([pil_decode(b) for b in blobs], 0)
+    mean, q999, mx = stats(out.cpu().numpy(), ref)
+    print(f"nvJPEG vs PIL {H}x{W} q{quality} ss{subsampling}: mean |d| {mean:.3f}, 99.9% {q999:.0f}, max {mx}")
+    assert mean <= 1.0 and q999 <= 6 and mx <= 32, (mean, q999, mx)
+    # a second batch of another size through the same decoder (state re-initialised), decoded into a caller-owned tensor
+    dst = torch.empty(2, H, W, 3, device="cuda", dtype=torch.uint8)
+    out2 = dec.decode(blobs[1:3], out=dst)
+    assert out2.data_ptr() == dst.data_ptr() and torch.equal(out2, out[1:3])
+    dec.close()
+
+
+def test_decode_errors(J):
+    dec = J.JpegDecoder()
+    with pytest.raises(RuntimeError):
+        dec.decode([b"this is not a jpeg stream, by a long way"])
+    from PIL import Image
+    blobs = []
+    for hw in ((32, 48), (48, 32)):
+        buf = io.BytesIO()
+        Image.fromarray(np.zeros(hw + (3,), np.uint8)).save(buf, format="JPEG")
+        blobs.append(buf.getvalue())
+    with pytest.raises(RuntimeError, match="expected"):
+        dec.decode(blobs)                                   # frames of one clip must share a size
+
+
+@pytest.fixture(scope="module")
+def env(tmp_path_factory):
+    from coarse_fine_networks_b200 import charades_fine as L
+    from coarse_fine_networks_b200 import spatial_transforms as ST
+    g = np.load(GOLD)
+    tmp = tmp_path_factory.mktemp("charades_gpu")
+    root = os.path.join(tmp, "frames")
+    blob, off = g["jpeg_bytes"], 0
+    for name, size in zip(g["jpeg_names"], g["jpeg_sizes"]):
+        path = os.path.join(root, str(name))
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            f.write(blob[off:off + int(size)].tobytes())
+        off += int(size)
+    split_file = os.path.join(tmp, "split.json")
+    with open(split_file, "w") as f:
+        f.write(str(g["split_json"]))
+    mean, std = list(g["mean"]), list(g["std"])
+    mk = lambda: ST.Compose([ST.MultiScaleRandomCropMultigrid(SCALES, 224), ST.RandomHorizontalFlip(), ST.ToTensor(255),
+                             ST.Normalize(mean, std)])
+    return type("E", (), dict(L=L, ST=ST, root=root, split_file=split_file, mk=mk, std=std))
+
+
+def test_loader_nvjpeg_matches_pil_path(J, env):
+    """Same seed, same item: the clip decoded by nvJPEG equals the PIL-decoded one up to the decoder tolerance (in units of
+    the normalised output 1 grey level = 1 / (255 * std) ~ 0.03)."""
+    kw = dict(task="class", frames=80, gamma_tau=5, crops=1, cache=False)
+    d_pil = env.L.Charades(env.split_file, "training", env.root, env.mk(), decode="pil", **kw)
+    d_gpu = env.L.Charades(env.split_file, "training", env.root, env.mk(), decode="nvjpeg", **kw)
+    for seed in (3, 12):
+        random.seed(seed)
+        a, la, va = d_pil[seed % 2]
+        random.seed(seed)
+        b, lb, vb = d_gpu[seed % 2]
+        assert a.shape == b.shape and va == vb and torch.equal(la, lb)
+        d = (a - b).abs() * 255 * min(env.std)
+        assert float(d.mean()) <= 1.0 and float(d.max()) <= 40, (float(d.mean()), float(d.max()))
+
+
+def test_host_items_behind_a_multi_worker_dataloader(J, env):
+    """host_items=True: workers do the host half only (no CUDA in forked workers), the main process finishes items in
+    device_collate; the batch equals the one built item by item with the same per-item seeds."""
+    kw = dict(task="class", frames=80, gamma_tau=5, crops=1, cache=False, decode="nvjpeg")
+    ds = env.L.Charades(env.split_file, "training", env.root, env.mk(), host_items=True, **kw)
+
+    def seed_worker(_):
+        random.seed(1234)
+    dl = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, num_workers=2, pin_memory=False, collate_fn=ds.device_collate,
+                                     worker_init_fn=seed_worker)
+    clips, labels, masks, vids = next(iter(dl))
+    assert clips.is_cuda and clips.shape[0] == 2 and clips.shape[2] == 3 and labels.shape[0] == 2 and len(vids) == 2
+    ref = env.L.Charades(env.split_file, "training", env.root, env.mk(), host_items=False, **kw)
+    random.seed(1234)
+    items = [ref[0], ref[1]]
+    want = env.L.mt_collate_fn(items)
+    assert tuple(want[3]) == tuple(vids) and torch.equal(want[1], labels) and torch.equal(want[2], masks)
+    assert torch.equal(want[0], clips)
