@@ -10,7 +10,9 @@ rank, BatchNorm statistics stay per rank exactly as under the reference's nn.Dat
 import torch
 import torch.distributed as dist
 
-from ._lib import call, ptr, stream_ptr
+import ctypes
+
+from ._lib import call, lib, ptr, stream_ptr
 
 FUSION_LR_MULT = 10.0        # train_coarse_fineFEAT.py:141
 
@@ -59,6 +61,34 @@ def is_fusion_param(name):
     return "rw" in name or "mix" in name
 
 
+class NativeComm:
+    """The C ABI's communicator (cf_comm_*: NCCL resolved with dlopen inside libcfnet_b200.so): ONE in-place fp32 sum
+    all-reduce of the flat gradient per step.  The 128-byte NCCL id is created on rank 0 and handed to the other ranks
+    through torch.distributed's object broadcast (any initialised backend, gloo is enough) -- the only use of
+    torch.distributed on this path."""
+
+    def __init__(self, process_group=None):
+        self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        buf = (ctypes.c_ubyte * 128)()
+        if self.rank == 0:
+            call("cf_comm_unique_id", ctypes.cast(buf, ctypes.c_void_p))
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
+        ident = (ctypes.c_ubyte * 128).from_buffer_copy(box[0])
+        self._h = ctypes.c_void_p()
+        call("cf_comm_init", ctypes.cast(ctypes.byref(self._h), ctypes.c_void_p), self.world, self.rank,
+             ctypes.cast(ident, ctypes.c_void_p))
+
+    def allreduce(self, flat):
+        call("cf_comm_allreduce", self._h, ptr(flat), flat.numel(), stream_ptr())
+
+    def close(self):
+        if self._h.value:
+            lib.cf_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+
 class FlatTrainer:
     """Owns ONE flat fp32 buffer each for parameters, gradients and momentum of a set of modules.
 
@@ -69,7 +99,10 @@ class FlatTrainer:
     also re-zeroes the gradient buffer.  Base parameters come first, fusion ('rw'/'mix') parameters
     last, so the two learning-rate groups are two contiguous ranges."""
 
-    def __init__(self, modules, lr, momentum=0.9, weight_decay=1e-5, fusion_lr_mult=FUSION_LR_MULT, process_group=None):
+    def __init__(self, modules, lr, momentum=0.9, weight_decay=1e-5, fusion_lr_mult=FUSION_LR_MULT, process_group=None,
+                 native_comm=False):
+        """native_comm=True: the gradient all-reduce goes through the C ABI's own NCCL communicator (cf_comm_allreduce)
+        instead of torch.distributed.all_reduce (same NCCL, same result)."""
         named = []
         for mi, m in enumerate(modules):
             named += [(f"{mi}.{n}", p) for n, p in m.named_parameters() if p.requires_grad]
@@ -103,11 +136,15 @@ class FlatTrainer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.n_params = sum(p.numel() for p in self.params)
+        self.comm = NativeComm(process_group) if (native_comm and self.world > 1 and dev.type == "cuda") else None
 
     def allreduce(self):
         """The one collective of the data-parallel step: sum of the flat gradient over all ranks."""
         if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            if self.comm is not None:
+                self.comm.allreduce(self.flat_g)
+            else:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
 
     def lrs(self):
         """(base-group lr, fusion-group lr) the next update uses."""

@@ -505,6 +505,16 @@ int cf_jpeg_decode_batch(void* decoder, const unsigned char* const* data, const 
 int cf_charades_loss(const float* logits, const float* labels, const float* masks, float* loss2, float* dlogits, int B, int C,
                      int T, int TL, float scale, int align_corners, cudaStream_t stream);
 
+/* The data-parallel collective: one NCCL communicator per process / GPU behind an opaque handle and one
+ * in-place fp32 SUM all-reduce of the flat gradient buffer per step over NVLink / NVSwitch -- replaces nn.DataParallel's
+ * per-step broadcast / gather / reduce-add (train_fine.py:122-123, train_coarse_fineFEAT.py:129-130).  NCCL is dlopen'ed
+ * (libnccl.so.2).  cf_comm_unique_id fills 128 bytes on ONE rank; the caller hands them to the other ranks (host side),
+ * then every rank calls cf_comm_init with its current CUDA device set.  The 1/world factor lives in cf_sgd_flat. */
+int cf_comm_unique_id(void* id128);
+int cf_comm_init(void** comm, int world, int rank, const void* id128);
+int cf_comm_allreduce(void* comm, float* buf, int64_t n, cudaStream_t stream);
+int cf_comm_destroy(void* comm);
+
 /* fused SGD with momentum over flat fp32 buffers (optim.SGD, train_fine.py:130): g = grad_scale*g + wd*p;
  * v = momentum*v + g; p -= lr*v; g = 0.  Elements [0,n_split) use lr0, the rest lr1 (the 'rw'/'mix'
  * parameter group at 10x, train_coarse_fineFEAT.py:137-141).  grad_scale = 1/world folds the
