@@ -48,6 +48,18 @@ struct CfOncePerDevice {
     }
 };
 
+// Experiment switches (environment variables selecting a replaced kernel variant for same-box A/B runs) exist only in the
+// -DCFNET_AB build (python -m coarse_fine_networks_b200.build --ab); the shipped library reads no environment.
+#ifdef CFNET_AB
+#include <stdlib.h>
+static inline int cf_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+#else
+static inline int cf_env(const char*, int dflt) { return dflt; }
+#endif
+
 static inline int cf_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline long long cf_cdiv64(long long a, long long b) { return (a + b - 1) / b; }
 

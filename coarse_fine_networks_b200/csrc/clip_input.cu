@@ -312,8 +312,7 @@ extern "C" int cf_clip_preprocess(const uint8_t* frames, float* out, const int* 
     a.ksize_h = ksize_h; a.ksize_v = ksize_v; a.flip = flip ? 1 : 0; a.rows_max = rows_max; a.out_stride_c = out_stride_c;
     // CFNET_CLIP_SPLIT=1 selects the two-group variant (A/B only: it lost the same-box comparison, 313 vs 272 us -- the kernel is
     // bound by the L1/LSU data pipe (byte loads, table look-ups), not by exposed load latency)
-    static int want_split = -1;
-    if (want_split < 0) { const char* e = getenv("CFNET_CLIP_SPLIT"); want_split = (e && e[0] == '1') ? 1 : 0; }
+    const int want_split = cf_env("CFNET_CLIP_SPLIT", 0);
     size_t smem = clip_smem_bytes(size, rows_max, ksize_v, 2);
     const bool split = want_split && smem <= 200 * 1024;               // two thread groups + double-buffered tile
     if (!split) smem = clip_smem_bytes(size, rows_max, ksize_v, 1);

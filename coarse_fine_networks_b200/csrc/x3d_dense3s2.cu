@@ -136,9 +136,7 @@ __global__ void __launch_bounds__(DG_THREADS) dense3_s2_dgrad_kernel(const DgArg
 
 // -1: not this kernel's problem (the caller falls through to the generic scatter path)
 int cf_dense_s2_dgrad_try(const cf_pw_args* a, cudaStream_t stream) {
-    static int off = -1;
-    if (off < 0) { const char* e = getenv("CFNET_DENSE_DGRAD_OFF"); off = (e && e[0] == '1') ? 1 : 0; }
-    if (off) return -1;
+    if (cf_env("CFNET_DENSE_DGRAD_OFF", 0)) return -1;
     const cf_geom& g = a->g;
     if (!a->scatter_out || a->accumulate || a->bias || a->stats_mode != CF_STATS_NONE || a->epi_mode != CF_EPI_NONE) return -1;
     if (!(g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 2 && g.sh == 2 && g.sw == 2 && g.pt == 1 && g.ph == 1 && g.pw == 1)) return -1;
@@ -295,9 +293,7 @@ __global__ void __launch_bounds__(FW_THREADS) dense3_s2_fwd_kernel(const FwArgs 
 
 // -1: not this kernel's problem (the caller falls through to the generic gathered GEMM)
 int cf_dense_s2_fwd_try(const cf_pw_args* a, cudaStream_t stream) {
-    static int off = -1;
-    if (off < 0) { const char* e = getenv("CFNET_DENSE_FWD_OFF"); off = (e && e[0] == '1') ? 1 : 0; }
-    if (off) return -1;
+    if (cf_env("CFNET_DENSE_FWD_OFF", 0)) return -1;
     const cf_geom& g = a->g;
     if (!a->gather_in || a->accumulate || a->epi_mode != CF_EPI_NONE || a->aux) return -1;
     if (a->stats_mode != CF_STATS_NONE && a->stats_mode != CF_STATS_SUM_SQ) return -1;
@@ -465,9 +461,7 @@ __global__ void __launch_bounds__(WG3_THREADS, 2) dense3_s2_wgrad_kernel(const W
 
 // -1: not this kernel's problem (the caller falls through to the generic gathered weight gradient)
 int cf_dense_s2_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream) {
-    static int off = -1;
-    if (off < 0) { const char* e = getenv("CFNET_DENSE_WGRAD_OFF"); off = (e && e[0] == '1') ? 1 : 0; }
-    if (off) return -1;
+    if (cf_env("CFNET_DENSE_WGRAD_OFF", 0)) return -1;
     const cf_geom& g = a->g;
     if (!a->gather_in) return -1;
     if (!(g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 2 && g.sh == 2 && g.sw == 2 && g.pt == 1 && g.ph == 1 && g.pw == 1)) return -1;

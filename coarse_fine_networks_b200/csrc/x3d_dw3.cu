@@ -380,12 +380,7 @@ static int d3_launch(const cf_dw_args* a, const D3Params& p, cudaStream_t stream
 
 // returns CF_OK when launched, -1 when not eligible (the caller runs the general kernels of x3d_dw.cu)
 int cf_dw3_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
-    static int disabled = -1;
-    if (disabled < 0) {
-        const char* e = getenv("CFNET_DW3_OFF");
-        disabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (disabled) return -1;
+    if (cf_env("CFNET_DW3_OFF", 0)) return -1;
     const cf_geom& g = a->g;
     if (!(g.kt == 3 && g.kh == 3 && g.kw == 3 && g.pt == 1 && g.ph == 1 && g.pw == 1 && g.st == 1 && g.sh == 1 && g.sw == 1)) return -1;
     if (g.T != g.Ti || g.H != g.Hi || g.W != g.Wi) return -1;
@@ -399,8 +394,7 @@ int cf_dw3_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (mode == D3_DGRAD && a->stats_mode == CF_STATS_SUM_SQ) return -1;
     D3Params p;
     p.B = a->B; p.C = a->C; p.T = g.T; p.H = g.H; p.W = g.W;
-    static int force_npw = -1;                                     // CFNET_DW3_NPW=1|2: tile width experiment
-    if (force_npw < 0) { const char* e = getenv("CFNET_DW3_NPW"); force_npw = e ? atoi(e) : 0; }
+    const int force_npw = cf_env("CFNET_DW3_NPW", 0);                // tile width experiment (-DCFNET_AB build only)
     const int npw = (g.W == 7 || force_npw == 1) ? 1 : 2;
     p.htiles = (g.H + D3_TH - 1) / D3_TH;
     p.wtiles = g.W / (D3_PW * npw);

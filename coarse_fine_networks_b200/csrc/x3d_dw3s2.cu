@@ -544,12 +544,7 @@ static int s2_launch(const cf_dw_args* a, const S2Params& p, cudaStream_t stream
 
 // mode: 0 forward, 1 data gradient, 2 weight gradient.  Returns CF_OK when launched, -1 when not eligible.
 int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
-    static int disabled = -1;
-    if (disabled < 0) {
-        const char* e = getenv("CFNET_DW3_OFF");
-        disabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (disabled) return -1;
+    if (cf_env("CFNET_DW3_OFF", 0)) return -1;
     const cf_geom& g = a->g;
     if (!(g.kt == 3 && g.kh == 3 && g.kw == 3 && g.pt == 1 && g.ph == 1 && g.pw == 1 && g.st == 1 && g.sh == 2 && g.sw == 2)) return -1;
     if (g.T != g.Ti || g.H != (g.Hi - 1) / 2 + 1 || g.W != (g.Wi - 1) / 2 + 1) return -1;

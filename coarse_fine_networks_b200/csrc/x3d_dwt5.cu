@@ -147,12 +147,7 @@ __global__ void __launch_bounds__(256) dwt5_kernel(const cf_dw_args a, const T5P
 
 // mode: 0 forward, 1 data gradient, 2 weight gradient.  Returns CF_OK when launched, -1 when not eligible.
 int cf_dwt5_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
-    static int disabled = -1;
-    if (disabled < 0) {
-        const char* e = getenv("CFNET_DWT5_OFF");
-        disabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (disabled) return -1;
+    if (cf_env("CFNET_DWT5_OFF", 0)) return -1;
     const cf_geom& g = a->g;
     if (!(g.kt == 5 && g.kh == 1 && g.kw == 1 && g.pt == 2 && g.ph == 0 && g.pw == 0 && g.st == 1 && g.sh == 1 && g.sw == 1)) return -1;
     if (g.T != g.Ti || g.H != g.Hi || g.W != g.Wi) return -1;

@@ -127,14 +127,6 @@ static int p2_sm_count() {
     return n;
 }
 
-#ifdef CFNET_AB          /* A/B switches are compiled in only for experiments (-DCFNET_AB); the shipped library reads no environment */
-static int p2_env(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-#else
-static int p2_env(const char*, int dflt) { return dflt; }
-#endif
 
 // debug: cycle counters of CTA 0 of the last persistent launch (built with -DCFNET_P2_TIMING -DCFNET_AB, CFNET_PW_TC_TIMING=1)
 extern "C" int cf_pw_tc_debug_read(long long* out16) {
@@ -181,7 +173,7 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     memset(&tmx, 0, sizeof(tmx));
     memset(&tmx2, 0, sizeof(tmx2));
     p.tma = 0; p.fold = 1; p.nraw = 0; p.raw_in_bytes = p.raw_stage_bytes = p.raw_off = 0;
-    if (p.gmode == 0 && p2_env("CFNET_P2_TMA", 1)) {
+    if (p.gmode == 0 && cf_env("CFNET_P2_TMA", 1)) {
         const int fold = (K % 4 == 0) ? 1 : ((K % 2 == 0) ? 2 : 4);
         if ((fold == 1 || K <= 64) && cf_make_row_tmap(&tmx, a->x, a->B, p.R, K, fold) &&
             (!x2 || cf_make_row_tmap(&tmx2, a->x2, a->B, p.R, K, fold))) {
@@ -275,8 +267,8 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
         attr_done.mark();
     }
     long long grid = p.total_tiles < p2_sm_count() ? p.total_tiles : p2_sm_count();
-    p.timing = p2_env("CFNET_PW_TC_TIMING", 0);
-    p.dbg_1x = p2_env("CFNET_PW_TC_1X", 0);
+    p.timing = cf_env("CFNET_PW_TC_TIMING", 0);
+    p.dbg_1x = cf_env("CFNET_PW_TC_1X", 0);
     p.g_j = (int)(grid % p.ntiles);
     p.g_rt = (int)(grid / p.ntiles);
     p2w8::pw_tc2_kernel<<<(unsigned)grid, (8 + 4 + 8) * 32, smem, stream>>>(*a, a->wpack, p, av, ev, tmx, tmx2);

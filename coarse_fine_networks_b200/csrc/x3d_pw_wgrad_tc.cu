@@ -505,14 +505,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
 }
 
 // ---------------------------------------------------------------------------------------
-#ifdef CFNET_AB          /* experiment switches exist only in the -DCFNET_AB build; the shipped library reads no environment */
-static int wg_env(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-#else
-static int wg_env(const char*, int dflt) { return dflt; }
-#endif
 
 static int wg_sm_count() {
     static int n = 0;
@@ -527,7 +519,7 @@ static int wg_sm_count() {
 
 // returns CF_OK when launched, -1 when the problem is not eligible (the caller runs the CUDA-core kernel)
 int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
-    if (wg_env("CFNET_PW_WGRAD_SIMT", 0)) return -1;
+    if (cf_env("CFNET_PW_WGRAD_SIMT", 0)) return -1;
     const int N = a->N, K = a->K;
     if (a->dbias || (N & 1) || (K & 1) || N > 512 || K > 512) return -1;
     if (a->gather_in && !(a->g.kt == 1 && a->g.kh == 1 && a->g.kw == 1 && a->g.pt == 0 && a->g.ph == 0 && a->g.pw == 0 && a->g.ch_stride == 1 &&
@@ -552,7 +544,7 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     {
         const long long cost0 = (long long)((N + 127) / 128) * 128 * ((K + 31) / 32 * 32);
         const long long cost1 = (long long)((K + 127) / 128) * 128 * ((N + 31) / 32 * 32);
-        p.swap = (cost1 < cost0 && !wg_env("CFNET_WG_NOSWAP", 0)) ? 1 : 0;
+        p.swap = (cost1 < cost0 && !cf_env("CFNET_WG_NOSWAP", 0)) ? 1 : 0;
     }
     const int Msz = p.swap ? K : N, Csz = p.swap ? N : K;
     const int mtiles = (Msz + 127) / 128;
@@ -583,7 +575,7 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     const bool aff2 = a->dy_mode == CF_PRO_AFFINE2;
     p.tma = 0; p.fold_dy = p.fold_x = 1; p.nraw = 0; p.raw_dy_bytes = p.raw_x_bytes = p.raw_stage_bytes = p.raw_off = 0;
     bool planned = false;
-    if (!p.gmode && wg_env("CFNET_WG_TMA", 1)) {
+    if (!p.gmode && cf_env("CFNET_WG_TMA", 1)) {
         const int fdy = (N % 4 == 0) ? 1 : 2, fx = (K % 4 == 0) ? 1 : 2;
         // 54-channel tensors (rows that are not 16-byte multiples) would need the folded whole-tile copies and 8-byte
         // shared-memory reads: measured 2-4 % slower than the register-load producers on the layer-1 shapes (same-box A/B,
@@ -611,7 +603,7 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
         }
     }
     if (!planned) {
-        int rb0 = wg_env("CFNET_WG_RB", 64);
+        int rb0 = cf_env("CFNET_WG_RB", 64);
         if (rb0 != 16 && rb0 != 32) rb0 = 64;
         p.RB = rb0;                                          // rows per stage: as many as leave >= 2 stages (per-stage overhead amortised)
         for (;;) {

@@ -158,12 +158,7 @@ static bool stem_geom_ok(const cf_geom& g, int K, int N) {
            g.pw == 1 && g.pos_stride == 1 && g.T == g.Ti && g.H == (g.Hi - 1) / 2 + 1 && g.W == (g.Wi - 1) / 2 + 1;
 }
 static bool stem_enabled() {
-    static int disabled = -1;
-    if (disabled < 0) {
-        const char* e = getenv("CFNET_STEM_OFF");
-        disabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    return !disabled;
+    return !cf_env("CFNET_STEM_OFF", 0);
 }
 static StemParams stem_params(int B, const cf_geom& g) {
     StemParams p;

@@ -4,8 +4,6 @@ cf_dw_conv_*, cf_bn_*, cf_se_*, cf_residual_*, cf_block_avgpool_*).
 Activations are channels-last fp32 ([B,C,T,H,W] logical shape, torch.channels_last_3d strides);
 BatchNorm / ReLU / SE / Swish never materialise: producers accumulate statistics, consumers
 apply per-(sample,channel) affine tables on load (see include/cfnet_b200.h)."""
-import os
-
 import torch
 
 from ._lib import STRUCTS, call, call_struct, lib, make, ptr, stream_ptr
@@ -40,9 +38,9 @@ def geom(T, H, W, Ti=None, Hi=None, Wi=None, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 
     return g
 
 
-# Dense pointwise GEMMs run on the tcgen05 tensor cores (3xTF32).  CFNET_PW_SIMT=1 forces the fp32 CUDA-core
-# kernel (used by the tests to cross-check the two paths; not a fallback: both are sm_100a kernels of the library).
-USE_TC = os.environ.get("CFNET_PW_SIMT", "0") != "1"
+# Dense pointwise GEMMs run on the tcgen05 tensor cores (3xTF32); pw_conv(..., tc=False) selects the fp32 CUDA-core kernel
+# (used by the tests to cross-check the two paths; not a fallback: both are sm_100a kernels of the library).
+USE_TC = True
 
 
 def pw_conv(x, w, y, B, K, N, g, *, w_sn=None, w_sk=1, x2=None, bias=None, pro=PRO_NONE, pro_tabs=(None, None, None),

@@ -49,3 +49,18 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_shipped_library_reads_no_environment():
+    """include/cfnet_b200.h promises no global state: experiment switches (getenv) may exist only inside the -DCFNET_AB
+    helper of cf_common.cuh; no other source file of the library calls getenv."""
+    import glob
+    import re
+    csrc = os.path.join(ROOT, "coarse_fine_networks_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh"))):
+        txt = re.sub(r"//[^\n]*", "", open(f).read())
+        if os.path.basename(f) == "cf_common.cuh":
+            inside = re.search(r"#ifdef CFNET_AB(.*?)#else", txt, flags=re.S).group(1)
+            assert txt.count("getenv(") == inside.count("getenv(") == 1
+        else:
+            assert "getenv(" not in txt, f
