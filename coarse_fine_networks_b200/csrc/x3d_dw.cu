@@ -699,12 +699,33 @@ extern "C" int cf_dw_conv_fwd(const cf_dw_args* a, cudaStream_t stream) {
     return launch_dw_fwd<1>(a, stream);
 }
 
+extern "C" int cf_dw_conv_wgrad(const cf_dw_args* a, cudaStream_t stream);
+static int dw_dgrad_impl(const cf_dw_args* a, cudaStream_t stream);
+
 extern "C" int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     int rc = dw_common_checks(a);
     if (rc) return rc;
     CF_CHECK_ARG(a->epi_mode == CF_EPI_NONE || (a->epi_mode == CF_EPI_DRELU && a->aux && a->epi_a && a->epi_b), "bad epilogue");
     CF_CHECK_ARG(a->stats_mode != CF_STATS_SUM_AUX || a->aux, "aux missing");
-    rc = cf_dw3_try(1, a, stream);
+    if (!a->dw_out) return dw_dgrad_impl(a, stream);
+    CF_CHECK_ARG(a->aux, "dw_out: aux (the forward input) missing");
+    rc = cf_env("CFNET_DW3_NOFUSE", 0) ? -1 : cf_dw3_try(3, a, stream);     // data gradient + weight gradient in one pass
+    if (rc >= 0) return rc;
+    cf_dw_args d = *a;
+    d.dw_out = nullptr;
+    rc = dw_dgrad_impl(&d, stream);
+    if (rc) return rc;
+    cf_dw_args w = *a;                                       // wgrad's contract: y = the weight gradient, act tables in epi_a / epi_b
+    w.y = a->dw_out;
+    w.dw_out = nullptr;
+    w.stats = nullptr;
+    w.stats_mode = CF_STATS_NONE;
+    w.epi_mode = CF_EPI_NONE;
+    return cf_dw_conv_wgrad(&w, stream);
+}
+
+static int dw_dgrad_impl(const cf_dw_args* a, cudaStream_t stream) {
+    int rc = cf_dw3_try(1, a, stream);
     if (rc >= 0) return rc;
     rc = cf_dw3s2_try(1, a, stream);
     if (rc >= 0) return rc;

@@ -15,6 +15,11 @@
 //             = the same kernel with flipped weights, d' = P*dU + Q*y2 + R (BatchNorm backward as an affine map)
 //   wgrad   : dw[c,dt,dh,dw] += sum_pos d'[t,h,w,c] * relu(a1*y1+b1)[t+dt-1,h+dh-1,w+dw-1,c]
 //             ring = activated y1 planes, d' read at the patch positions; 27 x 2 accumulators per thread
+//   fused   : the data-gradient pass also produces the weight gradient: substituting q = pos + tap - 1,
+//             dw[c,tap] = sum_q relu(a1*y1+b1)[q] * d'[q - tap + 1] -- the SAME d' neighbourhood values the data gradient
+//             multiplies with the flipped weights, times the activation at the output position q (the `aux` row the
+//             ReLU mask needs anyway).  One pass over (dU, y2, y1) instead of two: 27 more FMAs per output from registers,
+//             weights read from shared memory (their registers hold the 27 x 2 weight-gradient accumulators).
 #include "cf_common.cuh"
 #include "../../include/cfnet_b200.h"
 #include <stdlib.h>
@@ -25,7 +30,7 @@
 #define D3_TH 8                       /* tile rows = 4 patch rows of 2 */
 #define D3_HH (D3_TH + 2)
 
-enum { D3_FWD = 0, D3_DGRAD = 1, D3_WGRAD = 2 };
+enum { D3_FWD = 0, D3_DGRAD = 1, D3_WGRAD = 2, D3_FUSED = 3 };   // FUSED: data gradient + weight gradient in one pass
 
 struct D3Params {
     int B, C, T, H, W;
@@ -54,7 +59,8 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
     float* ring = sm;                                              // [3][PLANE]
     float* stg0 = ring + 3 * PLANE;                                // raw plane of the first source tensor
     float* stg1 = stg0 + PLANE;                                    // raw plane of the second one (AFFINE2 only)
-    const bool two_src = MODE == D3_DGRAD && a.pro_mode == CF_PRO_AFFINE2;    // must match d3_launch's staging count
+    constexpr bool DG = MODE == D3_DGRAD || MODE == D3_FUSED;                  // data-gradient form of the ring
+    const bool two_src = DG && a.pro_mode == CF_PRO_AFFINE2;                   // must match d3_launch's staging count
     float* tabs = stg0 + (two_src ? 2 : 1) * PLANE;                // [5][54]: ring prologue a,b,c ; epilogue a,b
     float* ws = tabs + 5 * D3_CS;                                  // [27][54]
 
@@ -100,14 +106,14 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
                 rb = a.pro_b ? a.pro_b[tc] : 0.f;
                 rc = a.pro_c ? a.pro_c[tc] : 0.f;
             }
-            if (MODE == D3_DGRAD && a.epi_mode == CF_EPI_DRELU) { ea = a.epi_a[tc]; eb = a.epi_b[tc]; }
+            if (DG && a.epi_mode == CF_EPI_DRELU) { ea = a.epi_a[tc]; eb = a.epi_b[tc]; }
         }
         tabs[i] = ra; tabs[D3_CS + i] = rb; tabs[2 * D3_CS + i] = rc; tabs[3 * D3_CS + i] = ea; tabs[4 * D3_CS + i] = eb;
     }
     if (MODE != D3_WGRAD) {
         for (int i = tid; i < 27 * D3_CS; i += NT) {
             const int tap = i / D3_CS, c = i - tap * D3_CS;
-            ws[i] = a.w[(size_t)(cs0 + c) * 27 + (MODE == D3_DGRAD ? 26 - tap : tap)];     // dgrad = conv with the flipped stencil
+            ws[i] = a.w[(size_t)(cs0 + c) * 27 + (DG ? 26 - tap : tap)];     // dgrad = conv with the flipped stencil
         }
     }
     __syncthreads();
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
         for (int k = 0; k < KPT; ++k) {
             if (vmask & (1u << k)) {
                 d3_cp_async8(stg0 + soff0 + k * (NPATCH * D3_CS), f0 + goff[k]);
-                if (MODE == D3_DGRAD && f1) d3_cp_async8(stg1 + soff0 + k * (NPATCH * D3_CS), f1 + goff[k]);
+                if (DG && f1) d3_cp_async8(stg1 + soff0 + k * (NPATCH * D3_CS), f1 + goff[k]);
             }
         }
     };
@@ -176,10 +182,10 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
     auto slot = [&](int t) { return ring + ((t - t0 + 1) % 3) * PLANE; };     // plane t0-1 -> slot 0
 
     // ---- per-thread state
-    float2 wreg[27];                                              // FWD/DGRAD: weights; WGRAD: the 27 accumulators
+    float2 wreg[27];                                              // FWD/DGRAD: weights; WGRAD/FUSED: the 27 accumulators
 #pragma unroll
     for (int i = 0; i < 27; ++i)
-        wreg[i] = MODE == D3_WGRAD ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(ws + i * D3_CS + lane * 2);
+        wreg[i] = (MODE == D3_WGRAD || MODE == D3_FUSED) ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(ws + i * D3_CS + lane * 2);
     float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
     // WGRAD: raw output-gradient values (and the second BatchNorm-backward operand) of the NEXT frame's patch, loaded one
     // step ahead so that their latency hides behind the current frame's FMAs
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
         if (MODE != D3_WGRAD) {
             // aux (pre-activation at the output positions) for the dgrad mask / statistics: issue early
             float2 aux[2][D3_PW];
-            const bool need_aux = MODE == D3_DGRAD && (a.epi_mode == CF_EPI_DRELU || a.stats_mode == CF_STATS_SUM_AUX);
+            const bool need_aux = DG && (a.epi_mode == CF_EPI_DRELU || a.stats_mode == CF_STATS_SUM_AUX);
             if (need_aux) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
@@ -231,10 +237,18 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
                                                        : make_float2(0.f, 0.f);
             }
             float2 acc[2][D3_PW];
+            float2 actv[MODE == D3_FUSED ? 2 : 1][MODE == D3_FUSED ? D3_PW : 1];       // relu(a1*y1+b1) at the output positions
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int j = 0; j < D3_PW; ++j) acc[r][j] = make_float2(0.f, 0.f);
+                for (int j = 0; j < D3_PW; ++j) {
+                    acc[r][j] = make_float2(0.f, 0.f);
+                    if (MODE == D3_FUSED) {                        // rows outside the image hold aux = 0 -> masked explicitly
+                        const bool rv = h0 + oh0 + r < H;
+                        actv[MODE == D3_FUSED ? r : 0][MODE == D3_FUSED ? j : 0] =
+                            make_float2(rv ? fmaxf(fmaf(ea.x, aux[r][j].x, eb.x), 0.f) : 0.f, rv ? fmaxf(fmaf(ea.y, aux[r][j].y, eb.y), 0.f) : 0.f);
+                    }
+                }
 #pragma unroll
             for (int dt = 0; dt < 3; ++dt) {
                 const float* pl = pbase_thr + ((sl0 + dt) % 3) * PLANE;
@@ -249,11 +263,25 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
                         if (orow < 0 || orow > 1) continue;
 #pragma unroll
                         for (int dw = 0; dw < 3; ++dw) {
-                            const float2 wv = wreg[(dt * 3 + dh) * 3 + dw];
+                            if (MODE == D3_FUSED) {
+                                const int ti = (dt * 3 + dh) * 3 + dw;
+                                const float2 wv = *reinterpret_cast<const float2*>(ws + ti * D3_CS + lane * 2);
+                                float2 g = wreg[ti];
 #pragma unroll
-                            for (int j = 0; j < D3_PW; ++j) {
-                                acc[orow][j].x = fmaf(in[j + dw].x, wv.x, acc[orow][j].x);
-                                acc[orow][j].y = fmaf(in[j + dw].y, wv.y, acc[orow][j].y);
+                                for (int j = 0; j < D3_PW; ++j) {
+                                    acc[orow][j].x = fmaf(in[j + dw].x, wv.x, acc[orow][j].x);
+                                    acc[orow][j].y = fmaf(in[j + dw].y, wv.y, acc[orow][j].y);
+                                    g.x = fmaf(in[j + dw].x, actv[orow][j].x, g.x);
+                                    g.y = fmaf(in[j + dw].y, actv[orow][j].y, g.y);
+                                }
+                                wreg[ti] = g;
+                            } else {
+                                const float2 wv = wreg[(dt * 3 + dh) * 3 + dw];
+#pragma unroll
+                                for (int j = 0; j < D3_PW; ++j) {
+                                    acc[orow][j].x = fmaf(in[j + dw].x, wv.x, acc[orow][j].x);
+                                    acc[orow][j].y = fmaf(in[j + dw].y, wv.y, acc[orow][j].y);
+                                }
                             }
                         }
                     }
@@ -266,13 +294,13 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
 #pragma unroll
                 for (int j = 0; j < D3_PW; ++j) {
                     float2 v = acc[r][j];
-                    if (MODE == D3_DGRAD && a.epi_mode == CF_EPI_DRELU) {
+                    if (DG && a.epi_mode == CF_EPI_DRELU) {
                         v.x = fmaf(ea.x, aux[r][j].x, eb.x) > 0.f ? v.x : 0.f;
                         v.y = fmaf(ea.y, aux[r][j].y, eb.y) > 0.f ? v.y : 0.f;
                     }
                     *reinterpret_cast<float2*>(a.y + (orow_base + (size_t)r * W + j) * C + c0) = v;
                     s1.x += v.x; s1.y += v.y;
-                    if (MODE == D3_DGRAD) { s2.x = fmaf(v.x, aux[r][j].x, s2.x); s2.y = fmaf(v.y, aux[r][j].y, s2.y); }
+                    if (DG) { s2.x = fmaf(v.x, aux[r][j].x, s2.x); s2.y = fmaf(v.y, aux[r][j].y, s2.y); }
                     else { s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); }
                 }
             }
@@ -332,7 +360,8 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
 
     // ---- CTA reductions over the patches (same channels), then global atomics.  The ring is free now.
     float* red = ring;
-    if (MODE == D3_WGRAD) {
+    if (MODE == D3_WGRAD || MODE == D3_FUSED) {
+        float* dwp = MODE == D3_FUSED ? a.dw_out : a.y;
 #pragma unroll
         for (int i = 0; i < 27; ++i) *reinterpret_cast<float2*>(red + ((size_t)patch * 27 + i) * D3_CS + lane * 2) = wreg[i];
         __syncthreads();
@@ -341,9 +370,11 @@ __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_arg
 #pragma unroll
             for (int q = 0; q < NPATCH; ++q) s += red[(size_t)q * 27 * D3_CS + i];
             const int tap = i / D3_CS, c = i - tap * D3_CS;
-            atomicAdd(a.y + (size_t)(cs0 + c) * 27 + tap, s);
+            atomicAdd(dwp + (size_t)(cs0 + c) * 27 + (MODE == D3_FUSED ? 26 - tap : tap), s);   // fused accumulators are indexed by the flipped tap
         }
-    } else if (a.stats_mode != CF_STATS_NONE) {
+        if (MODE == D3_FUSED) __syncthreads();
+    }
+    if (MODE != D3_WGRAD && a.stats_mode != CF_STATS_NONE) {
         *reinterpret_cast<float2*>(red + patch * 2 * D3_CS + lane * 2) = s1;
         *reinterpret_cast<float2*>(red + (patch * 2 + 1) * D3_CS + lane * 2) = s2;
         __syncthreads();
@@ -363,7 +394,7 @@ template <int MODE, int NPW>
 static int d3_launch(const cf_dw_args* a, const D3Params& p, cudaStream_t stream) {
     constexpr int TW = D3_PW * NPW, HW = TW + 2;
     constexpr int PLANE = D3_HH * HW * D3_CS;
-    const int nstg = (MODE == D3_DGRAD && a->pro_mode == CF_PRO_AFFINE2) ? 2 : 1;
+    const int nstg = ((MODE == D3_DGRAD || MODE == D3_FUSED) && a->pro_mode == CF_PRO_AFFINE2) ? 2 : 1;
     const size_t smem = (size_t)((3 + nstg) * PLANE + 5 * D3_CS + 27 * D3_CS) * sizeof(float);
     static CfOncePerDevice done;
     if (done.need()) {
@@ -391,7 +422,8 @@ int cf_dw3_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (mode == D3_FWD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE_RELU)) return -1;
     if (mode == D3_FWD && a->stats_mode == CF_STATS_SUM_AUX) return -1;
     if (mode != D3_FWD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE2)) return -1;
-    if (mode == D3_DGRAD && a->stats_mode == CF_STATS_SUM_SQ) return -1;
+    if ((mode == D3_DGRAD || mode == D3_FUSED) && a->stats_mode == CF_STATS_SUM_SQ) return -1;
+    if (mode == D3_FUSED && !(a->dw_out && a->aux && a->epi_mode == CF_EPI_DRELU && a->epi_a && a->epi_b)) return -1;
     D3Params p;
     p.B = a->B; p.C = a->C; p.T = g.T; p.H = g.H; p.W = g.W;
     const int force_npw = cf_env("CFNET_DW3_NPW", 0);                // tile width experiment (-DCFNET_AB build only)
@@ -413,9 +445,11 @@ int cf_dw3_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (npw == 1) {
         if (mode == D3_FWD) return d3_launch<D3_FWD, 1>(a, p, stream);
         if (mode == D3_DGRAD) return d3_launch<D3_DGRAD, 1>(a, p, stream);
+        if (mode == D3_FUSED) return d3_launch<D3_FUSED, 1>(a, p, stream);
         return d3_launch<D3_WGRAD, 1>(a, p, stream);
     }
     if (mode == D3_FWD) return d3_launch<D3_FWD, 2>(a, p, stream);
     if (mode == D3_DGRAD) return d3_launch<D3_DGRAD, 2>(a, p, stream);
+    if (mode == D3_FUSED) return d3_launch<D3_FUSED, 2>(a, p, stream);
     return d3_launch<D3_WGRAD, 2>(a, p, stream);
 }

@@ -68,9 +68,9 @@ def pw_wgrad(dy, x, dw, B, K, N, g, *, dy2=None, dy_mode=PRO_NONE, dy_tabs=(None
 
 
 def dw_call(fn, x, w, y, B, C, g, *, x2=None, pro=PRO_NONE, pro_tabs=(None, None, None), aux=None, epi=EPI_NONE,
-            epi_tabs=(None, None), stats=None, stats_mode=STATS_NONE):
+            epi_tabs=(None, None), stats=None, stats_mode=STATS_NONE, dw_out=None):
     a = make("cf_dw_args", x=x, x2=x2, w=w, y=y, pro_a=pro_tabs[0], pro_b=pro_tabs[1], pro_c=pro_tabs[2], aux=aux,
-             epi_a=epi_tabs[0], epi_b=epi_tabs[1], stats=stats, B=B, C=C, g=g, pro_mode=pro, epi_mode=epi,
+             epi_a=epi_tabs[0], epi_b=epi_tabs[1], stats=stats, dw_out=dw_out, B=B, C=C, g=g, pro_mode=pro, epi_mode=epi,
              stats_mode=stats_mode)
     call_struct(fn, a)
     return y
@@ -300,12 +300,10 @@ class BottleneckFn(torch.autograd.Function):
                      rows_per_sample=Rout)
             call_struct("cf_se_bwd", a)
         P2, Q2, R2 = bn_bwd_coeffs(sm(1, Ce), g2, m2, i2, dg2, db2, B, Ce, Rout, tr, gate=gate, cst=cst)
-        # conv2 (depthwise)
-        dw_call("cf_dw_conv_wgrad", dU, w2, dw2, B, Ce, g_dw, x2=y2, pro=PRO_AFFINE2, pro_tabs=(P2, Q2, R2), aux=y1,
-                epi_tabs=(a1, bb1))
+        # conv2 (depthwise): data gradient and weight gradient from one call (one pass over dU, y2, y1 for the stride-1 convs)
         dz1 = torch.empty_like(y1)
         dw_call("cf_dw_conv_dgrad", dU, w2, dz1, B, Ce, g_dw, x2=y2, pro=PRO_AFFINE2, pro_tabs=(P2, Q2, R2), aux=y1,
-                epi=EPI_DRELU, epi_tabs=(a1, bb1), stats=sm(2, Ce), stats_mode=STATS_SUM_AUX)
+                epi=EPI_DRELU, epi_tabs=(a1, bb1), stats=sm(2, Ce), stats_mode=STATS_SUM_AUX, dw_out=dw2)
         P1, Q1, R1 = bn_bwd_coeffs(sm(2, Ce), g1, m1, i1, dg1, db1, B, Ce, Rin, tr)
         # conv1
         pw_wgrad(dz1, x, dw1, B, Cin, Ce, g_in, dy2=y1, dy_mode=PRO_AFFINE2, dy_tabs=(P1, Q1, R1))

@@ -193,7 +193,10 @@ size_t cf_sizeof_pw_wgrad_args(void);
  *   dgrad: y[B,Ti,Hi,Wi,C] = epi( sum_taps pro(x[B,T,H,W,C], x2) * w[C,taps] ),  aux/epi tables at the
  *          input positions (the pre-activation the forward prologue consumed)
  *   wgrad: y[C,taps] += sum_pos pro(x[pos], x2[pos]) * act(aux[pos_in(tap)]),  act = relu(epi_a*aux+epi_b)
- *          when epi_a != NULL (x = output gradient, aux = forward input) */
+ *          when epi_a != NULL (x = output gradient, aux = forward input)
+ *   dgrad with dw_out != NULL (and epi_mode DRELU): the same call also accumulates the weight gradient
+ *          dw_out[C,taps] += ... (exactly what wgrad would add to y) -- for the 3x3x3 stride-1 convs in ONE pass over
+ *          (x, x2, aux) (x3d_dw3.cu), otherwise as the two kernels back to back. */
 typedef struct {
     const float* x;
     const float* x2;
@@ -206,6 +209,7 @@ typedef struct {
     const float* epi_a;
     const float* epi_b;
     double* stats;       /* [B,C,2] */
+    float* dw_out;       /* [C,taps] += (dgrad only) or NULL */
     int B, C;
     cf_geom g;
     int pro_mode, epi_mode, stats_mode;

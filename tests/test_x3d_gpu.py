@@ -253,6 +253,17 @@ def test_depthwise_fwd_bwd(X, C, stride, T, H, W):
     X.dw_call("cf_dw_conv_wgrad", rows(d), w.cuda(), dw, B, C, g, x2=rows(y2), pro=X.PRO_AFFINE2,
               pro_tabs=(P.cuda(), Q.cuda(), Rr.cuda()), aux=rows(x), epi_tabs=(ta.cuda(), tb.cuda()))
     close(dw, wr.grad.flatten(1), rtol=1e-4, atol=1e-4, what="dw wgrad")
+    # data gradient + weight gradient from ONE call (dw_out): one pass over (d, y2, x) on the stride-1 plane-marching kernel,
+    # the two kernels back to back elsewhere; dw_out is accumulated into (+=)
+    dz2 = X.new_act(B, C, T, H, W, "cuda")
+    sums2 = torch.zeros(B, C, 2, device="cuda", dtype=torch.float64)
+    dwf = torch.ones(C, 27, device="cuda")
+    X.dw_call("cf_dw_conv_dgrad", rows(d), w.cuda(), dz2, B, C, g, x2=rows(y2), pro=X.PRO_AFFINE2,
+              pro_tabs=(P.cuda(), Q.cuda(), Rr.cuda()), aux=rows(x), epi=X.EPI_DRELU, epi_tabs=(ta.cuda(), tb.cuda()),
+              stats=sums2, stats_mode=X.STATS_SUM_AUX, dw_out=dwf)
+    close(dz2, dz_ref, rtol=1e-4, atol=1e-4, what="fused dw dgrad")
+    close(sums2[..., 1], (dz_ref.double() * x.double()).sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-3, what="fused dw dgrad sum*aux")
+    close(dwf - 1.0, wr.grad.flatten(1), rtol=1e-4, atol=2e-4, what="fused dw wgrad")
 
 
 def test_depthwise_temporal_5x1x1(X):
