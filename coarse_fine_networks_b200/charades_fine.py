@@ -16,9 +16,10 @@ straight into the uint8 tensor the clip kernel reads.
 
 DataLoader workers: CUDA cannot be used in forked workers and pinned-memory collation does not apply to CUDA tensors, so with
 `num_workers > 0` build the dataset with `host_items=True`: `__getitem__` then does only the host half (window draw, file
-reads / PIL decode, the transform's random draw) and returns a plain dict; pass `collate_fn=dataset.device_collate` (runs in
-the main process: GPU decode + clip kernel + the reference's zero-padding collate).  Without it (`host_items=False`, the
-default) items are CUDA tensors as before and the loader must run with num_workers=0, pin_memory=False.
+reads / PIL decode, the transform's random draw) and returns a plain dict; pass `collate_fn=host_collate` (workers also
+run the collate function, so it only gathers the dicts) and finish every batch in the MAIN process with
+`dataset.device_collate(samples)` (GPU decode + clip kernel + the reference's zero-padding collate).  Without it
+(`host_items=False`, the default) items are CUDA tensors as before and the loader must run with num_workers=0, pin_memory=False.
 
 Differences, on purpose: the label cache `<split>_<split>labeldata_160.npy` is written as an object array (the reference's
 `np.save(list_of_tuples)` raises on numpy >= 1.24) and read back the way the reference reads it; the accimage backend is not
@@ -200,13 +201,19 @@ class Charades(torch.utils.data.Dataset):
         return s if self.host_items else self.finish(s)
 
     def device_collate(self, batch):
-        """collate_fn for host_items=True: runs in the main process."""
+        """Main-process half of a host_items=True loader: `for samples in loader: batch = dataset.device_collate(samples)`."""
         return mt_collate_fn([self.finish(s) for s in batch])
 
     def __getstate__(self):                                               # the nvJPEG decoder does not travel to worker processes
         d = dict(self.__dict__)
         d["_decoder"] = None
         return d
+
+
+def host_collate(batch):
+    """collate_fn for host_items=True datasets: DataLoader workers run the collate function too, so it only gathers the
+    host-side sample dicts; the main process turns them into a batch with `dataset.device_collate(samples)`."""
+    return list(batch)
 
 
 def mt_collate_fn(batch):

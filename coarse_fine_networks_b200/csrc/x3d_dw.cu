@@ -711,6 +711,8 @@ extern "C" int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a->aux, "dw_out: aux (the forward input) missing");
     rc = cf_env("CFNET_DW3_NOFUSE", 0) ? -1 : cf_dw3_try(3, a, stream);     // data gradient + weight gradient in one pass
     if (rc >= 0) return rc;
+    rc = cf_env("CFNET_DW3S2_NOFUSE", 0) ? -1 : cf_dw3s2_try(3, a, stream);  // the same for the stride-(1,2,2) convs
+    if (rc >= 0) return rc;
     cf_dw_args d = *a;
     d.dw_out = nullptr;
     rc = dw_dgrad_impl(&d, stream);

@@ -296,7 +296,13 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_kernel(const cf
 //   dz[ti, 2ho+a, 2wo+b, c] = [a1*y1+b1 > 0] * sum_dt sum_{(dh,ho') in S_a} sum_{(dw,wo') in S_b} d'[ti+1-dt, ho', wo'] w[dt,dh,dw]
 //   S_0 = {(1, o)},  S_1 = {(0, o+1), (2, o)}
 // ---------------------------------------------------------------------------------------
-template <int NPW>
+// FUSED: the same pass also produces the weight gradient.  Every (output position p, tap) pair of
+//   dw[c,tap] = sum_p d'[p] * relu(a1*y1+b1)[2p + tap - 1]
+// is visited exactly once by the gather form above -- as the term d'[p] * w[tap] of the input position q = 2p + tap - 1 -- so
+// the weight gradient is 27 more accumulators fed by the d' values already in registers times the activation at q (the
+// `aux` row the ReLU mask needs anyway; aux is re-read from L1/L2 for the epilogue, its registers hold the activations).
+// The weights move to shared memory (their registers hold the accumulators).
+template <int NPW, bool FUSED>
 __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(const cf_dw_args a, const S2Params p) {
     constexpr int OTW = S2_PW * NPW, RW = OTW + 1, RH = S2_OTH + 1;
     constexpr int NPATCH = S2_OTH * NPW, NT = S2_LANES * NPATCH;
@@ -404,9 +410,9 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(co
         };
         auto slot = [&](int t) { return ring + ((t - t0 + 1) % 3) * PLANE; };
 
-        float2 wreg[27];
+        float2 wreg[27];                                           // the weights; FUSED: the weight-gradient accumulators
 #pragma unroll
-        for (int i = 0; i < 27; ++i) wreg[i] = *reinterpret_cast<const float2*>(ws + i * S2_CS + lane * 2);
+        for (int i = 0; i < 27; ++i) wreg[i] = FUSED ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(ws + i * S2_CS + lane * 2);
         float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
         const int hi_base = 2 * (ho0 + pr), wi_base = 2 * (wo0 + pc * S2_PW);
         const float* pthr = ring + (pr * RW + pc * S2_PW) * S2_CS + lane * 2;
@@ -442,7 +448,14 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(co
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int j = 0; j < 2 * S2_PW; ++j) acc[r][j] = make_float2(0.f, 0.f);
+                for (int j = 0; j < 2 * S2_PW; ++j) {
+                    acc[r][j] = make_float2(0.f, 0.f);
+                    if (FUSED) {                                   // aux -> activation relu(ea*aux + eb) (0 outside the image)
+                        const bool v = hi_base + r < Hi && wi_base + j < Wi;
+                        aux[r][j] = make_float2(v ? fmaxf(fmaf(ea.x, aux[r][j].x, eb.x), 0.f) : 0.f,
+                                                v ? fmaxf(fmaf(ea.y, aux[r][j].y, eb.y), 0.f) : 0.f);
+                    }
+                }
 #pragma unroll
             for (int dt = 0; dt < 3; ++dt) {
                 // tap dt reads d' frame ti + 1 - dt: dt = 0 -> ti+1 (slot sl0+2), 1 -> ti (sl0+1), 2 -> ti-1 (sl0)
@@ -453,21 +466,37 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(co
                     in0[j] = *reinterpret_cast<const float2*>(pl + j * S2_CS);
                     in1[j] = *reinterpret_cast<const float2*>(pl + (RW + j) * S2_CS);
                 }
-                const float2* w = wreg + dt * 9;                   // w[dh * 3 + dw]
-#define S2_FMA(ACC, X, WV) ffma2(ACC, X, WV)
+                float2 wl[9];                                      // this dt's 9 spatial taps, w[dh * 3 + dw]
+#pragma unroll
+                for (int i = 0; i < 9; ++i)
+                    wl[i] = FUSED ? *reinterpret_cast<const float2*>(ws + (dt * 9 + i) * S2_CS + lane * 2) : wreg[dt * 9 + i];
+                float2* g = wreg + dt * 9;                         // FUSED: weight-gradient accumulators of these taps
+                // data gradient: ACC += X * w[tap];  weight gradient (FUSED): g[tap] += X * activation at ACC's position
+#define S2_FMA(R, J, X, TAP) do { ffma2(acc[R][J], X, wl[TAP]); if (FUSED) ffma2(g[TAP], X, aux[R][J]); } while (0)
 #pragma unroll
                 for (int j = 0; j < S2_PW; ++j) {
-                    S2_FMA(acc[0][2 * j], in0[j], w[1 * 3 + 1]);                                   // even row, even col
-                    S2_FMA(acc[0][2 * j + 1], in0[j + 1], w[1 * 3 + 0]);                           // even row, odd col
-                    S2_FMA(acc[0][2 * j + 1], in0[j], w[1 * 3 + 2]);
-                    S2_FMA(acc[1][2 * j], in1[j], w[0 * 3 + 1]);                                   // odd row, even col
-                    S2_FMA(acc[1][2 * j], in0[j], w[2 * 3 + 1]);
-                    S2_FMA(acc[1][2 * j + 1], in1[j + 1], w[0 * 3 + 0]);                           // odd row, odd col
-                    S2_FMA(acc[1][2 * j + 1], in1[j], w[0 * 3 + 2]);
-                    S2_FMA(acc[1][2 * j + 1], in0[j + 1], w[2 * 3 + 0]);
-                    S2_FMA(acc[1][2 * j + 1], in0[j], w[2 * 3 + 2]);
+                    S2_FMA(0, 2 * j, in0[j], 1 * 3 + 1);                                           // even row, even col
+                    S2_FMA(0, 2 * j + 1, in0[j + 1], 1 * 3 + 0);                                   // even row, odd col
+                    S2_FMA(0, 2 * j + 1, in0[j], 1 * 3 + 2);
+                    S2_FMA(1, 2 * j, in1[j], 0 * 3 + 1);                                           // odd row, even col
+                    S2_FMA(1, 2 * j, in0[j], 2 * 3 + 1);
+                    S2_FMA(1, 2 * j + 1, in1[j + 1], 0 * 3 + 0);                                   // odd row, odd col
+                    S2_FMA(1, 2 * j + 1, in1[j], 0 * 3 + 2);
+                    S2_FMA(1, 2 * j + 1, in0[j + 1], 2 * 3 + 0);
+                    S2_FMA(1, 2 * j + 1, in0[j], 2 * 3 + 2);
                 }
 #undef S2_FMA
+            }
+            if (FUSED && need_aux) {                               // the raw pre-activation again, for the mask and the statistics
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int j = 0; j < 2 * S2_PW; ++j) {
+                        const bool v = hi_base + r < Hi && wi_base + j < Wi;
+                        aux[r][j] = v ? __ldg(reinterpret_cast<const float2*>(
+                                            a.aux + ((((size_t)b * T + ti) * Hi + hi_base + r) * Wi + wi_base + j) * C + c0))
+                                      : make_float2(0.f, 0.f);
+                    }
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -489,6 +518,20 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(co
         }
         s2_cp_async_wait_all();
 
+        if (FUSED) {                                               // CTA reduction of the weight-gradient partials, then atomics
+            float* red = ring;
+#pragma unroll
+            for (int i = 0; i < 27; ++i) *reinterpret_cast<float2*>(red + ((size_t)patch * 27 + i) * S2_CS + lane * 2) = wreg[i];
+            __syncthreads();
+            for (int i = tid; i < 27 * S2_CS; i += NT) {
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < NPATCH; ++q) s += red[(size_t)q * 27 * S2_CS + i];
+                const int tap = i / S2_CS, c = i - tap * S2_CS;
+                atomicAdd(a.dw_out + (size_t)(cs0 + c) * 27 + tap, s);
+            }
+            __syncthreads();
+        }
         if (a.stats_mode != CF_STATS_NONE) {
             float* red = ring;
             *reinterpret_cast<float2*>(red + patch * 2 * S2_CS + lane * 2) = s1;
@@ -505,19 +548,19 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(co
     }   // pieces
 }
 
-template <int NPW>
+template <int NPW, bool FUSED>
 static int s2_launch_dgrad(const cf_dw_args* a, const S2Params& p, cudaStream_t stream) {
     constexpr int OTW = S2_PW * NPW;
     constexpr int PLANE = (S2_OTH + 1) * (OTW + 1) * S2_CS;
     const size_t smem = (size_t)(5 * PLANE + 5 * S2_CS + 27 * S2_CS) * sizeof(float);
     static CfOncePerDevice done;
     if (done.need()) {
-        cudaError_t e = cudaFuncSetAttribute(dw3s2_dgrad_kernel<NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(dw3s2_dgrad_kernel<NPW, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) { cf_set_error("dw3s2: cannot opt in to shared memory: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
         done.mark();
     }
     dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
-    dw3s2_dgrad_kernel<NPW><<<grid, S2_LANES * S2_OTH * NPW, smem, stream>>>(*a, p);
+    dw3s2_dgrad_kernel<NPW, FUSED><<<grid, S2_LANES * S2_OTH * NPW, smem, stream>>>(*a, p);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -542,7 +585,8 @@ static int s2_launch(const cf_dw_args* a, const S2Params& p, cudaStream_t stream
     return CF_OK;
 }
 
-// mode: 0 forward, 1 data gradient, 2 weight gradient.  Returns CF_OK when launched, -1 when not eligible.
+// mode: 0 forward, 1 data gradient, 2 weight gradient, 3 data + weight gradient in one pass (a->dw_out).
+// Returns CF_OK when launched, -1 when not eligible.
 int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (cf_env("CFNET_DW3_OFF", 0)) return -1;
     const cf_geom& g = a->g;
@@ -555,7 +599,8 @@ int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (mode == S2_FWD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE_RELU)) return -1;
     if (mode == S2_FWD && a->stats_mode == CF_STATS_SUM_AUX) return -1;
     if (mode != S2_FWD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE2)) return -1;
-    if (mode == 1 && a->stats_mode == CF_STATS_SUM_SQ) return -1;
+    if ((mode == 1 || mode == 3) && a->stats_mode == CF_STATS_SUM_SQ) return -1;
+    if (mode == 3 && !(a->dw_out && a->aux && a->epi_mode == CF_EPI_DRELU && a->epi_a && a->epi_b)) return -1;
     S2Params p;
     p.B = a->B; p.C = a->C; p.T = g.T; p.Hi = g.Hi; p.Wi = g.Wi; p.Ho = g.H; p.Wo = g.W;
     const int npw = g.W == 7 ? 1 : 2;
@@ -572,7 +617,8 @@ int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     long long spc = (p.total_steps + nsm - 1) / nsm;
     if (spc < 4) spc = 4;
     p.steps_per_cta = (int)spc;
-    if (mode == 1) return npw == 1 ? s2_launch_dgrad<1>(a, p, stream) : s2_launch_dgrad<2>(a, p, stream);
+    if (mode == 1) return npw == 1 ? s2_launch_dgrad<1, false>(a, p, stream) : s2_launch_dgrad<2, false>(a, p, stream);
+    if (mode == 3) return npw == 1 ? s2_launch_dgrad<1, true>(a, p, stream) : s2_launch_dgrad<2, true>(a, p, stream);
     if (npw == 1) return mode == S2_FWD ? s2_launch<S2_FWD, 1>(a, p, stream) : s2_launch<S2_WGRAD, 1>(a, p, stream);
     return mode == S2_FWD ? s2_launch<S2_FWD, 2>(a, p, stream) : s2_launch<S2_WGRAD, 2>(a, p, stream);
 }

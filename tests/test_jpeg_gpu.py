@@ -133,16 +133,19 @@ def test_loader_nvjpeg_matches_pil_path(J, env):
 
 
 def test_host_items_behind_a_multi_worker_dataloader(J, env):
-    """host_items=True: workers do the host half only (no CUDA in forked workers), the main process finishes items in
-    device_collate; the batch equals the one built item by item with the same per-item seeds."""
+    """host_items=True: workers do the host half only (no CUDA in forked workers; they also run the collate function, so
+    collate_fn=host_collate just gathers the dicts), the main process finishes the batch with device_collate; it equals
+    the one built item by item with the same per-item seeds."""
     kw = dict(task="class", frames=80, gamma_tau=5, crops=1, cache=False, decode="nvjpeg")
     ds = env.L.Charades(env.split_file, "training", env.root, env.mk(), host_items=True, **kw)
 
     def seed_worker(_):
         random.seed(1234)
-    dl = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, num_workers=2, pin_memory=False, collate_fn=ds.device_collate,
+    dl = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, num_workers=2, pin_memory=False, collate_fn=env.L.host_collate,
                                      worker_init_fn=seed_worker)
-    clips, labels, masks, vids = next(iter(dl))
+    samples = next(iter(dl))                                   # host-side dicts from a worker process
+    assert isinstance(samples, list) and isinstance(samples[0]["frames"][0], bytes)
+    clips, labels, masks, vids = ds.device_collate(samples)    # main process: nvJPEG decode + clip kernel + padding
     assert clips.is_cuda and clips.shape[0] == 2 and clips.shape[2] == 3 and labels.shape[0] == 2 and len(vids) == 2
     ref = env.L.Charades(env.split_file, "training", env.root, env.mk(), host_items=False, **kw)
     random.seed(1234)
