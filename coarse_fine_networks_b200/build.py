@@ -47,12 +47,17 @@ def _compile(src, verbose, obj_dir=OBJ_DIR, extra=()):
     return obj, True
 
 
-def build(force=False, verbose=False, ab=False):
+VARIANTS = {"cvt": ("-DCFNET_AB", "-DCFNET_TF32_CVT")}       # named experiment builds: libcfnet_b200_<name>.so
+
+
+def build(force=False, verbose=False, ab=False, variant=None):
     """ab=True builds libcfnet_b200_ab.so with -DCFNET_AB: the same library with its experiment switches (environment
     variables) compiled in -- select it with CFNET_LIB=<path> for same-box A/B runs; the shipped library reads no environment."""
     obj_dir = OBJ_DIR + ("_ab" if ab else "")
     lib = LIB.replace(".so", "_ab.so") if ab else LIB
     extra = ("-DCFNET_AB",) if ab else ()
+    if variant:
+        obj_dir, lib, extra = OBJ_DIR + "_" + variant, LIB.replace(".so", "_" + variant + ".so"), VARIANTS[variant]
     os.makedirs(obj_dir, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     if force:
@@ -70,4 +75,5 @@ def build(force=False, verbose=False, ab=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ab="--ab" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ab="--ab" in sys.argv,
+                variant=sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None))

@@ -85,8 +85,15 @@ __device__ __host__ __forceinline__ uint32_t sw128_off(int row, int q) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((q ^ (row & 7)) << 4));
 }
 
-// round-to-nearest TF32 (cvt.rna): with truncation the dropped lo*lo term and the hardware's truncation of lo are
-// one-signed and the error grows linearly in K (1.7e-5 at K = 2048); rounded, the residuals are symmetric.
+// 3xTF32 operand split: v = hi + lo with hi, lo rounded to TF32 (10 mantissa bits), round-to-nearest -- with truncation the
+// dropped lo*lo term and the hardware's truncation of lo are one-signed and the error grows linearly in K (1.7e-5 at
+// K = 2048); rounded, the residuals are symmetric.
+// `cvt.rna.tf32.f32` is EMULATED on sm_100a (ncu source view of round 1's kernels: VIADD +0x1000, FSETP |x|>=Inf, SEL, LOP3
+// per conversion -- 9 issue slots per split element, the largest single item of the GEMM producers' instruction stream).
+// The same rounding in integer arithmetic without the Inf/NaN guard: adding half a TF32 ulp to the magnitude bits and
+// masking is round-to-nearest (ties away from zero), +-Inf stays +-Inf, NaN stays NaN; 2 + 1 + 1 issue slots.  `lo` is not
+// masked: the tensor core ignores the 13 low mantissa bits of a TF32 operand.
+#ifdef CFNET_TF32_CVT        /* A/B: the cvt.rna form of round 1 (python -m coarse_fine_networks_b200.build --variant cvt) */
 __device__ __forceinline__ float tf32_rn(float v) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -96,6 +103,15 @@ __device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
     hi = tf32_rn(v);
     lo = tf32_rn(v - hi);
 }
+#else
+__device__ __forceinline__ float tf32_rn(float v) {
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
+    hi = tf32_rn(v);
+    lo = __uint_as_float(__float_as_uint(v - hi) + 0x1000u);
+}
+#endif
 
 
 // ---------------------------------------------------------------------------------------

@@ -711,7 +711,10 @@ extern "C" int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a->aux, "dw_out: aux (the forward input) missing");
     rc = cf_env("CFNET_DW3_NOFUSE", 0) ? -1 : cf_dw3_try(3, a, stream);     // data gradient + weight gradient in one pass
     if (rc >= 0) return rc;
-    rc = cf_env("CFNET_DW3S2_NOFUSE", 0) ? -1 : cf_dw3s2_try(3, a, stream);  // the same for the stride-(1,2,2) convs
+    // The stride-(1,2,2) kernel has the same one-pass form (dw3s2_dgrad_kernel<*, true>), but there it LOSES: 28 outputs
+    // per thread leave no registers for the 28 activations next to the mask operands (they are re-read) and the same-box
+    // A/B measured 103.2 vs 101.8 ms per step (profiles/r02_ab_same_box.md): experiment build only.
+    rc = cf_env("CFNET_DW3S2_FUSE", 0) ? cf_dw3s2_try(3, a, stream) : -1;
     if (rc >= 0) return rc;
     cf_dw_args d = *a;
     d.dw_out = nullptr;

@@ -259,69 +259,115 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
         long long item = item0;
         if (p.tma) {
             // ---- TMA-fed: the row block's dy (+ dy2) and x tiles are already in shared memory (raw ring, filled by the
-            // loader lane with cp.async.bulk.tensor); read -> prologue -> hi/lo split -> swizzled operand stage
+            // loader lane with cp.async.bulk.tensor); read -> prologue -> hi/lo split -> swizzled operand stage.
+            // Written for a SHORT instruction stream: the ncu source view of round 1's producers showed ~510 issue slots per
+            // thread and 64-row stage of which ~10 % were loads / FMAs / stores -- the rest address arithmetic, predicates
+            // and reconvergence of the generic batch / unit bookkeeping.  Here: one loop per tensor, all offsets of a
+            // thread (row, 16-byte slot) computed once, nothing per unit but a constant stride.
             int rs = 0;
             uint32_t rph = 0;
-            auto raw4 = [&](const uint8_t* reg, int fold, int C, int u, float* v) {
-                if (fold == 1) {
-                    const float4 t = *reinterpret_cast<const float4*>(reg + (size_t)u * p.chunk_bytes + row * 128 + q8 * 16);
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                } else {
-                    const int c = u * 32 + q8 * 4;
-                    const float* src = reinterpret_cast<const float*>(reg) + row * C + c;
-                    if (fold == 2) {
-#pragma unroll
-                        for (int e = 0; e < 4; e += 2) {
-                            if (c + e < C) {
-                                const float2 t = *reinterpret_cast<const float2*>(src + e);
-                                v[e] = t.x; v[e + 1] = t.y;
-                            } else {
-                                v[e] = 0.f; v[e + 1] = 0.f;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) v[e] = (c + e < C) ? src[e] : 0.f;
-                    }
-                }
-            };
+            const uint32_t roff1 = (uint32_t)row * 128u + (uint32_t)q8 * 16u;                  // fold == 1: [RB][32] chunks
+            const uint32_t ustride = (uint32_t)groups * p.chunk_bytes;
+            const int cq = q8 * 4;
+            const float* tA = tabA + cq;
+            const float* tB = tabB + cq;
+            const int nA = p.ndyc * 32, nB = p.nxc * 32;
             for (; item < item1; ++item) {
                 const bool rv = row < min(p.RB, p.R - rb * p.RB);
                 if (b != cur_b) {
                     named_bar_sync(1, WG_PROD_THREADS);
-                    for (int t = tid; t < p.ndyc * 32; t += WG_PROD_THREADS) {
+                    for (int t = tid; t < nA; t += WG_PROD_THREADS) {
                         const int n = n_base + t;
                         const bool v = n < N && DYM != CF_PRO_NONE;
                         tabA[t] = v ? a.dy_a[(size_t)b * N + n] : 0.f;
-                        tabA[p.ndyc * 32 + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
-                        tabA[2 * p.ndyc * 32 + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
+                        tabA[nA + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
+                        tabA[2 * nA + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
                     }
-                    for (int t = tid; t < p.nxc * 32; t += WG_PROD_THREADS) {
+                    for (int t = tid; t < nB; t += WG_PROD_THREADS) {
                         const int k = k_base + t;
                         const bool v = k < K && XM != CF_PRO_NONE;
                         tabB[t] = v ? a.x_a[(size_t)b * K + k] : 0.f;
-                        tabB[p.nxc * 32 + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
+                        tabB[nB + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
                     }
                     named_bar_sync(1, WG_PROD_THREADS);
                     cur_b = b;
                 }
                 mbar_wait_b(&rfull[rs], rph);
                 mbar_wait_b(&empty[s], ph ^ 1u);
-                const uint8_t* rst = raw + (size_t)rs * p.raw_stage_bytes;
+                const uint8_t* rdy = raw + (size_t)rs * p.raw_stage_bytes;
+                const uint8_t* rx = rdy + (aff2 ? 2u : 1u) * p.raw_dy_bytes;
                 uint8_t* stage = stages + (size_t)s * p.stage_bytes;
-                for (int u0 = grp; u0 < nunits; u0 += ustep) {
+                // ---- dy units (this thread's group takes every `groups`-th 32-channel chunk)
+                {
+                    uint8_t* dst = stage + p.dy_off + soff + (uint32_t)grp * p.chunk_bytes;
+                    for (int u = grp; u < p.ndyc; u += groups, dst += ustride) {
+                        float v[4], v2[4];
+                        if (p.fold_dy == 1) {
+                            const float4 t = *reinterpret_cast<const float4*>(rdy + (uint32_t)u * p.chunk_bytes + roff1);
+                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                            if (aff2) {
+                                const float4 t2 = *reinterpret_cast<const float4*>(rdy + p.raw_dy_bytes + (uint32_t)u * p.chunk_bytes + roff1);
+                                v2[0] = t2.x; v2[1] = t2.y; v2[2] = t2.z; v2[3] = t2.w;
+                            }
+                        } else {                                 // whole [RB][N] tile, 8-byte aligned rows (N even)
+                            const int c = u * 32 + cq;
+                            const float* src = reinterpret_cast<const float*>(rdy) + row * N + c;
 #pragma unroll
-                    for (int i = 0; i < WG_UB; ++i) {
-                        const int u = u0 + i * groups;
-                        if (u >= nunits) break;
-                        if (u < p.ndyc) {
-                            raw4(rst, p.fold_dy, N, u, vA[i]);
-                            if (aff2) raw4(rst + p.raw_dy_bytes, p.fold_dy, N, u, wA[i]);
-                        } else {
-                            raw4(rst + (aff2 ? 2u : 1u) * p.raw_dy_bytes, p.fold_x, K, u - p.ndyc, vA[i]);
+                            for (int e = 0; e < 4; e += 2) {
+                                float2 t = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
+                                if (c + e < N) {
+                                    t = *reinterpret_cast<const float2*>(src + e);
+                                    if (aff2) t2 = *reinterpret_cast<const float2*>(src + (p.raw_dy_bytes >> 2) + e);
+                                }
+                                v[e] = t.x; v[e + 1] = t.y; v2[e] = t2.x; v2[e + 1] = t2.y;
+                            }
                         }
+                        float hi[4], lo[4];
+                        if (DYM != CF_PRO_NONE) {
+                            const float4 ta = *reinterpret_cast<const float4*>(tA + u * 32);
+                            const float4 tb = *reinterpret_cast<const float4*>(tA + nA + u * 32);
+                            const float4 tc = *reinterpret_cast<const float4*>(tA + 2 * nA + u * 32);
+                            const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w}, pc[4] = {tc.x, tc.y, tc.z, tc.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = rv ? wg_pro<DYM>(v[e], aff2 ? v2[e] : 0.f, pa[e], pb[e], pc[e]) : 0.f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) tf32_split(v[e], hi[e], lo[e]);
+                        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(dst + p.dy_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                    store_batch(stage, u0, rv, vA, wA);
+                }
+                // ---- x units
+                {
+                    uint8_t* dst = stage + p.x_off + soff + (uint32_t)grp * p.chunk_bytes;
+                    for (int u = grp; u < p.nxc; u += groups, dst += ustride) {
+                        float v[4];
+                        if (p.fold_x == 1) {
+                            const float4 t = *reinterpret_cast<const float4*>(rx + (uint32_t)u * p.chunk_bytes + roff1);
+                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                        } else {
+                            const int c = u * 32 + cq;
+                            const float* src = reinterpret_cast<const float*>(rx) + row * K + c;
+#pragma unroll
+                            for (int e = 0; e < 4; e += 2) {
+                                float2 t = make_float2(0.f, 0.f);
+                                if (c + e < K) t = *reinterpret_cast<const float2*>(src + e);
+                                v[e] = t.x; v[e + 1] = t.y;
+                            }
+                        }
+                        float hi[4], lo[4];
+                        if (XM != CF_PRO_NONE) {
+                            const float4 ta = *reinterpret_cast<const float4*>(tB + u * 32);
+                            const float4 tb = *reinterpret_cast<const float4*>(tB + nB + u * 32);
+                            const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = rv ? wg_pro<XM>(v[e], 0.f, pa[e], pb[e], 0.f) : 0.f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) tf32_split(v[e], hi[e], lo[e]);
+                        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(dst + p.x_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rempty[rs]);                 // raw stage read: the loader may refill it
@@ -577,10 +623,9 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     bool planned = false;
     if (!p.gmode && cf_env("CFNET_WG_TMA", 1)) {
         const int fdy = (N % 4 == 0) ? 1 : 2, fx = (K % 4 == 0) ? 1 : 2;
-        // 54-channel tensors (rows that are not 16-byte multiples) would need the folded whole-tile copies and 8-byte
-        // shared-memory reads: measured 2-4 % slower than the register-load producers on the layer-1 shapes (same-box A/B,
-        // profiles/r02_ab_same_box.md), 13-19 % faster on the 16-byte-row shapes of layers 2-4
-        if (fdy == 1 && fx == 1) {
+        // 54-channel tensors (rows that are not 16-byte multiples) travel as folded whole-tile copies (no channel split then)
+        const bool split = p.msplit * p.nsplit > 1;
+        if ((fdy == 1 && fx == 1) || (!split && cf_env("CFNET_WG_TMA_FOLD", 1))) {
             for (int rb = 64; rb >= 16 && !planned; rb >>= 1) {
                 const uint32_t chunk = (uint32_t)rb * 128u;
                 const uint32_t stage = (uint32_t)(2 * (p.nchA_pad + p.nchB)) * chunk;

@@ -136,7 +136,7 @@ def test_host_items_behind_a_multi_worker_dataloader(J, env):
     """host_items=True: workers do the host half only (no CUDA in forked workers; they also run the collate function, so
     collate_fn=host_collate just gathers the dicts), the main process finishes the batch with device_collate; it equals
     the one built item by item with the same per-item seeds."""
-    kw = dict(task="class", frames=80, gamma_tau=5, crops=1, cache=False, decode="nvjpeg")
+    kw = dict(task="loc", frames=80, gamma_tau=5, crops=1, cache=False, decode="nvjpeg")      # mt_collate_fn pads [C,TL] labels
     ds = env.L.Charades(env.split_file, "training", env.root, env.mk(), host_items=True, **kw)
 
     def seed_worker(_):
