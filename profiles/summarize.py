@@ -60,5 +60,46 @@ def full(src, dst):
             f.write("\n")
 
 
+def mix(src, dst):
+    """Append the dynamic instruction mix, the issue utilisation and the stall reasons of every kernel of an ncu report
+    (raw + source pages): where the issue slots of a kernel go."""
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw[raw.index('"ID"'):])))
+    hdr = rows[0]
+    out = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(io.StringIO(out)))
+    with open(dst, "a") as f:
+        for r in rows[2:]:
+            f.write(f"### `{short(r[hdr.index('Kernel Name')])}`: issue slots and stalls\n\n")
+            for m in ("smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+                      "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.sum"):
+                if m in hdr:
+                    f.write(f"* {m} = {r[hdr.index(m)]}\n")
+            st = [(h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), float(r[i] or 0))
+                  for i, h in enumerate(hdr) if "issue_stalled" in h and h.endswith("_per_issue_active.ratio") and "not_issued" not in h]
+            st.sort(key=lambda kv: -kv[1])
+            f.write("* stalls per issued instruction: " + ", ".join(f"{k} {v:.2f}" for k, v in st[:8]) + "\n")
+        # instruction mix of the first kernel of the source page
+        h2 = None
+        agg, tot = collections.Counter(), 0
+        for r in srows:
+            if h2 is None:
+                if "Instructions Executed" in r:
+                    h2 = r
+                    ia, isrc = r.index("Instructions Executed"), r.index("Source")
+                continue
+            if len(r) <= ia or not r[ia].isdigit():
+                continue
+            src_txt = r[isrc].strip().split()
+            if not src_txt:
+                continue
+            op = (src_txt[1] if src_txt[0].startswith("@") and len(src_txt) > 1 else src_txt[0]).split(".")[0]
+            agg[op] += int(r[ia])
+            tot += int(r[ia])
+        if tot:
+            f.write("* dynamic instruction mix (warp instructions, all kernels of the report): " +
+                    ", ".join(f"{op} {100 * n / tot:.1f}%" for op, n in agg.most_common(16)) + f"; total {tot}\n\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "mix": mix}[sys.argv[1]](sys.argv[2], sys.argv[3])
