@@ -716,6 +716,8 @@ extern "C" int cf_dw_conv_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     // A/B measured 103.2 vs 101.8 ms per step (profiles/r02_ab_same_box.md): experiment build only.
     rc = cf_env("CFNET_DW3S2_FUSE", 0) ? cf_dw3s2_try(3, a, stream) : -1;
     if (rc >= 0) return rc;
+    rc = cf_env("CFNET_DWT5_NOFUSE", 0) ? -1 : cf_dwt5_try(3, a, stream);    // stem conv1_t: one march over (dz, yt, y0)
+    if (rc >= 0) return rc;
     cf_dw_args d = *a;
     d.dw_out = nullptr;
     rc = dw_dgrad_impl(&d, stream);

@@ -10,11 +10,13 @@
 //   forward : y[t]  = sum_dt pro(x[t+dt-2]) * w[dt]                               (+ sum y, sum y^2 per sample/channel)
 //   dgrad   : dx[t] = sum_dt d'[t-dt+2] * w[dt],   d' = P*dz + Q*y + R            (= forward with the flipped stencil)
 //   wgrad   : dw[dt] += sum_t d'[t] * act(x[t+dt-2]),  act = relu(a*x+b) when tables are given
+//   fused   : the data-gradient march also accumulates dw[dt] = sum_q act(x[q]) * d'[q-dt+2] from the d' window it holds
+//             (one more load per step -- the forward input at the output position -- instead of a second pass over d', y)
 #include "cf_common.cuh"
 #include "../../include/cfnet_b200.h"
 #include <stdlib.h>
 
-enum { T5_FWD = 0, T5_DGRAD = 1, T5_WGRAD = 2 };
+enum { T5_FWD = 0, T5_DGRAD = 1, T5_WGRAD = 2, T5_FUSED = 3 };   // FUSED: data gradient + weight gradient in one pass
 
 struct T5Params {
     int B, C, T;
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(256) dwt5_kernel(const cf_dw_args a, const T5P
     float4 w[5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-        const int jj = MODE == T5_DGRAD ? 4 - j : j;                // dgrad: flipped stencil
+        const int jj = (MODE == T5_DGRAD || MODE == T5_FUSED) ? 4 - j : j;    // dgrad: flipped stencil
         w[j] = (MODE == T5_WGRAD || !live) ? t5_zero()
                                            : make_float4(a.w[(size_t)(c0 + 0) * 5 + jj], a.w[(size_t)(c0 + 1) * 5 + jj],
                                                          a.w[(size_t)(c0 + 2) * 5 + jj], a.w[(size_t)(c0 + 3) * 5 + jj]);
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(256) dwt5_kernel(const cf_dw_args a, const T5P
     // window tensor: FWD a.x (pro NONE / AFFINE / AFFINE_RELU); DGRAD a.x (+ a.x2, AFFINE2); WGRAD a.aux (relu(a*x+b) if epi tables)
     const float* win = MODE == T5_WGRAD ? a.aux : a.x;
     const int win_mode = MODE == T5_WGRAD ? (a.epi_a ? CF_PRO_AFFINE_RELU : CF_PRO_NONE) : a.pro_mode;
+    const float4 ea4 = tab4(a.epi_a, 1.f), eb4 = tab4(a.epi_b, 0.f);     // FUSED: activation tables of the forward input
     const float4 wa = MODE == T5_WGRAD ? tab4(a.epi_a, 1.f) : tab4(a.pro_a, 1.f);
     const float4 wb = MODE == T5_WGRAD ? tab4(a.epi_b, 0.f) : tab4(a.pro_b, 0.f);
     const float4 wc = MODE == T5_WGRAD ? t5_zero() : tab4(a.pro_c, 0.f);
@@ -94,6 +97,18 @@ __global__ void __launch_bounds__(256) dwt5_kernel(const cf_dw_args a, const T5P
                 __stcs(reinterpret_cast<float4*>(a.y) + base + (size_t)t * p.F4, y);
                 s1.x += y.x; s1.y += y.y; s1.z += y.z; s1.w += y.w;
                 s2 = t5_fma(y, y, s2);
+                if (MODE == T5_FUSED) {                            // dw[dt] += act(x[t]) * d'[t - dt + 2]
+                    float4 xin = __ldg(reinterpret_cast<const float4*>(a.aux) + base + (size_t)t * p.F4);
+                    if (a.epi_a) {
+                        xin.x = fmaxf(fmaf(ea4.x, xin.x, eb4.x), 0.f); xin.y = fmaxf(fmaf(ea4.y, xin.y, eb4.y), 0.f);
+                        xin.z = fmaxf(fmaf(ea4.z, xin.z, eb4.z), 0.f); xin.w = fmaxf(fmaf(ea4.w, xin.w, eb4.w), 0.f);
+                    }
+                    acc[0] = t5_fma(xin, xp2, acc[0]);
+                    acc[1] = t5_fma(xin, xp1, acc[1]);
+                    acc[2] = t5_fma(xin, x0, acc[2]);
+                    acc[3] = t5_fma(xin, xm1, acc[3]);
+                    acc[4] = t5_fma(xin, xm2, acc[4]);
+                }
             }
         } else if (live) {
             float4 d = __ldg(reinterpret_cast<const float4*>(a.x) + base + (size_t)t * p.F4);
@@ -113,7 +128,8 @@ __global__ void __launch_bounds__(256) dwt5_kernel(const cf_dw_args a, const T5P
     }
 
     // ---- block reductions: threads with the same channel quad (e % CQ) share channels
-    if (MODE == T5_WGRAD) {
+    if (MODE == T5_WGRAD || MODE == T5_FUSED) {
+        float* dwp = MODE == T5_FUSED ? a.dw_out : a.y;
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             red[(j * 4 + 0) * 256 + tid] = acc[j].x; red[(j * 4 + 1) * 256 + tid] = acc[j].y;
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(256) dwt5_kernel(const cf_dw_args a, const T5P
             float s = 0.f;
             for (int u = start; u < 256; u += CQ) s += red[v * 256 + u];
             const int j = v >> 2, i = v & 3;
-            atomicAdd(a.y + (size_t)(q * 4 + i) * 5 + j, s);
+            atomicAdd(dwp + (size_t)(q * 4 + i) * 5 + j, s);
         }
     } else if (a.stats_mode != CF_STATS_NONE) {
         red[0 * 256 + tid] = s1.x; red[1 * 256 + tid] = s1.y; red[2 * 256 + tid] = s1.z; red[3 * 256 + tid] = s1.w;
@@ -145,7 +161,8 @@ __global__ void __launch_bounds__(256) dwt5_kernel(const cf_dw_args a, const T5P
     }
 }
 
-// mode: 0 forward, 1 data gradient, 2 weight gradient.  Returns CF_OK when launched, -1 when not eligible.
+// mode: 0 forward, 1 data gradient, 2 weight gradient, 3 data + weight gradient (a->dw_out).  Returns CF_OK when launched,
+// -1 when not eligible.
 int cf_dwt5_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (cf_env("CFNET_DWT5_OFF", 0)) return -1;
     const cf_geom& g = a->g;
@@ -158,7 +175,8 @@ int cf_dwt5_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (al & 15) return -1;
     if (mode == T5_FWD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE_RELU)) return -1;
     if (mode == T5_FWD && a->stats_mode == CF_STATS_SUM_AUX) return -1;
-    if (mode == T5_DGRAD && (a->epi_mode != CF_EPI_NONE || a->stats_mode != CF_STATS_NONE)) return -1;
+    if ((mode == T5_DGRAD || mode == T5_FUSED) && (a->epi_mode != CF_EPI_NONE || a->stats_mode != CF_STATS_NONE)) return -1;
+    if (mode == T5_FUSED && !(a->dw_out && a->aux)) return -1;
     if (mode != T5_FWD && !(a->pro_mode == CF_PRO_NONE || a->pro_mode == CF_PRO_AFFINE || a->pro_mode == CF_PRO_AFFINE2)) return -1;
     T5Params p;
     p.B = a->B; p.C = a->C; p.T = g.T;
@@ -174,6 +192,7 @@ int cf_dwt5_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     dim3 grid((unsigned)blocks, (unsigned)p.ntseg, (unsigned)a->B);
     if (mode == T5_FWD) dwt5_kernel<T5_FWD><<<grid, 256, 0, stream>>>(*a, p);
     else if (mode == T5_DGRAD) dwt5_kernel<T5_DGRAD><<<grid, 256, 0, stream>>>(*a, p);
+    else if (mode == T5_FUSED) dwt5_kernel<T5_FUSED><<<grid, 256, 0, stream>>>(*a, p);
     else dwt5_kernel<T5_WGRAD><<<grid, 256, 0, stream>>>(*a, p);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();

@@ -369,9 +369,8 @@ class StemFn(torch.autograd.Function):
         dz = torch.empty_like(out)
         residual_bwd(dout, out, yt, dz, sums, B, C, R)
         P, Q, Rr = bn_bwd_coeffs(sums, gamma, m, i, dgam, dbet, B, C, R, ctx.cfg.training)
-        dw_call("cf_dw_conv_wgrad", dz, wt, dwt, B, C, g_t, x2=yt, pro=PRO_AFFINE2, pro_tabs=(P, Q, Rr), aux=y0)
-        dy0 = torch.empty_like(y0)
-        dw_call("cf_dw_conv_dgrad", dz, wt, dy0, B, C, g_t, x2=yt, pro=PRO_AFFINE2, pro_tabs=(P, Q, Rr))
+        dy0 = torch.empty_like(y0)                # conv1_t: data gradient + weight gradient in one march over (dz, yt, y0)
+        dw_call("cf_dw_conv_dgrad", dz, wt, dy0, B, C, g_t, x2=yt, pro=PRO_AFFINE2, pro_tabs=(P, Q, Rr), aux=y0, dw_out=dwt)
         pw_wgrad(dy0, x, dws, B, Ci * 9, C, g_s, gather_in=1)
         dx = None
         if ctx.needs_input_grad[0]:

@@ -284,6 +284,22 @@ def test_depthwise_temporal_5x1x1(X):
     dw = torch.zeros(C, 5, device="cuda")
     X.dw_call("cf_dw_conv_wgrad", rows(gy), w.cuda(), dw, B, C, g, aux=rows(x))
     close(dw, wr.grad.flatten(1), rtol=1e-5, atol=1e-4, what="conv1_t wgrad")
+    # data gradient + weight gradient from one march (dw_out), with the BatchNorm-backward prologue the stem uses,
+    # T long enough for several T segments
+    T2 = 40
+    x = synth_tensor((B, C, T2, H, W), 64)
+    d, y2 = synth_tensor((B, C, T2, H, W), 65), synth_tensor((B, C, T2, H, W), 66)
+    P, Q, Rr = synth_tensor((B, C), 67), synth_tensor((B, C), 68), synth_tensor((B, C), 69)
+    v = lambda t: t.view(B, -1, 1, 1, 1)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    F.conv3d(xr, wr, padding=(2, 0, 0), groups=C).backward(v(P) * d + v(Q) * y2 + v(Rr))
+    g2 = X.geom(T2, H, W, k=(5, 1, 1), p=(2, 0, 0))
+    dx2 = X.new_act(B, C, T2, H, W, "cuda")
+    dwf = torch.ones(C, 5, device="cuda")
+    X.dw_call("cf_dw_conv_dgrad", rows(d), w.cuda(), dx2, B, C, g2, x2=rows(y2), pro=X.PRO_AFFINE2,
+              pro_tabs=(P.cuda(), Q.cuda(), Rr.cuda()), aux=rows(x), dw_out=dwf)
+    close(dx2, xr.grad, rtol=1e-4, atol=1e-4, what="conv1_t fused dgrad")
+    close(dwf - 1.0, wr.grad.flatten(1), rtol=1e-4, atol=2e-3, what="conv1_t fused wgrad")
 
 
 # ------------------------------------------------------------------------------ module level
