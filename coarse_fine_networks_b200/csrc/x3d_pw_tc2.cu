@@ -128,6 +128,49 @@ static int p2_sm_count() {
 }
 
 
+// ---- packing many weights in one launch (the channel tile of the default tiling; cf_pw_conv_tc re-packs if it narrows it)
+extern "C" int cf_pw_pack_nt(int K, int N) {
+    if (K <= 0 || N <= 0) return 0;
+    P2Params p;
+    p2_tiling(K, N, p);
+    return p.NT;
+}
+extern "C" size_t cf_sizeof_pack_item(void) { return sizeof(cf_pack_item); }
+
+__global__ void __launch_bounds__(256) pw_pack_many_kernel(const cf_pack_item* __restrict__ items) {
+    const cf_pack_item it = items[blockIdx.x];
+    const int NT = it.nt, NTp = (NT + 15) / 16 * 16;
+    const int ntiles = (it.N + NT - 1) / NT, nchunks = (it.K + TC_KC - 1) / TC_KC;
+    const long long total = (long long)ntiles * nchunks * NTp * 8;
+    for (long long i = (long long)blockIdx.y * 256 + threadIdx.x; i < total; i += (long long)gridDim.y * 256) {
+        const int q = (int)(i & 7);
+        long long t = i >> 3;
+        const int nl = (int)(t % NTp); t /= NTp;
+        const int c = (int)(t % nchunks);
+        const int j = (int)(t / nchunks);
+        const int n = j * NT + nl;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = c * TC_KC + q * 4 + e;
+            const float v = (nl < NT && n < it.N && k < it.K) ? __ldg(it.w + (long long)n * it.w_sn + (long long)k * it.w_sk) : 0.f;
+            tf32_split(v, hi[e], lo[e]);
+        }
+        char* blk = (char*)it.pack + ((long long)(j * nchunks + c) * 2 * NTp * 128);
+        const uint32_t off = sw128_off(nl, q);
+        *reinterpret_cast<float4*>(blk + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(blk + (size_t)NTp * 128 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+extern "C" int cf_pw_pack_many(const cf_pack_item* items, int n, cudaStream_t stream) {
+    CF_CHECK_ARG(items && n > 0 && n <= 65535, "bad argument");
+    pw_pack_many_kernel<<<dim3((unsigned)n, 8), 256, 0, stream>>>(items);
+    CF_COUNT_LAUNCH(1);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+}
+
 // debug: cycle counters of CTA 0 of the last persistent launch (built with -DCFNET_P2_TIMING -DCFNET_AB, CFNET_PW_TC_TIMING=1)
 extern "C" int cf_pw_tc_debug_read(long long* out16) {
     long long zero[32] = {0};
@@ -256,7 +299,8 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     p.acc_stride = (p.NTp + 31) / 32 * 32;
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < 2 * p.acc_stride) p.tmem_cols <<= 1;
-    cf_pw_tc_pack_launch(a->w, a->w_sn, a->w_sk, a->wpack, K, N, p.NT, p.NTp, p.ntiles, p.nchunks, stream);
+    const bool prepacked = a->wpack_nt > 0 && a->wpack_nt == p.NT;   // packed once per optimizer step by cf_pw_pack_many
+    if (!prepacked) cf_pw_tc_pack_launch(a->w, a->w_sn, a->w_sk, a->wpack, K, N, p.NT, p.NTp, p.ntiles, p.nchunks, stream);
     static CfOncePerDevice attr_done;
     if (attr_done.need()) {
         cudaError_t e = cudaFuncSetAttribute(p2w8::pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_MAX);
@@ -272,7 +316,7 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     p.g_j = (int)(grid % p.ntiles);
     p.g_rt = (int)(grid / p.ntiles);
     p2w8::pw_tc2_kernel<<<(unsigned)grid, (8 + 4 + 8) * 32, smem, stream>>>(*a, a->wpack, p, av, ev, tmx, tmx2);
-    CF_COUNT_LAUNCH(2);
+    CF_COUNT_LAUNCH(prepacked ? 1 : 2);
     CF_CHECK_LAUNCH();
     return CF_OK;
 }

@@ -131,6 +131,9 @@ class FlatTrainer:
             p._cf_grad = self.flat_g[off:off + n].view(p.shape)
             p.grad = p._cf_grad
         self._offs, self._n_base = offs, len(base)
+        if dev.type == "cuda":
+            from . import x3d_ops
+            x3d_ops.PACKS.register(self.flat_p)      # GEMM weights inside this buffer keep persistent packs (x3d_ops.PackCache)
         self.lr, self.momentum, self.weight_decay, self.fusion_lr_mult = lr, momentum, weight_decay, fusion_lr_mult
         self.fusion_lr = None          # explicit learning rate of the fusion group (set by lr_warmup); None = lr * fusion_lr_mult
         self.group = process_group
@@ -154,6 +157,9 @@ class FlatTrainer:
         lr0, lr1 = self.lrs()
         call("cf_sgd_flat", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_v), self.n, self.n_split, lr0, lr1,
              float(self.momentum), float(self.weight_decay), 1.0 / self.world, stream_ptr())
+        if self.flat_p.is_cuda:
+            from . import x3d_ops
+            x3d_ops.PACKS.weights_changed()          # one launch re-packs every GEMM weight of the step (cf_pw_pack_many)
 
     def step(self):
         self.allreduce()

@@ -43,18 +43,91 @@ def geom(T, H, W, Ti=None, Hi=None, Wi=None, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 
 USE_TC = True
 
 
+class PackCache:
+    """Packed (hi/lo TF32 split, swizzled) copies of GEMM weights that live across conv calls.
+
+    Without it every tensor-core pw_conv launches a small packing kernel first (272 per training step).  Weights owned by a
+    train.FlatTrainer change exactly once per step, so the trainer registers its flat parameter buffer here; a conv whose
+    weight lies inside a registered buffer keeps a persistent pack, and FlatTrainer.step() re-packs ALL of them with ONE
+    launch (cf_pw_pack_many) right after the SGD update.  An entry is trusted only if (i) the global weights version is
+    the one it was packed at and (ii) the tensor's autograd version counter is unchanged (load_state_dict / in-place edits
+    bump it) -- otherwise the call packs again.  Weights outside registered buffers are packed per call as before."""
+
+    def __init__(self):
+        self.ranges = []           # [(lo, hi, weakref to the flat buffer)]
+        self.entries = {}          # (ptr, w_sn, w_sk, K, N) -> dict(buf, nt, gver, tver, w)
+        self.gver = 0
+        self._items = None
+        self._items_n = -1
+
+    def register(self, flat):
+        import weakref
+        self.ranges.append((flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size(), weakref.ref(flat)))
+
+    def _owned(self, ptr_):
+        alive = [r for r in self.ranges if r[2]() is not None]
+        if len(alive) != len(self.ranges):                      # a trainer went away: drop its packs
+            self.ranges = alive
+            self.entries = {k: e for k, e in self.entries.items() if any(lo <= k[0] < hi for lo, hi, _ in alive)}
+            self._items_n = -1
+        return any(lo <= ptr_ < hi for lo, hi, _ in self.ranges)
+
+    def lookup(self, w, w_sn, w_sk, K, N, nbytes):
+        """-> (buffer, wpack_nt) for a weight inside a registered buffer, else None."""
+        if not self.ranges or not self._owned(w.data_ptr()):
+            return None
+        key = (w.data_ptr(), int(w_sn), int(w_sk), int(K), int(N))
+        e = self.entries.get(key)
+        if e is None:
+            e = dict(buf=torch.empty(nbytes // 4, device=w.device, dtype=torch.float32), nt=int(lib.cf_pw_pack_nt(K, N)), gver=-1,
+                     tver=-1, w=w)
+            self.entries[key] = e
+        if e["gver"] == self.gver and e["tver"] == w._version:
+            return e["buf"], e["nt"]
+        e["gver"], e["tver"], e["w"] = self.gver, w._version, w       # this call packs into the persistent buffer
+        return e["buf"], 0
+
+    def weights_changed(self):
+        """Called by FlatTrainer after the SGD kernel: every registered weight changed; re-pack all known ones in one launch."""
+        self.gver += 1
+        if not self.entries:
+            return
+        if self._items_n != len(self.entries):
+            import ctypes
+            Item = STRUCTS["cf_pack_item"]
+            arr = (Item * len(self.entries))()
+            for i, ((p_, sn, sk, K, N), e) in enumerate(self.entries.items()):
+                arr[i].w, arr[i].pack, arr[i].w_sn, arr[i].w_sk = p_, e["buf"].data_ptr(), sn, sk
+                arr[i].K, arr[i].N, arr[i].nt, arr[i].pad = K, N, e["nt"], 0
+            raw = bytes(arr)
+            dev = next(iter(self.entries.values()))["buf"].device
+            self._items = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            self._items_n = len(self.entries)
+        call("cf_pw_pack_many", ptr(self._items), self._items_n, stream_ptr())
+        for e in self.entries.values():
+            e["gver"], e["tver"] = self.gver, e["w"]._version
+
+
+PACKS = PackCache()
+
+
 def pw_conv(x, w, y, B, K, N, g, *, w_sn=None, w_sk=1, x2=None, bias=None, pro=PRO_NONE, pro_tabs=(None, None, None),
             epi=EPI_NONE, aux=None, epi_tabs=(None, None), stats=None, stats_mode=STATS_NONE, gather_in=0, scatter_out=0,
             accumulate=0, tc=None):
-    wpack, wbytes = None, 0
+    wpack, wbytes, wnt = None, 0, 0
     strided_1x1 = (g.kt * g.kh * g.kw == 1 and g.ch_stride == 1 and g.pt == 0 and g.ph == 0 and g.pw == 0)
+    sn = K if w_sn is None else w_sn
     if (USE_TC if tc is None else tc) and ((not gather_in and not scatter_out) or strided_1x1):
         wbytes = int(lib.cf_pw_tc_ws_bytes(K, N))
-        wpack = torch.empty(wbytes // 4, device=y.device, dtype=torch.float32)
+        hit = PACKS.lookup(w, sn, w_sk, K, N, wbytes)
+        if hit is not None:
+            wpack, wnt = hit
+        else:
+            wpack = torch.empty(wbytes // 4, device=y.device, dtype=torch.float32)
     a = make("cf_pw_args", x=x, x2=x2, w=w, bias=bias, y=y, pro_a=pro_tabs[0], pro_b=pro_tabs[1], pro_c=pro_tabs[2],
-             aux=aux, epi_a=epi_tabs[0], epi_b=epi_tabs[1], stats=stats, w_sn=(K if w_sn is None else w_sn), w_sk=w_sk,
+             aux=aux, epi_a=epi_tabs[0], epi_b=epi_tabs[1], stats=stats, w_sn=sn, w_sk=w_sk,
              B=B, K=K, N=N, g=g, gather_in=gather_in, scatter_out=scatter_out, accumulate=accumulate, pro_mode=pro,
-             epi_mode=epi, stats_mode=stats_mode, wpack=wpack, wpack_bytes=wbytes)
+             epi_mode=epi, stats_mode=stats_mode, wpack=wpack, wpack_bytes=wbytes, wpack_nt=wnt)
     call_struct("cf_pw_conv", a)
     return y
 

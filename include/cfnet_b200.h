@@ -158,10 +158,25 @@ typedef struct {
                           * problem is dense (no gather / scatter) the GEMM runs on the tcgen05 tensor cores
                           * (3xTF32, fp32 accumulation in TMEM); NULL selects the fp32 CUDA-core kernel. */
     int64_t wpack_bytes;
+    int wpack_nt;        /* 0: wpack is scratch, this call packs w into it.  > 0: wpack already holds w packed by
+                          * cf_pw_pack_many with channel tile cf_pw_pack_nt(K,N) == wpack_nt (weights that did not
+                          * change since): the persistent kernel skips its packing launch when its tiling matches. */
 } cf_pw_args;
 int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream);
 /* bytes of the packed (hi/lo split, swizzled) weight workspace of the tensor-core path */
 size_t cf_pw_tc_ws_bytes(int K, int N);
+/* Packing the weights of MANY GEMMs in one launch (once per optimizer step instead of once per conv call):
+ * item i packs w (strides w_sn, w_sk; [N,K] logical) into pack (cf_pw_tc_ws_bytes(K,N) bytes) with the channel tile
+ * nt = cf_pw_pack_nt(K,N).  `items` is a DEVICE array of n items. */
+typedef struct {
+    const float* w;
+    float* pack;
+    int64_t w_sn, w_sk;
+    int K, N, nt, pad;
+} cf_pack_item;
+int cf_pw_pack_nt(int K, int N);
+int cf_pw_pack_many(const cf_pack_item* items, int n, cudaStream_t stream);
+size_t cf_sizeof_pack_item(void);
 /* debug: per-role cycle counters of CTA 0 of the last tensor-core launch made with CFNET_PW_TC_TIMING=1 (24 values) */
 int cf_pw_tc_debug_read(long long* out16);
 
