@@ -470,3 +470,25 @@ def test_fine_net_global_tower_vs_oracle():
     for k in ("layer1", "layer2", "layer3", "layer4", "conv5"):
         assert feats[k].shape == ref[k].shape
         close(feats[k], ref[k], rtol=2e-4, atol=2e-5, what=k)
+
+
+def test_x3d_xl_variant_runs_and_matches_the_oracle():
+    """generate_model('XL') (x3d_fine.py:388-402: blocks [5,10,25,15], widths 72/162/306/630 -> 32/72/136/280): none of the
+    widths is a multiple of 54, so every depthwise conv takes the general kernels and the GEMMs other tilings; train-mode
+    logits against the oracle on a small clip (train mode: the key-hashed synthetic running statistics do not describe a
+    normalised net), and the backward runs."""
+    from coarse_fine_networks_b200 import x3d_fine as M
+    m = M.generate_model("XL", n_classes=7, task="loc", base_bn_splits=1, dropout=0.0)
+    sd = synth_state_dict(m.state_dict(), 91)
+    m.load_state_dict(sd, strict=True)
+    x = synth_tensor((2, 3, 4, 64, 64), 92)
+    with torch.no_grad():
+        ref = O.fine_forward(sd, x, True)
+    m.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    o2 = m([xg, None])
+    assert o2.shape == (2, 7, 4)
+    err = (o2.detach().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 1e-3, err
+    o2.square().mean().backward()
+    assert torch.isfinite(xg.grad).all() and all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
