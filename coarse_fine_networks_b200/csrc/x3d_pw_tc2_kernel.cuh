@@ -271,7 +271,7 @@ __device__ __forceinline__ void p2_loader(const cf_pw_args& a, const P2Params& p
     P2Item it;
     for (p2_first(it, p); it.valid; p2_advance(it, p)) {
         if (p.fold != 1 && it.c != 0) continue;
-        mbar_wait_b(&rempty[rs], rph ^ 1u);                  // every producer warp has read this raw stage
+        mbar_wait_relaxed(&rempty[rs], rph ^ 1u);            // every producer warp has read this raw stage
         uint8_t* dst = raw + (size_t)rs * p.raw_stage_bytes;
         mbar_expect_tx(&rfull[rs], bytes);
         const int c0 = p.fold == 1 ? it.c * TC_KC : 0, c1 = it.r0 / p.fold;
