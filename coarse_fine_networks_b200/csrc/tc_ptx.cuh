@@ -148,18 +148,6 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
     }
     __trap();
 }
-// The same bounded wait for a role that runs far ahead of its consumers (the TMA loader lane): no burst of polls, a longer
-// back-off -- a polling warp takes issue slots from the working warps of its scheduler.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    if (mbar_try(addr, parity)) return;
-#pragma unroll 1
-    for (int spin = 0; spin < (1 << 21); ++spin) {
-        __nanosleep(512);
-        if (mbar_try(addr, parity)) return;
-    }
-    __trap();
-}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -280,10 +280,11 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const cf_residual_bwd
     const int b = blockIdx.y, C = a.C, CV = C / V, tid = threadIdx.x;
     for (int i = tid; i < 4 * C; i += 256) sm[i] = 0.f;
     __syncthreads();
-    const int PY = 256 / CV, cv = tid % CV, lane = tid / CV;
+    // 256 threads = PY row lanes x CVb channel vectors; more than 256 channel vectors (X3D-XL: 630 channels) are taken in slabs
+    const int CVb = CV < 256 ? CV : 256, PY = 256 / CVb, cvl = tid % CVb, lane = tid / CVb;
     long long r0 = (long long)blockIdx.x * chunk;
     long long r1 = r0 + chunk < a.rows_per_sample ? r0 + chunk : a.rows_per_sample;
-    if (lane < PY) {
+    if (lane < PY) for (int cv = cvl; cv < CV; cv += CVb) {
         const int c0 = cv * V;
         VecF<V> s0, s1, s2;
 #pragma unroll
@@ -378,13 +379,13 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const cf_pool_bwd_args
     const bool do_sums = a.sums != nullptr;
     if (do_sums) for (int i = tid; i < 2 * C; i += 256) sm[i] = 0.f;
     __syncthreads();
-    const int PY = 256 / CV, cv = tid % CV, lane = tid / CV;
+    const int CVb = CV < 256 ? CV : 256, PY = 256 / CVb, cvl = tid % CVb, lane = tid / CVb;       // channel vectors in slabs of 256
     const int Ho = a.H / a.rh, Wo = a.W / a.rw;
     const long long R = (long long)a.T * a.H * a.W;
     long long r0 = (long long)blockIdx.x * chunk;
     long long r1 = r0 + chunk < R ? r0 + chunk : R;
     const float inv = 1.0f / (float)(a.rh * a.rw);
-    if (lane < PY) {
+    if (lane < PY) for (int cv = cvl; cv < CV; cv += CVb) {
         const int c0 = cv * V;
         VecF<V> ta, tb, s0, s1;
         const bool pro = a.tab_a != nullptr;
@@ -522,8 +523,7 @@ extern "C" int cf_residual_bwd(const cf_residual_bwd_args* a, cudaStream_t strea
     int v = vec_for(a->C, a->dout ? a->dout : a->out, a->out, a->y, a->dz);
     if (a->dpool && (((uintptr_t)a->dpool) & 15) && v == 4) v = 2;
     if (a->res && (((uintptr_t)a->res) & 15) && v == 4) v = 2;
-    if (a->C / v > 256) { cf_set_error("cf_residual_bwd: C/vec > 256"); return CF_ERR_ARG; }
-    int chunk = chunk_for(a->rows_per_sample, a->B, 256 / (a->C / v));
+    int chunk = chunk_for(a->rows_per_sample, a->B, 256 / (a->C / v > 256 ? 256 : a->C / v));
     dim3 grid((unsigned)cf_cdiv64(a->rows_per_sample, chunk), (unsigned)a->B);
     size_t smem = (size_t)4 * a->C * 4;
     if (v == 4) residual_bwd_kernel<4><<<grid, 256, smem, stream>>>(*a, chunk);
@@ -555,9 +555,8 @@ extern "C" int cf_block_avgpool_bwd(const cf_pool_bwd_args* a, cudaStream_t stre
     CF_CHECK_ARG(!a->tab_a || (a->x && a->tab_b), "prologue tables need x");
     CF_CHECK_ARG(!a->sums || a->x, "sums need x");
     int v = vec_for(a->C, a->dy, a->dz, a->x, nullptr);
-    if (a->C / v > 256) { cf_set_error("cf_block_avgpool_bwd: C/vec > 256"); return CF_ERR_ARG; }
     long long R = (long long)a->T * a->H * a->W;
-    int chunk = chunk_for(R, a->B, 256 / (a->C / v));
+    int chunk = chunk_for(R, a->B, 256 / (a->C / v > 256 ? 256 : a->C / v));
     dim3 grid((unsigned)cf_cdiv64(R, chunk), (unsigned)a->B);
     size_t smem = (size_t)2 * a->C * 4;
     if (v == 4) avgpool_bwd_kernel<4><<<grid, 256, smem, stream>>>(*a, chunk);
@@ -591,10 +590,10 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
     const int b = blockIdx.y, CV = C / V, tid = threadIdx.x;
     for (int i = tid; i < 2 * C; i += 256) sm[i] = 0.f;
     __syncthreads();
-    const int PY = 256 / CV, cv = tid % CV, lane = tid / CV;
+    const int CVb = CV < 256 ? CV : 256, PY = 256 / CVb, cvl = tid % CVb, lane = tid / CVb;
     long long r0 = (long long)blockIdx.x * chunk;
     long long r1 = r0 + chunk < rows ? r0 + chunk : rows;
-    if (lane < PY) {
+    if (lane < PY) for (int cv = cvl; cv < CV; cv += CVb) {
         const int c0 = cv * V;
         VecF<V> s0, s1;
 #pragma unroll
@@ -650,9 +649,8 @@ __global__ void swish_bwd_kernel(const float* __restrict__ x, const float* __res
 extern "C" int cf_channel_stats(const float* x, const float* y, double* stats, int B, int C, int64_t rows, cudaStream_t stream) {
     CF_CHECK_ARG(x && stats && B > 0 && B <= 65535 && C > 0 && rows > 0, "bad argument");
     int v = vec_for(C, x, y, nullptr, nullptr);
-    while (C / v > 256 && v < 4) v *= 2;
-    if (C / v > 256 || C % v) { cf_set_error("cf_channel_stats: C too large"); return CF_ERR_ARG; }
-    int chunk = chunk_for(rows, B, 256 / (C / v));
+    if (C % v) { cf_set_error("cf_channel_stats: bad channel count"); return CF_ERR_ARG; }
+    int chunk = chunk_for(rows, B, 256 / ((C / v) > 256 ? 256 : (C / v)));
     dim3 grid((unsigned)cf_cdiv64(rows, chunk), (unsigned)B);
     size_t smem = (size_t)2 * C * 4;
     if (v == 4) channel_stats_kernel<4><<<grid, 256, smem, stream>>>(x, y, stats, C, rows, chunk);

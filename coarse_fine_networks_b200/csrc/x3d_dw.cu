@@ -257,12 +257,12 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const cf_dw_args a, int c
     const int tid = threadIdx.x, b = blockIdx.y;
     for (int i = tid; i < TAPS * C; i += 256) sm[i] = 0.f;
     __syncthreads();
-    const int CV = C / V, PY = 256 / CV;
-    const int cv = tid % CV, lane = tid / CV;
+    const int CV = C / V, CVb = CV < 256 ? CV : 256, PY = 256 / CVb;          // channel vectors in slabs of 256 (X3D-XL: 630 channels)
+    const int cvl = tid % CVb, lane = tid / CVb;
     const long long R = (long long)g.T * g.H * g.W;
     const long long p0 = (long long)blockIdx.x * chunk;
     const long long p1 = p0 + chunk < R ? p0 + chunk : R;
-    if (lane < PY) {
+    if (lane < PY) for (int cv = cvl; cv < CV; cv += CVb) {
         const int c0 = cv * V;
         Vec<V> da, db, dc, xa, xb;
 #pragma unroll
@@ -470,13 +470,13 @@ __global__ void __launch_bounds__(256) dw_wgrad3_kernel(const cf_dw_args a, int 
     __syncthreads();
     constexpr int TWG = 2;
     constexpr int SPAN = (TWG - 1) * ST + 3;
-    const int CV = C / V, PY = 256 / CV;
-    const int cv = tid % CV, lane = tid / CV;
+    const int CV = C / V, CVb = CV < 256 ? CV : 256, PY = 256 / CVb;          // channel vectors in slabs of 256 (X3D-XL: 630 channels)
+    const int cvl = tid % CVb, lane = tid / CVb;
     const int WG = (g.W + TWG - 1) / TWG;
     const long long NG = (long long)g.T * g.H * WG;          // position groups per sample
     const long long p0 = (long long)blockIdx.x * chunk;
     const long long p1 = p0 + chunk < NG ? p0 + chunk : NG;
-    if (lane < PY) {
+    if (lane < PY) for (int cv = cvl; cv < CV; cv += CVb) {
         const int c0 = cv * V;
         const bool aff2 = a.pro_mode == CF_PRO_AFFINE2;
         const bool act = a.epi_a != nullptr;
@@ -619,7 +619,7 @@ static int launch_dw_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     const cf_geom& g = a->g;
     size_t smem = (size_t)TAPS * a->C * sizeof(float);
     long long R = (long long)g.T * g.H * g.W;
-    int PY = 256 / (a->C / V);
+    int PY = 256 / ((a->C / V) > 256 ? 256 : (a->C / V));
     long long want_ctas = cf_cdiv64(148 * 4, a->B);
     long long chunk = cf_cdiv64(R, want_ctas);
     if (chunk < 4LL * PY) chunk = 4LL * PY;
@@ -656,7 +656,7 @@ static int launch_dw_wgrad3(const cf_dw_args* a, cudaStream_t stream) {
     const cf_geom& g = a->g;
     size_t smem = (size_t)27 * a->C * sizeof(float);
     long long NG = (long long)g.T * g.H * ((g.W + 1) / 2);
-    int PY = 256 / (a->C / V);
+    int PY = 256 / ((a->C / V) > 256 ? 256 : (a->C / V));
     long long want_ctas = cf_cdiv64(148 * 4, a->B);
     long long chunk = cf_cdiv64(NG, want_ctas);
     if (chunk < 4LL * PY) chunk = 4LL * PY;
@@ -765,7 +765,6 @@ extern "C" int cf_dw_conv_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     if (rc >= 0) return rc;
     int taps = a->g.kt * a->g.kh * a->g.kw;
     int v = pick_vec(a->C, a->x, a->aux);
-    if (a->C / v > 256) { cf_set_error("cf_dw_conv_wgrad: C/vec > 256"); return CF_ERR_ARG; }
     if (is_333(a->g)) {
         const bool s2 = a->g.sh == 2;
         if (v == 4) return s2 ? launch_dw_wgrad3<4, 2>(a, stream) : launch_dw_wgrad3<4, 1>(a, stream);

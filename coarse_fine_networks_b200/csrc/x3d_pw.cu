@@ -185,12 +185,15 @@ __global__ void __launch_bounds__(256) pw_conv_kernel(const cf_pw_args a, int ti
             if (n >= N) continue;
             float v = acc[i][j] + bi[j];
             float auxv = 0.f;
-            if ((epi >= CF_EPI_DRELU && epi <= CF_EPI_ADD_AUX) || smode == CF_STATS_SUM_AUX) auxv = __ldg(a.aux + dense + n);
+            if ((epi >= CF_EPI_DRELU && epi <= CF_EPI_ADD_AUX) || epi == CF_EPI_AFFINE_ADD_RELU || smode == CF_STATS_SUM_AUX)
+                auxv = __ldg(a.aux + dense + n);
             if (epi == CF_EPI_RELU) v = fmaxf(v, 0.f);
             else if (epi == CF_EPI_DRELU) v = (fmaf(ea[j], auxv, eb[j]) > 0.f) ? v : 0.f;
             else if (epi == CF_EPI_DSWISH) v *= cf_dswish(fmaf(ea[j], auxv, eb[j]));
             else if (epi == CF_EPI_ADD_AUX) v += auxv;
             else if (epi == CF_EPI_SIGMOID) v = cf_sigmoid(v);
+            else if (epi == CF_EPI_AFFINE) v = fmaf(ea[j], v, eb[j]);
+            else if (epi == CF_EPI_AFFINE_ADD_RELU) v = fmaxf(fmaf(ea[j], v, eb[j]) + auxv, 0.f);
             s1[j] += v;
             s2[j] += (smode == CF_STATS_SUM_AUX) ? v * auxv : v * v;
             if (!a.scatter_out) {
@@ -370,7 +373,9 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a->B > 0 && a->K > 0 && a->N > 0 && geom_ok(a->g, a->gather_in || a->scatter_out), "bad shape");
     CF_CHECK_ARG(a->pro_mode == CF_PRO_NONE || a->pro_a, "prologue tables missing");
     CF_CHECK_ARG(a->pro_mode != CF_PRO_AFFINE2 || (a->x2 && !a->gather_in), "AFFINE2 needs a dense second input");
-    CF_CHECK_ARG(((a->epi_mode < CF_EPI_DRELU || a->epi_mode > CF_EPI_ADD_AUX) && a->stats_mode != CF_STATS_SUM_AUX) || a->aux, "aux tensor missing");
+    CF_CHECK_ARG(((a->epi_mode < CF_EPI_DRELU || a->epi_mode > CF_EPI_ADD_AUX) && a->epi_mode != CF_EPI_AFFINE_ADD_RELU &&
+                  a->stats_mode != CF_STATS_SUM_AUX) || a->aux, "aux tensor missing");
+    CF_CHECK_ARG((a->epi_mode != CF_EPI_AFFINE && a->epi_mode != CF_EPI_AFFINE_ADD_RELU) || (a->epi_a && a->epi_b), "epilogue tables missing");
     CF_CHECK_ARG(a->stats_mode == CF_STATS_NONE || a->stats, "stats buffer missing");
     CF_CHECK_ARG(!(a->gather_in && a->scatter_out), "gather_in and scatter_out are exclusive");
     int taps = a->g.kt * a->g.kh * a->g.kw;

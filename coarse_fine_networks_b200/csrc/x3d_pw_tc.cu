@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const cf_pw_args a, c
             s1[e] = 0.f;
             s2[e] = 0.f;
         }
-        const bool need_aux = (epi >= CF_EPI_DRELU && epi <= CF_EPI_ADD_AUX) || smode == CF_STATS_SUM_AUX;
+        const bool need_aux = (epi >= CF_EPI_DRELU && epi <= CF_EPI_ADD_AUX) || epi == CF_EPI_AFFINE_ADD_RELU || smode == CF_STATS_SUM_AUX;
         for (int r = rs; r < rows_valid; r += rpp) {
             const size_t dense = ((size_t)b * R + r0 + r) * N + n;
             float vv[EV], ax[EV];
@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const cf_pw_args a, c
                 else if (epi == CF_EPI_DSWISH) t *= tc_dswish(fmaf(ea[e], ax[e], eb[e]));
                 else if (epi == CF_EPI_ADD_AUX) t += ax[e];
                 else if (epi == CF_EPI_SIGMOID) t = cf_sigmoid(t);
+                else if (epi == CF_EPI_AFFINE) t = fmaf(ea[e], t, eb[e]);
+                else if (epi == CF_EPI_AFFINE_ADD_RELU) t = fmaxf(fmaf(ea[e], t, eb[e]) + ax[e], 0.f);
                 vv[e] = t;
                 s1[e] += t;
                 s2[e] += (smode == CF_STATS_SUM_AUX) ? t * ax[e] : t * t;

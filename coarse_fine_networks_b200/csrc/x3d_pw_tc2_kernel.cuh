@@ -271,7 +271,7 @@ __device__ __forceinline__ void p2_loader(const cf_pw_args& a, const P2Params& p
     P2Item it;
     for (p2_first(it, p); it.valid; p2_advance(it, p)) {
         if (p.fold != 1 && it.c != 0) continue;
-        mbar_wait_relaxed(&rempty[rs], rph ^ 1u);            // every producer warp has read this raw stage
+        mbar_wait_b(&rempty[rs], rph ^ 1u);                  // every producer warp has read this raw stage
         uint8_t* dst = raw + (size_t)rs * p.raw_stage_bytes;
         mbar_expect_tx(&rfull[rs], bytes);
         const int c0 = p.fold == 1 ? it.c * TC_KC : 0, c1 = it.r0 / p.fold;
@@ -486,7 +486,7 @@ __device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const P2Param
                                               float* __restrict__ dp, const float* __restrict__ ap, size_t gstep, int rs, int rows_valid,
                                               const float* bi, const float* ea, const float* eb, bool has_bias, float* s1, float* s2) {
     constexpr int CPR = 32 / EV, RPP = 128 / CPR, NPASS = TC_BM / RPP;
-    constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX;
+    constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX || EPI == CF_EPI_AFFINE_ADD_RELU;
     constexpr bool NEED_AUX = EPI_AUX || SMODE == CF_STATS_SUM_AUX;
     float ax[NEED_AUX ? NPASS : 1][EV];
     if (NEED_AUX) {
@@ -517,6 +517,8 @@ __device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const P2Param
             else if (EPI == CF_EPI_DSWISH) t *= p2_dswish(fmaf(ea[e], axe[e], eb[e]));
             else if (EPI == CF_EPI_ADD_AUX) t += axe[e];
             else if (EPI == CF_EPI_SIGMOID) t = p2_sigmoid(t);
+            else if (EPI == CF_EPI_AFFINE) t = fmaf(ea[e], t, eb[e]);
+            else if (EPI == CF_EPI_AFFINE_ADD_RELU) t = fmaxf(fmaf(ea[e], t, eb[e]) + axe[e], 0.f);
             vv[e] = t;
         }
         if (SMODE != CF_STATS_NONE) {
@@ -558,8 +560,9 @@ __device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const P2Param
 #pragma unroll
         for (int e = 0; e < EV; ++e) {
             bi[e] = a.bias ? a.bias[n + e] : 0.f;
-            ea[e] = (EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH) ? a.epi_a[(size_t)b * N + n + e] : 1.f;
-            eb[e] = (EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH) ? a.epi_b[(size_t)b * N + n + e] : 0.f;
+            constexpr bool EPI_TAB = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_AFFINE || EPI == CF_EPI_AFFINE_ADD_RELU;
+            ea[e] = EPI_TAB ? a.epi_a[(size_t)b * N + n + e] : 1.f;
+            eb[e] = EPI_TAB ? a.epi_b[(size_t)b * N + n + e] : 0.f;
         }
         const size_t g0 = ((size_t)b * R + r0 + rs) * N + n;
         const size_t gstep = (size_t)RPP * N;
@@ -788,6 +791,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args 
         case CF_EPI_DSWISH: P2_EPI_S(EV_, CF_EPI_DSWISH) break;          \
         case CF_EPI_ADD_AUX: P2_EPI_S(EV_, CF_EPI_ADD_AUX) break;        \
         case CF_EPI_SIGMOID: P2_EPI_S(EV_, CF_EPI_SIGMOID) break;        \
+        case CF_EPI_AFFINE: P2_EPI_S(EV_, CF_EPI_AFFINE) break;          \
+        case CF_EPI_AFFINE_ADD_RELU: P2_EPI_S(EV_, CF_EPI_AFFINE_ADD_RELU) break; \
         default: P2_EPI_S(EV_, CF_EPI_NONE) break;                       \
     }
         if (ev == 4) { P2_EPI(4) } else { P2_EPI(2) }

@@ -22,7 +22,6 @@
 #include "tma_host.cuh"
 #include <stdlib.h>
 #include <string.h>
-#include <type_traits>
 
 #define WG_PROD_WARPS 16
 #define WG_PROD_THREADS (WG_PROD_WARPS * 32)
@@ -263,143 +262,122 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
             // loader lane with cp.async.bulk.tensor); read -> prologue -> hi/lo split -> swizzled operand stage.
             // Written for a SHORT instruction stream: the ncu source view of round 1's producers showed ~510 issue slots per
             // thread and 64-row stage of which ~10 % were loads / FMAs / stores -- the rest address arithmetic, predicates
-            // and reconvergence of the generic batch / unit bookkeeping.  Here: one loop per tensor, the fold of each tensor a
-            // compile-time constant, every kernel parameter the loop uses in a register, all offsets of a thread (row,
-            // 16-byte slot) computed once, nothing per unit but constant strides.
-            auto tma_loop = [&](auto fdy_c, auto fx_c) {
-                constexpr int FDY = decltype(fdy_c)::value, FX = decltype(fx_c)::value;
-                int rs = 0;
-                uint32_t rph = 0;
-                const uint32_t chunk = p.chunk_bytes, raw_dy = p.raw_dy_bytes, raw_stage = p.raw_stage_bytes, stage_bytes = p.stage_bytes;
-                const uint32_t dy_lo = p.dy_lo, x_lo = p.x_lo;
-                const int ndyc = p.ndyc, nxc = p.nxc, nraw = p.nraw, nstages = p.nstages, RB = p.RB, R = p.R, rbps = p.rbps;
-                const int nA = ndyc * 32, nB = nxc * 32, cq = q8 * 4;
-                const uint32_t ustride = (uint32_t)groups * chunk;
-                // per-thread read offsets into a raw stage (unit `grp`), advanced by a constant per unit
-                const uint32_t rdy0 = FDY == 1 ? (uint32_t)grp * chunk + (uint32_t)row * 128u + (uint32_t)q8 * 16u
-                                               : (uint32_t)(row * N + grp * 32 + cq) * 4u;
-                const uint32_t rdy_step = FDY == 1 ? ustride : (uint32_t)groups * 128u;
-                const uint32_t rx0 = (aff2 ? 2u : 1u) * raw_dy + (FX == 1 ? (uint32_t)grp * chunk + (uint32_t)row * 128u + (uint32_t)q8 * 16u
-                                                                           : (uint32_t)(row * K + grp * 32 + cq) * 4u);
-                const uint32_t rx_step = FX == 1 ? ustride : (uint32_t)groups * 128u;
-                const uint32_t sdy0 = p.dy_off + soff + (uint32_t)grp * chunk, sx0 = p.x_off + soff + (uint32_t)grp * chunk;
-                const float* tA = tabA + cq + grp * 32;
-                const float* tB = tabB + cq + grp * 32;
-                const int tstep = groups * 32;
-                for (; item < item1; ++item) {
-                    const bool rv = row < R - rb * RB;               // (row < RB always)
-                    if (b != cur_b) {
-                        named_bar_sync(1, WG_PROD_THREADS);
-                        for (int t = tid; t < nA; t += WG_PROD_THREADS) {
-                            const int n = n_base + t;
-                            const bool v = n < N && DYM != CF_PRO_NONE;
-                            tabA[t] = v ? a.dy_a[(size_t)b * N + n] : 0.f;
-                            tabA[nA + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
-                            tabA[2 * nA + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
-                        }
-                        for (int t = tid; t < nB; t += WG_PROD_THREADS) {
-                            const int k = k_base + t;
-                            const bool v = k < K && XM != CF_PRO_NONE;
-                            tabB[t] = v ? a.x_a[(size_t)b * K + k] : 0.f;
-                            tabB[nB + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
-                        }
-                        named_bar_sync(1, WG_PROD_THREADS);
-                        cur_b = b;
+            // and reconvergence of the generic batch / unit bookkeeping.  Here: one loop per tensor, all offsets of a
+            // thread (row, 16-byte slot) computed once, nothing per unit but a constant stride.
+            int rs = 0;
+            uint32_t rph = 0;
+            const uint32_t roff1 = (uint32_t)row * 128u + (uint32_t)q8 * 16u;                  // fold == 1: [RB][32] chunks
+            const uint32_t ustride = (uint32_t)groups * p.chunk_bytes;
+            const int cq = q8 * 4;
+            const float* tA = tabA + cq;
+            const float* tB = tabB + cq;
+            const int nA = p.ndyc * 32, nB = p.nxc * 32;
+            for (; item < item1; ++item) {
+                const bool rv = row < min(p.RB, p.R - rb * p.RB);
+                if (b != cur_b) {
+                    named_bar_sync(1, WG_PROD_THREADS);
+                    for (int t = tid; t < nA; t += WG_PROD_THREADS) {
+                        const int n = n_base + t;
+                        const bool v = n < N && DYM != CF_PRO_NONE;
+                        tabA[t] = v ? a.dy_a[(size_t)b * N + n] : 0.f;
+                        tabA[nA + t] = (v && a.dy_b) ? a.dy_b[(size_t)b * N + n] : 0.f;
+                        tabA[2 * nA + t] = (v && a.dy_c) ? a.dy_c[(size_t)b * N + n] : 0.f;
                     }
-                    mbar_wait_b(&rfull[rs], rph);
-                    mbar_wait_b(&empty[s], ph ^ 1u);
-                    const uint8_t* rst = raw + (uint32_t)rs * raw_stage;
-                    uint8_t* stage = stages + (uint32_t)s * stage_bytes;
-                    // ---- dy units (this thread's group takes every `groups`-th 32-channel chunk)
-                    {
-                        const uint8_t* src = rst + rdy0;
-                        uint8_t* dst = stage + sdy0;
-                        const float* tp = tA;
-                        int c = grp * 32 + cq;
-                        for (int u = grp; u < ndyc; u += groups, src += rdy_step, dst += ustride, tp += tstep, c += tstep) {
-                            float v[4], v2[4];
-                            if (FDY == 1) {
-                                const float4 t = *reinterpret_cast<const float4*>(src);
-                                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                                if (aff2) {
-                                    const float4 t2 = *reinterpret_cast<const float4*>(src + raw_dy);
-                                    v2[0] = t2.x; v2[1] = t2.y; v2[2] = t2.z; v2[3] = t2.w;
-                                }
-                            } else {                                 // whole [RB][N] tile, 8-byte aligned rows (N even)
-#pragma unroll
-                                for (int e = 0; e < 4; e += 2) {
-                                    float2 t = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
-                                    if (c + e < N) {
-                                        t = *reinterpret_cast<const float2*>(src + e * 4);
-                                        if (aff2) t2 = *reinterpret_cast<const float2*>(src + raw_dy + e * 4);
-                                    }
-                                    v[e] = t.x; v[e + 1] = t.y; v2[e] = t2.x; v2[e + 1] = t2.y;
-                                }
-                            }
-                            float hi[4], lo[4];
-                            if (DYM != CF_PRO_NONE) {
-                                const float4 ta = *reinterpret_cast<const float4*>(tp);
-                                const float4 tb = *reinterpret_cast<const float4*>(tp + nA);
-                                const float4 tc = *reinterpret_cast<const float4*>(tp + 2 * nA);
-                                const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w}, pc[4] = {tc.x, tc.y, tc.z, tc.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) v[e] = rv ? wg_pro<DYM>(v[e], aff2 ? v2[e] : 0.f, pa[e], pb[e], pc[e]) : 0.f;
-                            }
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) tf32_split(v[e], hi[e], lo[e]);
-                            *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<float4*>(dst + dy_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                        }
+                    for (int t = tid; t < nB; t += WG_PROD_THREADS) {
+                        const int k = k_base + t;
+                        const bool v = k < K && XM != CF_PRO_NONE;
+                        tabB[t] = v ? a.x_a[(size_t)b * K + k] : 0.f;
+                        tabB[nB + t] = (v && a.x_b) ? a.x_b[(size_t)b * K + k] : 0.f;
                     }
-                    // ---- x units
-                    {
-                        const uint8_t* src = rst + rx0;
-                        uint8_t* dst = stage + sx0;
-                        const float* tp = tB;
-                        int c = grp * 32 + cq;
-                        for (int u = grp; u < nxc; u += groups, src += rx_step, dst += ustride, tp += tstep, c += tstep) {
-                            float v[4];
-                            if (FX == 1) {
-                                const float4 t = *reinterpret_cast<const float4*>(src);
-                                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; e += 2) {
-                                    float2 t = make_float2(0.f, 0.f);
-                                    if (c + e < K) t = *reinterpret_cast<const float2*>(src + e * 4);
-                                    v[e] = t.x; v[e + 1] = t.y;
-                                }
-                            }
-                            float hi[4], lo[4];
-                            if (XM != CF_PRO_NONE) {
-                                const float4 ta = *reinterpret_cast<const float4*>(tp);
-                                const float4 tb = *reinterpret_cast<const float4*>(tp + nB);
-                                const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) v[e] = rv ? wg_pro<XM>(v[e], 0.f, pa[e], pb[e], 0.f) : 0.f;
-                            }
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) tf32_split(v[e], hi[e], lo[e]);
-                            *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<float4*>(dst + x_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&rempty[rs]);                 // raw stage read: the loader may refill it
-                    if (++rs == nraw) { rs = 0; rph ^= 1u; }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[s]);
-                    if (++s == nstages) { s = 0; ph ^= 1u; }
-                    if (++rb == rbps) { rb = 0; ++b; }
+                    named_bar_sync(1, WG_PROD_THREADS);
+                    cur_b = b;
                 }
-            };
-            using I1 = std::integral_constant<int, 1>;
-            using I2 = std::integral_constant<int, 2>;
-            if (p.fold_dy == 1 && p.fold_x == 1) tma_loop(I1{}, I1{});
-            else if (p.fold_dy == 1) tma_loop(I1{}, I2{});
-            else if (p.fold_x == 1) tma_loop(I2{}, I1{});
-            else tma_loop(I2{}, I2{});
+                mbar_wait_b(&rfull[rs], rph);
+                mbar_wait_b(&empty[s], ph ^ 1u);
+                const uint8_t* rdy = raw + (size_t)rs * p.raw_stage_bytes;
+                const uint8_t* rx = rdy + (aff2 ? 2u : 1u) * p.raw_dy_bytes;
+                uint8_t* stage = stages + (size_t)s * p.stage_bytes;
+                // ---- dy units (this thread's group takes every `groups`-th 32-channel chunk)
+                {
+                    uint8_t* dst = stage + p.dy_off + soff + (uint32_t)grp * p.chunk_bytes;
+                    for (int u = grp; u < p.ndyc; u += groups, dst += ustride) {
+                        float v[4], v2[4];
+                        if (p.fold_dy == 1) {
+                            const float4 t = *reinterpret_cast<const float4*>(rdy + (uint32_t)u * p.chunk_bytes + roff1);
+                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                            if (aff2) {
+                                const float4 t2 = *reinterpret_cast<const float4*>(rdy + p.raw_dy_bytes + (uint32_t)u * p.chunk_bytes + roff1);
+                                v2[0] = t2.x; v2[1] = t2.y; v2[2] = t2.z; v2[3] = t2.w;
+                            }
+                        } else {                                 // whole [RB][N] tile, 8-byte aligned rows (N even)
+                            const int c = u * 32 + cq;
+                            const float* src = reinterpret_cast<const float*>(rdy) + row * N + c;
+#pragma unroll
+                            for (int e = 0; e < 4; e += 2) {
+                                float2 t = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
+                                if (c + e < N) {
+                                    t = *reinterpret_cast<const float2*>(src + e);
+                                    if (aff2) t2 = *reinterpret_cast<const float2*>(src + (p.raw_dy_bytes >> 2) + e);
+                                }
+                                v[e] = t.x; v[e + 1] = t.y; v2[e] = t2.x; v2[e + 1] = t2.y;
+                            }
+                        }
+                        float hi[4], lo[4];
+                        if (DYM != CF_PRO_NONE) {
+                            const float4 ta = *reinterpret_cast<const float4*>(tA + u * 32);
+                            const float4 tb = *reinterpret_cast<const float4*>(tA + nA + u * 32);
+                            const float4 tc = *reinterpret_cast<const float4*>(tA + 2 * nA + u * 32);
+                            const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w}, pc[4] = {tc.x, tc.y, tc.z, tc.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = rv ? wg_pro<DYM>(v[e], aff2 ? v2[e] : 0.f, pa[e], pb[e], pc[e]) : 0.f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) tf32_split(v[e], hi[e], lo[e]);
+                        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(dst + p.dy_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                // ---- x units
+                {
+                    uint8_t* dst = stage + p.x_off + soff + (uint32_t)grp * p.chunk_bytes;
+                    for (int u = grp; u < p.nxc; u += groups, dst += ustride) {
+                        float v[4];
+                        if (p.fold_x == 1) {
+                            const float4 t = *reinterpret_cast<const float4*>(rx + (uint32_t)u * p.chunk_bytes + roff1);
+                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                        } else {
+                            const int c = u * 32 + cq;
+                            const float* src = reinterpret_cast<const float*>(rx) + row * K + c;
+#pragma unroll
+                            for (int e = 0; e < 4; e += 2) {
+                                float2 t = make_float2(0.f, 0.f);
+                                if (c + e < K) t = *reinterpret_cast<const float2*>(src + e);
+                                v[e] = t.x; v[e + 1] = t.y;
+                            }
+                        }
+                        float hi[4], lo[4];
+                        if (XM != CF_PRO_NONE) {
+                            const float4 ta = *reinterpret_cast<const float4*>(tB + u * 32);
+                            const float4 tb = *reinterpret_cast<const float4*>(tB + nB + u * 32);
+                            const float pa[4] = {ta.x, ta.y, ta.z, ta.w}, pb[4] = {tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = rv ? wg_pro<XM>(v[e], 0.f, pa[e], pb[e], 0.f) : 0.f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) tf32_split(v[e], hi[e], lo[e]);
+                        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(dst + p.x_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rempty[rs]);                 // raw stage read: the loader may refill it
+                if (++rs == p.nraw) { rs = 0; rph ^= 1u; }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+                if (++s == p.nstages) { s = 0; ph ^= 1u; }
+                if (++rb == p.rbps) { rb = 0; ++b; }
+            }
         }
         if (!p.tma && item0 < item1 && grp < nunits) load_batch(b, rb, grp, vA, wA);
 
@@ -478,7 +456,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
             int b = (int)(item0 / p.rbps);
             int rb = (int)(item0 - (long long)b * p.rbps);
             for (long long item = item0; item < item1; ++item) {
-                mbar_wait_relaxed(&rempty[rs], rph ^ 1u);              // runs stages ahead: poll rarely, leave the issue slots to the producers
+                mbar_wait_b(&rempty[rs], rph ^ 1u);
                 uint8_t* dst = raw + (size_t)rs * p.raw_stage_bytes;
                 mbar_expect_tx(&rfull[rs], p.raw_stage_bytes);
                 const int r0 = rb * p.RB;

@@ -95,7 +95,7 @@ def se_width(width, multiplier=0.0625, min_width=8, divisor=8):
 
 
 class _BlockCfg:
-    __slots__ = ("stride", "t_stride", "training", "bn1", "bn2", "bn3", "bnd", "arena", "pool")
+    __slots__ = ("stride", "t_stride", "training", "bn1", "bn2", "bn3", "bnd", "arena", "pool", "inference")
 
 
 class Bottleneck(nn.Module):
@@ -140,6 +140,7 @@ class Bottleneck(nn.Module):
         cfg.bnd = X.BNCfg(ds[1]) if ds is not None else None
         cfg.arena = getattr(self, "_arena", None)               # set by the owning ResNet for the duration of a forward pass
         cfg.pool = pool
+        cfg.inference = (not self.training) and not torch.is_grad_enabled()     # eval without autograd: folded three-launch block
         params = (self.conv1.weight, self.bn1.weight, self.bn1.bias,
                   self.conv2.weight, self.bn2.weight, self.bn2.bias,
                   self.conv3.weight, self.bn3.weight, self.bn3.bias,

@@ -11,7 +11,7 @@ from ._lib import STRUCTS, call, call_struct, lib, make, ptr, stream_ptr
 CL3 = torch.channels_last_3d
 
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU, PRO_AFFINE_SWISH, PRO_AFFINE2 = 0, 1, 2, 3, 4
-EPI_NONE, EPI_RELU, EPI_DRELU, EPI_DSWISH, EPI_ADD_AUX, EPI_SIGMOID = 0, 1, 2, 3, 4, 5
+EPI_NONE, EPI_RELU, EPI_DRELU, EPI_DSWISH, EPI_ADD_AUX, EPI_SIGMOID, EPI_AFFINE, EPI_AFFINE_ADD_RELU = 0, 1, 2, 3, 4, 5, 6, 7
 STATS_NONE, STATS_SUM_SQ, STATS_SUM_AUX = 0, 1, 2
 
 
@@ -188,8 +188,16 @@ class BNCfg:
 
 
 def bn_finalize(stats, bn, B, C, rows, training, device):
-    """-> (tab_a, tab_b, mean, invstd); updates split_bn running statistics in training."""
+    """-> (tab_a, tab_b, mean, invstd); updates split_bn running statistics in training.
+    Eval-mode tables depend only on the running statistics and the affine parameters: they are cached on the module and
+    rebuilt when one of those tensors changes (autograd version counters; aggregate_stats() re-assigns bn.running_*)."""
     m = bn.m
+    if not training:
+        key = (B, str(device), m.bn.running_mean.data_ptr(), m.bn.running_var.data_ptr(), m.bn.running_mean._version,
+               m.bn.running_var._version, m.weight._version, m.bias._version, m.weight.data_ptr())
+        hit = getattr(m, "_cf_eval_tabs", None)
+        if hit is not None and hit[0] == key and not torch.cuda.is_current_stream_capturing():
+            return hit[1]
     splits = m.num_splits if training else 1
     tabs = torch.empty(2, B, C, device=device, dtype=torch.float32)
     ms = torch.empty(2, splits, C, device=device, dtype=torch.float32)
@@ -203,6 +211,8 @@ def bn_finalize(stats, bn, B, C, rows, training, device):
              momentum=float(m.split_bn.momentum if m.split_bn.momentum is not None else 0.1), eps=float(m.split_bn.eps),
              training=int(training))
     call_struct("cf_bn_finalize", a)
+    if not training:
+        m._cf_eval_tabs = (key, (tabs[0], tabs[1], ms[0], ms[1]))
     return tabs[0], tabs[1], ms[0], ms[1]
 
 
@@ -275,6 +285,8 @@ class BottleneckFn(torch.autograd.Function):
         tr = cfg.training
         has_se, has_ds = fw1 is not None, wd is not None
         Cmax = max(Ce, Co)
+        if not tr and getattr(cfg, "inference", False):
+            return BottleneckFn._inference(x, cfg, w1, w2, w3, fw1, fb1, fw2, fb2, wd, (B, Cin, Ce, Co, T, H, W, To, Ho, Wo, s, ts))
         need_stats = tr or has_se                      # eval: only the SE pool needs sum(y2)
         stats = _zeros64(cfg, 4, B, Cmax, 2, device=dev) if need_stats else None
         st = (lambda i, C: stats[i].view(-1)[: B * C * 2]) if need_stats else (lambda i, C: None)
@@ -328,6 +340,54 @@ class BottleneckFn(torch.autograd.Function):
         ctx.save_for_backward(x, y1, y2, y3, yd, out, w1, g1, w2, g2, w3, g3, fw1, fw2, wd, gd)
         ctx.param_shapes = [p for p in (w1, g1, b1, w2, g2, b2, w3, g3, b3, fw1, fb1, fw2, fb2, wd, gd, bd)]
         if pool is not None:
+            return out, pooled
+        return out
+
+    @staticmethod
+    def _inference(x, cfg, w1, w2, w3, fw1, fb1, fw2, fb2, wd, dims):
+        """Eval mode without autograd (validation, feature extraction): every BatchNorm is a constant affine map, so the
+        block is THREE conv launches -- conv1 | depthwise (bn1+ReLU prologue) | conv3 (bn2 [+SE] + Swish prologue, and bn3 +
+        shortcut + ReLU folded into its epilogue: x3d_fine.py:167-173) -- plus the SE gate and, in the first block of a stage,
+        the shortcut conv with its BatchNorm folded into ITS epilogue.  The training-mode sequence needs y3 and a separate
+        residual join because bn3's batch statistics only exist after conv3 has finished; here nothing is materialised
+        between conv3 and the block output, and nothing is saved."""
+        B, Cin, Ce, Co, T, H, W, To, Ho, Wo, s, ts = dims
+        dev = x.device
+        has_se, has_ds = fw1 is not None, wd is not None
+        Rin, Rout = T * H * W, To * Ho * Wo
+        g_in, g_out = geom(T, H, W), geom(To, Ho, Wo)
+        g_dw = geom(To, Ho, Wo, T, H, W, k=(3, 3, 3), s=(ts, s, s), p=(1, 1, 1))
+        y1 = new_act(B, Ce, T, H, W, dev)
+        pw_conv(x, w1, y1, B, Cin, Ce, g_in)
+        a1, bb1, _, _ = bn_finalize(None, cfg.bn1, B, Ce, Rin, False, dev)
+        y2 = new_act(B, Ce, To, Ho, Wo, dev)
+        stats = _zeros64(cfg, B, Ce, 2, device=dev) if has_se else None          # SE pooling: sum of the raw conv2 output
+        dw_call("cf_dw_conv_fwd", y1, w2, y2, B, Ce, g_dw, pro=PRO_AFFINE_RELU, pro_tabs=(a1, bb1, None), stats=stats,
+                stats_mode=STATS_SUM_SQ if has_se else STATS_NONE)
+        ga, gb, _, _ = bn_finalize(None, cfg.bn2, B, Ce, Rout, False, dev)
+        if has_se:
+            Wd = fw1.shape[0]
+            sv = torch.empty(4, B, Ce, device=dev, dtype=torch.float32)
+            hid = torch.empty(B, Wd, device=dev, dtype=torch.float32)
+            call_struct("cf_se_fwd", make("cf_se_args", stats=stats.view(-1), tab_a=ga, tab_b=gb, w1=fw1, b1=fb1, w2=fw2, b2=fb2,
+                                          pooled=sv[0], hidden=hid, gate=sv[1], out_a=sv[2], out_b=sv[3], B=B, C=Ce, Wd=Wd,
+                                          rows_per_sample=Rout))
+            ga, gb = sv[2], sv[3]
+        shortcut = x
+        if has_ds:
+            g_ds = geom(To, Ho, Wo, T, H, W, s=(ts, s, s), pos_stride=Cin, ch_stride=1, sample_stride=Rin * Cin)
+            ad, bbd, _, _ = bn_finalize(None, cfg.bnd, B, Co, Rout, False, dev)
+            shortcut = new_act(B, Co, To, Ho, Wo, dev)
+            pw_conv(x, wd, shortcut, B, Cin, Co, g_ds, gather_in=1, epi=EPI_AFFINE, epi_tabs=(ad, bbd))
+        a3, bb3, _, _ = bn_finalize(None, cfg.bn3, B, Co, Rout, False, dev)
+        out = new_act(B, Co, To, Ho, Wo, dev)
+        pw_conv(y2, w3, out, B, Ce, Co, g_out, pro=PRO_AFFINE_SWISH, pro_tabs=(ga, gb, None), epi=EPI_AFFINE_ADD_RELU, aux=shortcut,
+                epi_tabs=(a3, bb3))
+        pool = getattr(cfg, "pool", None)
+        if pool is not None:                                       # stage-final block of the global tower (x3d_fine.py:345-354)
+            pooled = new_act(B, Co, To, Ho // pool[0], Wo // pool[1], dev)
+            call_struct("cf_block_avgpool_fwd", make("cf_pool_args", x=out, y=pooled, tab_a=None, tab_b=None, B=B, C=Co, T=To, H=Ho,
+                                                     W=Wo, rh=pool[0], rw=pool[1]))
             return out, pooled
         return out
 

@@ -103,6 +103,8 @@ int cf_temporal_gather_bwd_coord(const float* gout, const float* x, const int32_
 #define CF_EPI_DSWISH 3        /* acc * swish'(ea*aux + eb)           */
 #define CF_EPI_ADD_AUX 4       /* acc + aux                           */
 #define CF_EPI_SIGMOID 5       /* sigmoid(acc + bias)                 */
+#define CF_EPI_AFFINE 6        /* ea*acc + eb        folded (eval) BatchNorm of a shortcut conv (x3d_fine.py:286-288)       */
+#define CF_EPI_AFFINE_ADD_RELU 7 /* relu(ea*acc + eb + aux)  folded bn3 + residual + ReLU in conv3's epilogue (:167-173, eval) */
 /* statistics accumulated (double atomics) into stats[b][n][0..1] */
 #define CF_STATS_NONE 0
 #define CF_STATS_SUM_SQ 1      /* sum y, sum y^2      (forward: BatchNorm + SE pooling) */
