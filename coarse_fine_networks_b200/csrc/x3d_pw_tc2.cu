@@ -180,7 +180,22 @@ extern "C" int cf_pw_tc_debug_read(long long* out16) {
 }
 
 // called by cf_pw_conv (x3d_pw.cu) for dense problems when the caller supplied a weight-pack workspace
-int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
+static int p2_run(const cf_pw_args* a, cudaStream_t stream, int* plan_nt);
+
+int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) { return p2_run(a, stream, nullptr); }
+
+// The channel tile the persistent kernel WOULD use for this call (its shared-memory plan may narrow the default tile):
+// what a persistent pack of the weights has to be made with; 0 when the call does not take the persistent kernel.
+extern "C" int cf_pw_plan_nt(const cf_pw_args* a) {
+    if (!a || !a->wpack) return 0;
+    int nt = 0;
+    const int rc = p2_run(a, nullptr, &nt);
+    return rc == CF_OK ? nt : 0;
+}
+
+// plan_nt != NULL: plan only (no launch, no packing), *plan_nt = the channel tile
+static int p2_run(const cf_pw_args* a, cudaStream_t stream, int* plan_nt) {
+    if (plan_nt) *plan_nt = 0;
     const int K = a->K, N = a->N;
     P2Params p;
     p2_tiling(K, N, p);
@@ -208,7 +223,7 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
     p.gH = a->g.H; p.gW = a->g.W; p.gHi = a->g.Hi; p.gWi = a->g.Wi; p.gst = a->g.st; p.gsh = a->g.sh; p.gsw = a->g.sw;
     p.g_sample_stride = a->g.sample_stride;
     if (av == 1 || ev == 1 || (a->accumulate && p.gmode != 2) || (a->stats_mode != CF_STATS_NONE && N > P2_RED_N))
-        return p.gmode ? -1 : cf_pw_conv_tc_v1(a, stream);      // (-1: the caller falls back to the CUDA-core gather kernel)
+        return (p.gmode || plan_nt) ? -1 : cf_pw_conv_tc_v1(a, stream);      // (-1: the caller falls back to the CUDA-core gather kernel)
 
     // ---- TMA-fed producers: dense rows (gathered rows keep the register-load producers), describable by a tensor map
     const bool x2 = a->pro_mode == CF_PRO_AFFINE2;
@@ -294,6 +309,10 @@ int cf_pw_conv_tc(const cf_pw_args* a, cudaStream_t stream) {
         }
     }
     CF_CHECK_ARG(planned, "K too large for the tensor-core path");
+    if (plan_nt) {
+        *plan_nt = p.NT;
+        return CF_OK;
+    }
     CF_CHECK_ARG(a->wpack_bytes >= (int64_t)((size_t)p.ntiles * p.nchunks * p.b_chunk_bytes), "weight-pack workspace too small");
     CF_CHECK_ARG(p.total_tiles < (1LL << 31), "too many tiles");
     p.acc_stride = (p.NTp + 31) / 32 * 32;

@@ -79,32 +79,41 @@ class PackCache:
         key = (w.data_ptr(), int(w_sn), int(w_sk), int(K), int(N))
         e = self.entries.get(key)
         if e is None:
-            e = dict(buf=torch.empty(nbytes // 4, device=w.device, dtype=torch.float32), nt=int(lib.cf_pw_pack_nt(K, N)), gver=-1,
-                     tver=-1, w=w)
+            e = dict(buf=torch.empty(nbytes // 4, device=w.device, dtype=torch.float32), nt=None, gver=-1, tver=-1, w=w)
             self.entries[key] = e
-        if e["gver"] == self.gver and e["tver"] == w._version:
+            self._items_n = -1
+        if e["nt"] and e["gver"] == self.gver and e["tver"] == w._version:
             return e["buf"], e["nt"]
         e["gver"], e["tver"], e["w"] = self.gver, w._version, w       # this call packs into the persistent buffer
         return e["buf"], 0
+
+    def set_plan(self, w, w_sn, w_sk, K, N, nt):
+        """The channel tile the first call of this (weight, layout) planned (cf_pw_plan_nt): what pack_many packs with."""
+        e = self.entries.get((w.data_ptr(), int(w_sn), int(w_sk), int(K), int(N)))
+        if e is not None and e["nt"] is None:
+            e["nt"] = int(nt)
+            self._items_n = -1
 
     def weights_changed(self):
         """Called by FlatTrainer after the SGD kernel: every registered weight changed; re-pack all known ones in one launch."""
         self.gver += 1
         if not self.entries:
             return
-        if self._items_n != len(self.entries):
-            import ctypes
+        live = [(k, e) for k, e in self.entries.items() if e["nt"]]      # (nt == 0: the call does not take the persistent kernel)
+        if not live:
+            return
+        if self._items_n != len(live):
             Item = STRUCTS["cf_pack_item"]
-            arr = (Item * len(self.entries))()
-            for i, ((p_, sn, sk, K, N), e) in enumerate(self.entries.items()):
+            arr = (Item * len(live))()
+            for i, ((p_, sn, sk, K, N), e) in enumerate(live):
                 arr[i].w, arr[i].pack, arr[i].w_sn, arr[i].w_sk = p_, e["buf"].data_ptr(), sn, sk
                 arr[i].K, arr[i].N, arr[i].nt, arr[i].pad = K, N, e["nt"], 0
             raw = bytes(arr)
             dev = next(iter(self.entries.values()))["buf"].device
             self._items = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
-            self._items_n = len(self.entries)
+            self._items_n = len(live)
         call("cf_pw_pack_many", ptr(self._items), self._items_n, stream_ptr())
-        for e in self.entries.values():
+        for _, e in live:
             e["gver"], e["tver"] = self.gver, e["w"]._version
 
 
@@ -114,7 +123,7 @@ PACKS = PackCache()
 def pw_conv(x, w, y, B, K, N, g, *, w_sn=None, w_sk=1, x2=None, bias=None, pro=PRO_NONE, pro_tabs=(None, None, None),
             epi=EPI_NONE, aux=None, epi_tabs=(None, None), stats=None, stats_mode=STATS_NONE, gather_in=0, scatter_out=0,
             accumulate=0, tc=None):
-    wpack, wbytes, wnt = None, 0, 0
+    wpack, wbytes, wnt, hit = None, 0, 0, None
     strided_1x1 = (g.kt * g.kh * g.kw == 1 and g.ch_stride == 1 and g.pt == 0 and g.ph == 0 and g.pw == 0)
     sn = K if w_sn is None else w_sn
     if (USE_TC if tc is None else tc) and ((not gather_in and not scatter_out) or strided_1x1):
@@ -128,6 +137,9 @@ def pw_conv(x, w, y, B, K, N, g, *, w_sn=None, w_sk=1, x2=None, bias=None, pro=P
              aux=aux, epi_a=epi_tabs[0], epi_b=epi_tabs[1], stats=stats, w_sn=sn, w_sk=w_sk,
              B=B, K=K, N=N, g=g, gather_in=gather_in, scatter_out=scatter_out, accumulate=accumulate, pro_mode=pro,
              epi_mode=epi, stats_mode=stats_mode, wpack=wpack, wpack_bytes=wbytes, wpack_nt=wnt)
+    if hit is not None and wnt == 0:
+        import ctypes
+        PACKS.set_plan(w, sn, w_sk, K, N, lib.cf_pw_plan_nt(ctypes.byref(a)))
     call_struct("cf_pw_conv", a)
     return y
 

@@ -176,7 +176,9 @@ typedef struct {
     int64_t w_sn, w_sk;
     int K, N, nt, pad;
 } cf_pack_item;
-int cf_pw_pack_nt(int K, int N);
+int cf_pw_pack_nt(int K, int N);                 /* the default channel tile for (K,N) */
+int cf_pw_plan_nt(const cf_pw_args* a);          /* the channel tile THIS call will use (its shared-memory plan may narrow the
+                                                  * default), 0 if it does not take the persistent tensor-core kernel */
 int cf_pw_pack_many(const cf_pack_item* items, int n, cudaStream_t stream);
 size_t cf_sizeof_pack_item(void);
 /* debug: per-role cycle counters of CTA 0 of the last tensor-core launch made with CFNET_PW_TC_TIMING=1 (24 values) */
