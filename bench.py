@@ -281,6 +281,7 @@ def build_models(which, device, seed=0):
                                            t_pool="grid", learnedMixing=True, isMixing=True)
         coarse.replace_logits(N_CLASSES)
         coarse.rw6.dropout.p = 0.0
+        coarse.fusion_streams = os.environ.get("CF_FUSION_STREAMS", "1") != "0"      # harness switch for same-box A/B runs
     mods = [m.to(device).train() for m in (fine, coarse) if m is not None]
     return fine, coarse, mods
 
@@ -335,6 +336,8 @@ class TrainWorkload:
         # train_fine.py:199 resamples with align_corners=True, train_coarse_fineFEAT.py:226 on the default grid
         loss, _ = self.train.charades_loss(logits, self.labels, self.lmask, align_corners=(self.which == "fine"))
         loss.backward()
+        from coarse_fine_networks_b200 import x3d_ops
+        x3d_ops.join_side_streams()              # forked fusion-block branches rejoin (required to end a graph capture)
         self.loss = loss.detach()
 
     def parity_check(self):

@@ -143,6 +143,9 @@ class FlatTrainer:
 
     def allreduce(self):
         """The one collective of the data-parallel step: sum of the flat gradient over all ranks."""
+        if self.flat_g.is_cuda:
+            from . import x3d_ops
+            x3d_ops.join_side_streams()         # weight-gradient kernels of forked branches write into flat_g untracked
         if self.world > 1:
             if self.comm is not None:
                 self.comm.allreduce(self.flat_g)

@@ -218,6 +218,37 @@ class ResNet(_FineResNet):
         self.fc2 = nn.Linear(2048, n_classes).to(dev)
         self.rw6 = RewightLayer(n_classes, n_classes, self.feat_depth['conv5'], height=7, pool=True).to(dev)
 
+    fusion_streams = True          # run the independent Rewight branches of the fusion block on side streams (CUDA only)
+
+    def _fork_branches(self, rws, feats, feat_masks, GX, flags, first=0):
+        """Start rw.forward_base(...) of independent Rewight layers.  Each branch is a chain of small kernels (k=1 Conv1d
+        GEMMs over a few thousand rows, the Tf-contraction): launch-latency-bound in sequence, so on CUDA each branch is
+        forked onto its own stream; autograd runs a branch's backward on the same stream.  -> handle for _join_branches."""
+        if not (self.fusion_streams and feats[0].is_cuda):
+            return [(None, rw.forward_base(f, feat_masks, GX, fl)) for rw, f, fl in zip(rws, feats, flags)]
+        main = torch.cuda.current_stream()
+        streams = X.side_streams(feats[0].device, first + len(rws))[first:]
+        pending = []
+        for rw, f, fl, s in zip(rws, feats, flags, streams):
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                pending.append((s, rw.forward_base(f, feat_masks, GX, fl)))
+        return pending
+
+    @staticmethod
+    def _join_branches(pending):
+        """Wait for forked branches on the current stream and hand their outputs over to it."""
+        outs = []
+        for s, o in pending:
+            if s is not None:
+                main = torch.cuda.current_stream()
+                main.wait_stream(s)
+                for t in o:
+                    if t is not None:
+                        t.record_stream(main)
+            outs.append(o)
+        return outs
+
     def _forward(self, inp):
         x, feat, feat_masks, i, meta = inp
         t_in = x.shape[2]
@@ -229,8 +260,11 @@ class ResNet(_FineResNet):
         keys = ('layer1', 'layer2', 'layer3', 'layer4')
         rws = (self.rw2, self.rw3, self.rw4, self.rw5)
         layers = (self.layer2, self.layer3, self.layer4, None)
+        # rw6 (the logits' scale / shift, :719-720) depends on the fine features and GX only: it starts here, on its own stream,
+        # and is joined at the head (extract_feat returns before the head and never needs it)
+        rw6_pending = None if self.extract_feat else self._fork_branches([self.rw6], [feat['conv5']], feat_masks, GX, [False], first=0)
         if self.isMixing:                                                      # :655-679
-            maps = [rw.forward_base(feat[k], feat_masks, GX, True) for rw, k in zip(rws, keys)]
+            maps = self._join_branches(self._fork_branches(rws, [feat[k] for k in keys], feat_masks, GX, [True] * 4, first=1))
             bias, scale = [m[0] for m in maps], [m[1] for m in maps]
             hb, wb = bias[0].shape[3], bias[0].shape[4]
             for j, layer in enumerate(layers):
@@ -251,7 +285,7 @@ class ResNet(_FineResNet):
         if self.extract_feat:
             return pooled
         logits = self._head(pooled)                                            # [B,n_cls,Tl]  :706-716
-        b6, s6 = self.rw6.forward_base(feat['conv5'], feat_masks, GX, False)   # :719-720
+        (b6, s6), = self._join_branches(rw6_pending)                           # :719-720 (started right after the Gaussian)
         lg = logits.unsqueeze(3).unsqueeze(4)
         x = FU.FilmFn.apply(lg, s6, b6).squeeze(4).squeeze(3)                  # :721
         x = GridUnpool([x, gx, True])                                          # :724

@@ -161,6 +161,30 @@ def dw_call(fn, x, w, y, B, C, g, *, x2=None, pro=PRO_NONE, pro_tabs=(None, None
     return y
 
 
+# Side streams for independent small-kernel chains (the five Rewight branches of the fusion block: a few thousand rows each,
+# launch-latency-bound one after the other, concurrent when forked).  Weight-gradient kernels write straight into the flat
+# gradient buffer, which autograd does not track: whoever consumes the gradients joins the side streams first
+# (train.FlatTrainer.allreduce does; bench.py joins before it ends a CUDA-graph capture).
+_SIDE = {}
+
+
+def side_streams(device, n):
+    key = str(device)
+    pool = _SIDE.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+def join_side_streams():
+    """Make the current stream wait for everything enqueued on the side streams so far."""
+    if not _SIDE:
+        return
+    cur = torch.cuda.current_stream()
+    for s in _SIDE.get(str(cur.device), []):
+        cur.wait_stream(s)
+
+
 class StatsArena:
     """One zero-filled fp64 buffer for all the BatchNorm statistics / backward sums of a forward pass: ONE memset per
     network pass instead of two per block (the fp64 atomics of the producer epilogues accumulate into slices of it).
