@@ -64,6 +64,32 @@ static inline int cf_cdiv(long long a, long long b) { return (int)((a + b - 1) /
 static inline long long cf_cdiv64(long long a, long long b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch.  Every kernel launched through cf_launch() starts with cf_pdl_enter(): it waits until the
+// grid before it in the stream has completed and its writes are visible (griddepcontrol.wait: a no-op without a programmatic
+// edge), then lets the grid AFTER it be scheduled (launch_dependents).  The next kernel's CTAs are therefore placed on the
+// SMs while this one drains and sit at their own wait, instead of being launched after the drain: the data dependence is the
+// stream's usual one (nothing of a kernel runs before its predecessor has finished), only the launch latency between the
+// ~1 200 dependent kernels of a step is taken off the critical path.  Stream capture records the edge as programmatic.
+__device__ __forceinline__ void cf_pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t cf_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cf_env("CFNET_PDL", 1) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float cf_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -36,6 +36,7 @@ template <int V> __device__ __forceinline__ VecF<V> ldtab(const float* p) {
 
 // ---------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(const cf_bn_args a) {
+    cf_pdl_enter();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.C) return;
     const int C = a.C, S = a.splits;
@@ -77,6 +78,7 @@ __global__ void bn_finalize_kernel(const cf_bn_args a) {
 }
 
 __global__ void bn_bwd_coeffs_kernel(const cf_bn_bwd_args a) {
+    cf_pdl_enter();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.C) return;
     const int C = a.C, S = a.splits;
@@ -117,6 +119,7 @@ __global__ void bn_bwd_coeffs_kernel(const cf_bn_bwd_args a) {
 // SE forward: one CTA per sample
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) se_fwd_kernel(const cf_se_args a) {
+    cf_pdl_enter();
     extern __shared__ float sm[];            // pooled[C] | hidden[Wd]
     const int b = blockIdx.x, tid = threadIdx.x, C = a.C, Wd = a.Wd;
     float* pooled = sm;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(256) se_fwd_kernel(const cf_se_args a) {
 }
 
 __global__ void __launch_bounds__(256) se_bwd_kernel(const cf_se_bwd_args a) {
+    cf_pdl_enter();
     extern __shared__ float sm[];            // dlogit[C] | dpre[Wd]
     const int b = blockIdx.x, tid = threadIdx.x, C = a.C, Wd = a.Wd;
     float* dlog = sm;
@@ -200,6 +204,7 @@ __global__ void __launch_bounds__(256) se_bwd_kernel(const cf_se_bwd_args a) {
 // ---------------------------------------------------------------------------------------
 template <int V>
 __global__ void __launch_bounds__(256) residual_fwd_kernel(const cf_residual_args a) {
+    cf_pdl_enter();
     const int b = blockIdx.y, C = a.C, CV = C / V;
     long long n = a.rows_per_sample * CV;
     long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -232,6 +237,7 @@ __global__ void __launch_bounds__(256) residual_fwd_kernel(const cf_residual_arg
 // the stage output instead of in a second full read of it
 template <int V>
 __global__ void __launch_bounds__(256) residual_pool_fwd_kernel(const cf_residual_args a) {
+    cf_pdl_enter();
     const int b = blockIdx.y, C = a.C, CV = C / V;
     const int Ho = a.H / a.rh, Wo = a.W / a.rw;
     long long n = (long long)a.T * Ho * Wo * CV;
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(256) residual_pool_fwd_kernel(const cf_residua
 // rows of one sample are split in chunks over grid.x; 256 threads = PY row lanes x CV channel vectors
 template <int V>
 __global__ void __launch_bounds__(256) residual_bwd_kernel(const cf_residual_bwd_args a, int chunk) {
+    cf_pdl_enter();
     extern __shared__ float sm[];            // [4][C]
     const int b = blockIdx.y, C = a.C, CV = C / V, tid = threadIdx.x;
     for (int i = tid; i < 4 * C; i += 256) sm[i] = 0.f;
@@ -343,6 +350,7 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const cf_residual_bwd
 // ---------------------------------------------------------------------------------------
 template <int V>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const cf_pool_args a) {
+    cf_pdl_enter();
     const int b = blockIdx.y, C = a.C, CV = C / V;
     const int Ho = a.H / a.rh, Wo = a.W / a.rw;
     long long n = (long long)a.T * Ho * Wo * CV;
@@ -374,6 +382,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const cf_pool_args a) 
 
 template <int V>
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const cf_pool_bwd_args a, int chunk) {
+    cf_pdl_enter();
     extern __shared__ float sm[];            // [2][C]
     const int b = blockIdx.y, C = a.C, CV = C / V, tid = threadIdx.x;
     const bool do_sums = a.sums != nullptr;
@@ -450,7 +459,7 @@ extern "C" int cf_bn_finalize(const cf_bn_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->gamma && a->beta && a->tab_a && a->tab_b && a->mean && a->invstd, "null pointer");
     CF_CHECK_ARG(a->B > 0 && a->C > 0 && a->splits > 0 && a->B % a->splits == 0, "bad shape (B % splits)");
     CF_CHECK_ARG(a->training ? (a->stats != nullptr) : (a->running_mean && a->running_var), "missing statistics");
-    bn_finalize_kernel<<<cf_cdiv(a->C, 128), 128, 0, stream>>>(*a);
+    cf_launch(bn_finalize_kernel, cf_cdiv(a->C, 128), 128, 0, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -459,7 +468,7 @@ extern "C" int cf_bn_finalize(const cf_bn_args* a, cudaStream_t stream) {
 extern "C" int cf_bn_bwd_coeffs(const cf_bn_bwd_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->sums && a->gamma && a->mean && a->invstd && a->tab_p && a->tab_q && a->tab_r, "null pointer");
     CF_CHECK_ARG(a->B > 0 && a->C > 0 && a->splits > 0 && a->B % a->splits == 0, "bad shape (B % splits)");
-    bn_bwd_coeffs_kernel<<<cf_cdiv(a->C, 128), 128, 0, stream>>>(*a);
+    cf_launch(bn_bwd_coeffs_kernel, cf_cdiv(a->C, 128), 128, 0, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -469,7 +478,7 @@ extern "C" int cf_se_fwd(const cf_se_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->stats && a->tab_a && a->tab_b && a->w1 && a->b1 && a->w2 && a->b2, "null pointer");
     CF_CHECK_ARG(a->pooled && a->hidden && a->gate && a->out_a && a->out_b, "null output");
     CF_CHECK_ARG(a->B > 0 && a->C > 0 && a->Wd > 0 && (size_t)(a->C + a->Wd) * 4 <= 48 * 1024, "bad shape");
-    se_fwd_kernel<<<a->B, 256, (size_t)(a->C + a->Wd) * 4, stream>>>(*a);
+    cf_launch(se_fwd_kernel, a->B, 256, (size_t)(a->C + a->Wd) * 4, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -479,7 +488,7 @@ extern "C" int cf_se_bwd(const cf_se_bwd_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->sums && a->stats_y && a->tab_a && a->tab_b && a->w1 && a->w2 && a->pooled && a->hidden && a->gate, "null pointer");
     CF_CHECK_ARG(a->dw1 && a->db1 && a->dw2 && a->db2 && a->cst, "null output");
     CF_CHECK_ARG(a->B > 0 && a->C > 0 && a->Wd > 0 && (size_t)(a->C + a->Wd) * 4 <= 48 * 1024, "bad shape");
-    se_bwd_kernel<<<a->B, 256, (size_t)(a->C + a->Wd) * 4, stream>>>(*a);
+    cf_launch(se_bwd_kernel, a->B, 256, (size_t)(a->C + a->Wd) * 4, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -496,18 +505,18 @@ extern "C" int cf_residual_fwd(const cf_residual_args* a, cudaStream_t stream) {
         if ((((uintptr_t)a->pooled) & 15) && v == 4) v = 2;
         long long np = (long long)a->T * (a->H / a->rh) * (a->W / a->rw) * (a->C / v);
         dim3 gp((unsigned)cf_cdiv64(np, 256), (unsigned)a->B);
-        if (v == 4) residual_pool_fwd_kernel<4><<<gp, 256, 0, stream>>>(*a);
-        else if (v == 2) residual_pool_fwd_kernel<2><<<gp, 256, 0, stream>>>(*a);
-        else residual_pool_fwd_kernel<1><<<gp, 256, 0, stream>>>(*a);
+        if (v == 4) cf_launch(residual_pool_fwd_kernel<4>, gp, 256, 0, stream, *a);
+        else if (v == 2) cf_launch(residual_pool_fwd_kernel<2>, gp, 256, 0, stream, *a);
+        else cf_launch(residual_pool_fwd_kernel<1>, gp, 256, 0, stream, *a);
         CF_COUNT_LAUNCH(1);
         CF_CHECK_LAUNCH();
         return CF_OK;
     }
     long long n = a->rows_per_sample * (a->C / v);
     dim3 grid((unsigned)cf_cdiv64(n, 256), (unsigned)a->B);
-    if (v == 4) residual_fwd_kernel<4><<<grid, 256, 0, stream>>>(*a);
-    else if (v == 2) residual_fwd_kernel<2><<<grid, 256, 0, stream>>>(*a);
-    else residual_fwd_kernel<1><<<grid, 256, 0, stream>>>(*a);
+    if (v == 4) cf_launch(residual_fwd_kernel<4>, grid, 256, 0, stream, *a);
+    else if (v == 2) cf_launch(residual_fwd_kernel<2>, grid, 256, 0, stream, *a);
+    else cf_launch(residual_fwd_kernel<1>, grid, 256, 0, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -526,9 +535,9 @@ extern "C" int cf_residual_bwd(const cf_residual_bwd_args* a, cudaStream_t strea
     int chunk = chunk_for(a->rows_per_sample, a->B, 256 / (a->C / v > 256 ? 256 : a->C / v));
     dim3 grid((unsigned)cf_cdiv64(a->rows_per_sample, chunk), (unsigned)a->B);
     size_t smem = (size_t)4 * a->C * 4;
-    if (v == 4) residual_bwd_kernel<4><<<grid, 256, smem, stream>>>(*a, chunk);
-    else if (v == 2) residual_bwd_kernel<2><<<grid, 256, smem, stream>>>(*a, chunk);
-    else residual_bwd_kernel<1><<<grid, 256, smem, stream>>>(*a, chunk);
+    if (v == 4) cf_launch(residual_bwd_kernel<4>, grid, 256, smem, stream, *a, chunk);
+    else if (v == 2) cf_launch(residual_bwd_kernel<2>, grid, 256, smem, stream, *a, chunk);
+    else cf_launch(residual_bwd_kernel<1>, grid, 256, smem, stream, *a, chunk);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -541,9 +550,9 @@ extern "C" int cf_block_avgpool_fwd(const cf_pool_args* a, cudaStream_t stream) 
     int v = vec_for(a->C, a->x, a->y, nullptr, nullptr);
     long long n = (long long)a->T * (a->H / a->rh) * (a->W / a->rw) * (a->C / v);
     dim3 grid((unsigned)cf_cdiv64(n, 256), (unsigned)a->B);
-    if (v == 4) avgpool_fwd_kernel<4><<<grid, 256, 0, stream>>>(*a);
-    else if (v == 2) avgpool_fwd_kernel<2><<<grid, 256, 0, stream>>>(*a);
-    else avgpool_fwd_kernel<1><<<grid, 256, 0, stream>>>(*a);
+    if (v == 4) cf_launch(avgpool_fwd_kernel<4>, grid, 256, 0, stream, *a);
+    else if (v == 2) cf_launch(avgpool_fwd_kernel<2>, grid, 256, 0, stream, *a);
+    else cf_launch(avgpool_fwd_kernel<1>, grid, 256, 0, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -559,22 +568,23 @@ extern "C" int cf_block_avgpool_bwd(const cf_pool_bwd_args* a, cudaStream_t stre
     int chunk = chunk_for(R, a->B, 256 / (a->C / v > 256 ? 256 : a->C / v));
     dim3 grid((unsigned)cf_cdiv64(R, chunk), (unsigned)a->B);
     size_t smem = (size_t)2 * a->C * 4;
-    if (v == 4) avgpool_bwd_kernel<4><<<grid, 256, smem, stream>>>(*a, chunk);
-    else if (v == 2) avgpool_bwd_kernel<2><<<grid, 256, smem, stream>>>(*a, chunk);
-    else avgpool_bwd_kernel<1><<<grid, 256, smem, stream>>>(*a, chunk);
+    if (v == 4) cf_launch(avgpool_bwd_kernel<4>, grid, 256, smem, stream, *a, chunk);
+    else if (v == 2) cf_launch(avgpool_bwd_kernel<2>, grid, 256, smem, stream, *a, chunk);
+    else cf_launch(avgpool_bwd_kernel<1>, grid, 256, smem, stream, *a, chunk);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
 }
 
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ out, long long n) {
+    cf_pdl_enter();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = y[i] > 0.f ? dy[i] : 0.f;
 }
 
 extern "C" int cf_relu_bwd(const float* dy, const float* y, float* out, int64_t n, cudaStream_t stream) {
     CF_CHECK_ARG(dy && y && out && n > 0, "bad argument");
-    relu_bwd_kernel<<<(unsigned)cf_cdiv64(n, 256), 256, 0, stream>>>(dy, y, out, n);
+    cf_launch(relu_bwd_kernel, (unsigned)cf_cdiv64(n, 256), 256, 0, stream, dy, y, out, n);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -586,6 +596,7 @@ extern "C" int cf_relu_bwd(const float* dy, const float* y, float* out, int64_t 
 template <int V>
 __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                             double* __restrict__ stats, int C, long long rows, int chunk) {
+    cf_pdl_enter();
     extern __shared__ float sm[];            // [2][C]
     const int b = blockIdx.y, CV = C / V, tid = threadIdx.x;
     for (int i = tid; i < 2 * C; i += 256) sm[i] = 0.f;
@@ -617,6 +628,7 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
 }
 
 __global__ void __launch_bounds__(256) affine_apply_kernel(const cf_affine_args a) {
+    cf_pdl_enter();
     const int b = blockIdx.y, C = a.C;
     long long n = a.rows_per_sample * C;
     long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -638,10 +650,12 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(const cf_affine_args 
 }
 
 __global__ void swish_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+    cf_pdl_enter();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { float v = x[i]; out[i] = v * cf_sigmoid(v); }
 }
 __global__ void swish_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
+    cf_pdl_enter();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { float v = x[i], s = cf_sigmoid(v); dx[i] = dy[i] * (s * (1.f + v * (1.f - s))); }
 }
@@ -653,9 +667,9 @@ extern "C" int cf_channel_stats(const float* x, const float* y, double* stats, i
     int chunk = chunk_for(rows, B, 256 / ((C / v) > 256 ? 256 : (C / v)));
     dim3 grid((unsigned)cf_cdiv64(rows, chunk), (unsigned)B);
     size_t smem = (size_t)2 * C * 4;
-    if (v == 4) channel_stats_kernel<4><<<grid, 256, smem, stream>>>(x, y, stats, C, rows, chunk);
-    else if (v == 2) channel_stats_kernel<2><<<grid, 256, smem, stream>>>(x, y, stats, C, rows, chunk);
-    else channel_stats_kernel<1><<<grid, 256, smem, stream>>>(x, y, stats, C, rows, chunk);
+    if (v == 4) cf_launch(channel_stats_kernel<4>, grid, 256, smem, stream, x, y, stats, C, rows, chunk);
+    else if (v == 2) cf_launch(channel_stats_kernel<2>, grid, 256, smem, stream, x, y, stats, C, rows, chunk);
+    else cf_launch(channel_stats_kernel<1>, grid, 256, smem, stream, x, y, stats, C, rows, chunk);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -665,7 +679,7 @@ extern "C" int cf_affine_apply(const cf_affine_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->x && a->out && a->tab_a && a->B > 0 && a->B <= 65535 && a->C > 0 && a->rows_per_sample > 0, "bad argument");
     CF_CHECK_ARG(a->mode != CF_PRO_AFFINE2 || a->x2, "AFFINE2 needs x2");
     dim3 grid((unsigned)cf_cdiv64(a->rows_per_sample * a->C, 256), (unsigned)a->B);
-    affine_apply_kernel<<<grid, 256, 0, stream>>>(*a);
+    cf_launch(affine_apply_kernel, grid, 256, 0, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -673,7 +687,7 @@ extern "C" int cf_affine_apply(const cf_affine_args* a, cudaStream_t stream) {
 
 extern "C" int cf_swish_fwd(const float* x, float* out, int64_t n, cudaStream_t stream) {
     CF_CHECK_ARG(x && out && n > 0, "bad argument");
-    swish_fwd_kernel<<<(unsigned)cf_cdiv64(n, 256), 256, 0, stream>>>(x, out, n);
+    cf_launch(swish_fwd_kernel, (unsigned)cf_cdiv64(n, 256), 256, 0, stream, x, out, n);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -681,7 +695,7 @@ extern "C" int cf_swish_fwd(const float* x, float* out, int64_t n, cudaStream_t 
 
 extern "C" int cf_swish_bwd(const float* x, const float* dy, float* dx, int64_t n, cudaStream_t stream) {
     CF_CHECK_ARG(x && dy && dx && n > 0, "bad argument");
-    swish_bwd_kernel<<<(unsigned)cf_cdiv64(n, 256), 256, 0, stream>>>(x, dy, dx, n);
+    cf_launch(swish_bwd_kernel, (unsigned)cf_cdiv64(n, 256), 256, 0, stream, x, dy, dx, n);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

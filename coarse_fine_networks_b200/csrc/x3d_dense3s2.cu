@@ -32,6 +32,7 @@ struct DgArgs {
 
 template <int C>
 __global__ void __launch_bounds__(DG_THREADS) dense3_s2_dgrad_kernel(const DgArgs a) {
+    cf_pdl_enter();
     constexpr int C4 = C / 4;
     __shared__ __align__(16) float w_s[8][C][C];          // [tap slot][co][ci]
     __shared__ float tab[3][C];
@@ -152,7 +153,7 @@ int cf_dense_s2_dgrad_try(const cf_pw_args* a, cudaStream_t stream) {
     d.dz = a->x; d.y = a->x2; d.w = a->w; d.P = a->pro_a; d.Q = a->pro_b; d.R = a->pro_c; d.dx = a->y;
     d.To = g.T; d.Ho = g.H; d.Wo = g.W; d.Ti = g.Ti; d.Hi = g.Hi; d.Wi = g.Wi;
     d.sample_stride = g.sample_stride; d.affine2 = a->pro_mode == CF_PRO_AFFINE2;
-    dense3_s2_dgrad_kernel<24><<<(unsigned)ctas, DG_THREADS, 0, stream>>>(d);
+    cf_launch(dense3_s2_dgrad_kernel<24>, (unsigned)ctas, DG_THREADS, 0, stream, d);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -185,6 +186,7 @@ struct FwArgs {
 
 template <int C>
 __global__ void __launch_bounds__(FW_THREADS) dense3_s2_fwd_kernel(const FwArgs a) {
+    cf_pdl_enter();
     constexpr int C4 = C / 4;
     extern __shared__ __align__(16) float fw_smem[];
     float* w_s = fw_smem;                                 // [27][FW_TAPSTRIDE]: [tap][ci][co]
@@ -317,7 +319,7 @@ int cf_dense_s2_fwd_try(const cf_pw_args* a, cudaStream_t stream) {
         if (e != cudaSuccess) { cf_set_error("cf_dense_s2_fwd: smem opt-in failed: %s", cudaGetErrorString(e)); return CF_ERR_CUDA; }
         attr_done.mark();
     }
-    dense3_s2_fwd_kernel<24><<<(unsigned)(tiles * a->B), FW_THREADS, smem, stream>>>(f);
+    cf_launch(dense3_s2_fwd_kernel<24>, (unsigned)(tiles * a->B), FW_THREADS, smem, stream, f);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -353,6 +355,7 @@ struct Wg3Args {
 
 template <int C>
 __global__ void __launch_bounds__(WG3_THREADS, 2) dense3_s2_wgrad_kernel(const Wg3Args a) {
+    cf_pdl_enter();
     constexpr int C4 = C / 4;                                 // 6
     extern __shared__ __align__(16) float wg_smem[];
     float* dzs = wg_smem;                                     // [WG3_ROWS][C]
@@ -490,7 +493,7 @@ int cf_dense_s2_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     }
     long long ctas = cps * a->B;
     if (ctas > 148 * 2) ctas = 148 * 2;
-    dense3_s2_wgrad_kernel<24><<<(unsigned)ctas, WG3_THREADS, smem, stream>>>(w);
+    cf_launch(dense3_s2_wgrad_kernel<24>, (unsigned)ctas, WG3_THREADS, smem, stream, w);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

@@ -51,6 +51,7 @@ __device__ __forceinline__ float dw_pro(int mode, float x, float x2, float a, fl
 // ---------------------------------------------------------------------------------------
 template <int V, int KW, int SW, int TW>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const cf_dw_args a) {
+    cf_pdl_enter();
     extern __shared__ __align__(16) float sm[];
     const cf_geom& g = a.g;
     const int C = a.C, taps = g.kt * g.kh * KW;
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const cf_dw_args a) {
 // ---------------------------------------------------------------------------------------
 template <int V>
 __global__ void __launch_bounds__(256) dw_dgrad_kernel(const cf_dw_args a) {
+    cf_pdl_enter();
     extern __shared__ __align__(16) float sm[];
     const cf_geom& g = a.g;
     const int C = a.C, taps = g.kt * g.kh * g.kw;
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(256) dw_dgrad_kernel(const cf_dw_args a) {
 // ---------------------------------------------------------------------------------------
 template <int V, int TAPS>
 __global__ void __launch_bounds__(256) dw_wgrad_kernel(const cf_dw_args a, int chunk) {
+    cf_pdl_enter();
     extern __shared__ __align__(16) float sm[];     // [TAPS][C]
     const cf_geom& g = a.g;
     const int C = a.C;
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const cf_dw_args a, int c
 // data gradient: dx[ti,hi,wi] = sum_taps pro(d[t,h,w]) * w[tap], t = ti+1-dt, h = (hi+1-dh)/ST, w = (wi+1-dw)/ST
 template <int V, int ST>
 __global__ void __launch_bounds__(256) dw_dgrad3_kernel(const cf_dw_args a) {
+    cf_pdl_enter();
     extern __shared__ __align__(16) float sm[];
     const cf_geom& g = a.g;
     const int C = a.C;
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(256) dw_dgrad3_kernel(const cf_dw_args a) {
 // TWG = 2 neighbouring output positions along W so the 3 input rows are loaded once for both
 template <int V, int ST>
 __global__ void __launch_bounds__(256) dw_wgrad3_kernel(const cf_dw_args a, int chunk) {
+    cf_pdl_enter();
     extern __shared__ __align__(16) float sm[];     // [27][C]
     const cf_geom& g = a.g;
     const int C = a.C;
@@ -587,7 +592,7 @@ static int launch_dw_fwd(const cf_dw_args* a, cudaStream_t stream) {
     do {                                                                                \
         static CfOncePerDevice done;                                                       \
         if (done.need()) { set_smem(dw_fwd_kernel<V, KW_, SW_, TW>); done.mark(); }           \
-        dw_fwd_kernel<V, KW_, SW_, TW><<<grid, 256, smem, stream>>>(*a);                \
+        cf_launch(dw_fwd_kernel<V, KW_, SW_, TW>, grid, 256, smem, stream, *a);                \
     } while (0)
     if (g.kw == 3 && g.sw == 1) CF_DW_LAUNCH(3, 1);
     else if (g.kw == 3 && g.sw == 2) CF_DW_LAUNCH(3, 2);
@@ -608,7 +613,7 @@ static int launch_dw_dgrad(const cf_dw_args* a, cudaStream_t stream) {
     dim3 grid((unsigned)cf_cdiv64(ntask, 256), (unsigned)a->B);
     static CfOncePerDevice done;
     if (done.need()) { set_smem(dw_dgrad_kernel<V>); done.mark(); }
-    dw_dgrad_kernel<V><<<grid, 256, smem, stream>>>(*a);
+    cf_launch(dw_dgrad_kernel<V>, grid, 256, smem, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -626,7 +631,7 @@ static int launch_dw_wgrad(const cf_dw_args* a, cudaStream_t stream) {
     dim3 grid((unsigned)cf_cdiv64(R, chunk), (unsigned)a->B);
     static CfOncePerDevice done;
     if (done.need()) { set_smem(dw_wgrad_kernel<V, TAPS>); done.mark(); }
-    dw_wgrad_kernel<V, TAPS><<<grid, 256, smem, stream>>>(*a, (int)chunk);
+    cf_launch(dw_wgrad_kernel<V, TAPS>, grid, 256, smem, stream, *a, (int)chunk);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -645,7 +650,7 @@ static int launch_dw_dgrad3(const cf_dw_args* a, cudaStream_t stream) {
     dim3 grid((unsigned)cf_cdiv64(ntask, 256), (unsigned)a->B);
     static CfOncePerDevice done;
     if (done.need()) { set_smem(dw_dgrad3_kernel<V, ST>); done.mark(); }
-    dw_dgrad3_kernel<V, ST><<<grid, 256, smem, stream>>>(*a);
+    cf_launch(dw_dgrad3_kernel<V, ST>, grid, 256, smem, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -663,7 +668,7 @@ static int launch_dw_wgrad3(const cf_dw_args* a, cudaStream_t stream) {
     dim3 grid((unsigned)cf_cdiv64(NG, chunk), (unsigned)a->B);
     static CfOncePerDevice done;
     if (done.need()) { set_smem(dw_wgrad3_kernel<V, ST>); done.mark(); }
-    dw_wgrad3_kernel<V, ST><<<grid, 256, smem, stream>>>(*a, (int)chunk);
+    cf_launch(dw_wgrad3_kernel<V, ST>, grid, 256, smem, stream, *a, (int)chunk);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

@@ -50,6 +50,7 @@ __device__ __forceinline__ void d3_cp_async_wait_all() {
 // MODE: D3_FWD / D3_DGRAD / D3_WGRAD;  NPW: patches along W (tile width 7 * NPW)
 template <int MODE, int NPW>
 __global__ void __launch_bounds__(D3_LANES * 4 * NPW) dw3_kernel(const cf_dw_args a, const D3Params p) {
+    cf_pdl_enter();
     constexpr int TW = D3_PW * NPW, HW = TW + 2;
     constexpr int NPATCH = 4 * NPW, NT = D3_LANES * NPATCH;
     constexpr int NPOS = D3_HH * HW;                               // haloed positions per plane
@@ -403,7 +404,7 @@ static int d3_launch(const cf_dw_args* a, const D3Params& p, cudaStream_t stream
         done.mark();
     }
     dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
-    dw3_kernel<MODE, NPW><<<grid, D3_LANES * 4 * NPW, smem, stream>>>(*a, p);
+    cf_launch(dw3_kernel<MODE, NPW>, grid, D3_LANES * 4 * NPW, smem, stream, *a, p);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

@@ -39,6 +39,7 @@ __device__ __forceinline__ void s2_cp_async_wait_all() {
 
 template <int MODE, int NPW>
 __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_kernel(const cf_dw_args a, const S2Params p) {
+    cf_pdl_enter();
     constexpr int OTW = S2_PW * NPW, IW = 2 * OTW + 1;
     constexpr int NPATCH = S2_OTH * NPW, NT = S2_LANES * NPATCH;
     constexpr int NPOS = S2_IH * IW;
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_kernel(const cf
 // The weights move to shared memory (their registers hold the accumulators).
 template <int NPW, bool FUSED>
 __global__ void __launch_bounds__(S2_LANES * S2_OTH * NPW) dw3s2_dgrad_kernel(const cf_dw_args a, const S2Params p) {
+    cf_pdl_enter();
     constexpr int OTW = S2_PW * NPW, RW = OTW + 1, RH = S2_OTH + 1;
     constexpr int NPATCH = S2_OTH * NPW, NT = S2_LANES * NPATCH;
     constexpr int NPOS = RH * RW;
@@ -560,7 +562,7 @@ static int s2_launch_dgrad(const cf_dw_args* a, const S2Params& p, cudaStream_t 
         done.mark();
     }
     dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
-    dw3s2_dgrad_kernel<NPW, FUSED><<<grid, S2_LANES * S2_OTH * NPW, smem, stream>>>(*a, p);
+    cf_launch(dw3s2_dgrad_kernel<NPW, FUSED>, grid, S2_LANES * S2_OTH * NPW, smem, stream, *a, p);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -579,7 +581,7 @@ static int s2_launch(const cf_dw_args* a, const S2Params& p, cudaStream_t stream
         done.mark();
     }
     dim3 grid((unsigned)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta));
-    dw3s2_kernel<MODE, NPW><<<grid, S2_LANES * S2_OTH * NPW, smem, stream>>>(*a, p);
+    cf_launch(dw3s2_kernel<MODE, NPW>, grid, S2_LANES * S2_OTH * NPW, smem, stream, *a, p);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

@@ -31,6 +31,7 @@ __device__ __forceinline__ float4 t5_fma(float4 a, float4 b, float4 c) {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) dwt5_kernel(const cf_dw_args a, const T5Params p) {
+    cf_pdl_enter();
     __shared__ float red[20 * 256];
     const int tid = threadIdx.x;
     const long long e = (long long)blockIdx.x * 256 + tid;
@@ -190,10 +191,10 @@ int cf_dwt5_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     p.ntseg = (g.T + tseg - 1) / tseg;
     if (blocks > 2147483647LL || p.ntseg > 65535 || a->B > 65535) return -1;
     dim3 grid((unsigned)blocks, (unsigned)p.ntseg, (unsigned)a->B);
-    if (mode == T5_FWD) dwt5_kernel<T5_FWD><<<grid, 256, 0, stream>>>(*a, p);
-    else if (mode == T5_DGRAD) dwt5_kernel<T5_DGRAD><<<grid, 256, 0, stream>>>(*a, p);
-    else if (mode == T5_FUSED) dwt5_kernel<T5_FUSED><<<grid, 256, 0, stream>>>(*a, p);
-    else dwt5_kernel<T5_WGRAD><<<grid, 256, 0, stream>>>(*a, p);
+    if (mode == T5_FWD) cf_launch(dwt5_kernel<T5_FWD>, grid, 256, 0, stream, *a, p);
+    else if (mode == T5_DGRAD) cf_launch(dwt5_kernel<T5_DGRAD>, grid, 256, 0, stream, *a, p);
+    else if (mode == T5_FUSED) cf_launch(dwt5_kernel<T5_FUSED>, grid, 256, 0, stream, *a, p);
+    else cf_launch(dwt5_kernel<T5_WGRAD>, grid, 256, 0, stream, *a, p);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

@@ -56,6 +56,7 @@ __device__ __forceinline__ long long gathered_off(const cf_geom& g, unsigned pos
 
 template <int BN_, bool GATHER>
 __global__ void __launch_bounds__(256) pw_conv_kernel(const cf_pw_args a, int tiles_per_sample, int R) {
+    cf_pdl_enter();
     constexpr int TN = BN_ / 16;
     constexpr int LDB = BN_ + 4;
     extern __shared__ __align__(16) float smem[];
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(256) pw_conv_kernel(const cf_pw_args a, int ti
 
 template <bool GATHER>
 __global__ void __launch_bounds__(256) pw_wgrad_kernel(const cf_pw_wgrad_args a, int splits, int rows_per_split, int R) {
+    cf_pdl_enter();
     __shared__ __align__(16) float Ds[WG_BM * WG_LD];
     __shared__ __align__(16) float Xs[WG_BM * WG_LD];
     const int tid = threadIdx.x;
@@ -362,7 +364,7 @@ static int launch_pw(const cf_pw_args* a, int R, cudaStream_t stream) {
     }
     if (smem > 100 * 1024) { cf_set_error("cf_pw_conv: K too large for the table cache"); return CF_ERR_ARG; }
     dim3 grid((unsigned)(tps * a->B), (unsigned)cf_cdiv(a->N, BN_));
-    pw_conv_kernel<BN_, GATHER><<<grid, 256, smem, stream>>>(*a, tps, R);
+    cf_launch(pw_conv_kernel<BN_, GATHER>, grid, 256, smem, stream, *a, tps, R);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -411,6 +413,7 @@ extern "C" int cf_pw_conv(const cf_pw_args* a, cudaStream_t stream) {
 // on the tensor-core kernel.  CTA = 32 columns x a chunk of rows, 8 row lanes, 128-byte row segments per warp.
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ dbias, long long rows,
                                                         int N, int chunk) {
+    cf_pdl_enter();
     __shared__ float part[8][33];
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + lx;
@@ -461,7 +464,7 @@ extern "C" int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream) {
                 int chunk = (int)cf_cdiv64(rows, want < 1 ? 1 : want);
                 chunk = chunk < 256 ? 256 : ((chunk + 31) / 32) * 32;
                 dim3 grid((unsigned)ct, (unsigned)cf_cdiv64(rows, chunk));
-                bias_grad_kernel<<<grid, 256, 0, stream>>>(a->dy, a->dbias, rows, a->N, chunk);
+                cf_launch(bias_grad_kernel, grid, 256, 0, stream, a->dy, a->dbias, rows, a->N, chunk);
                 CF_COUNT_LAUNCH(1);
                 CF_CHECK_LAUNCH();
                 return CF_OK;
@@ -483,8 +486,8 @@ extern "C" int cf_pw_wgrad(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     splits = cf_cdiv(R, rps);
     CF_CHECK_ARG((long long)a->B * splits <= 65535, "grid.z overflow");
     dim3 grid((unsigned)nt, (unsigned)kt, (unsigned)(a->B * splits));
-    if (a->gather_in) pw_wgrad_kernel<true><<<grid, 256, 0, stream>>>(*a, splits, rps, R);
-    else pw_wgrad_kernel<false><<<grid, 256, 0, stream>>>(*a, splits, rps, R);
+    if (a->gather_in) cf_launch(pw_wgrad_kernel<true>, grid, 256, 0, stream, *a, splits, rps, R);
+    else cf_launch(pw_wgrad_kernel<false>, grid, 256, 0, stream, *a, splits, rps, R);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;

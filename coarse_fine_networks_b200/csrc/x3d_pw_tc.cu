@@ -51,6 +51,7 @@ __device__ __forceinline__ float tc_pro(int mode, float x, float x2, float a, fl
 // ---------------------------------------------------------------------------------------
 __global__ void pw_tc_pack_kernel(const float* __restrict__ w, long long w_sn, long long w_sk, float* __restrict__ pack, int K,
                                   int N, int NT, int NTp, int ntiles, int nchunks) {
+    cf_pdl_enter();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)ntiles * nchunks * NTp * 8;
     if (i >= total) return;
@@ -124,6 +125,7 @@ template <int AV, int EV>
 __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const cf_pw_args a, const float* __restrict__ pack, int R,
                                                            int tiles_per_sample, int NT, int NTp, int nchunks,
                                                            uint32_t tmem_cols) {
+    cf_pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_b[2];
     __shared__ __align__(8) uint64_t mma_done[2];
@@ -350,7 +352,7 @@ static size_t tc_v1_ws_bytes(int K, int N) {
 void cf_pw_tc_pack_launch(const float* w, long long w_sn, long long w_sk, float* pack, int K, int N, int NT, int NTp, int ntiles,
                           int nchunks, cudaStream_t stream) {
     long long total = (long long)ntiles * nchunks * NTp * 8;
-    pw_tc_pack_kernel<<<(unsigned)cf_cdiv64(total, 256), 256, 0, stream>>>(w, w_sn, w_sk, pack, K, N, NT, NTp, ntiles, nchunks);
+    cf_launch(pw_tc_pack_kernel, (unsigned)cf_cdiv64(total, 256), 256, 0, stream, w, w_sn, w_sk, pack, K, N, NT, NTp, ntiles, nchunks);
 }
 
 static size_t tc_smem_bytes(const TcTiling& t, int K) {
@@ -368,7 +370,7 @@ static int launch_tc(const cf_pw_args* a, const TcTiling& t, int R, uint32_t tme
     }
     int tps = cf_cdiv(R, TC_BM);
     dim3 grid((unsigned)(tps * a->B), (unsigned)t.ntiles);
-    pw_tc_kernel<AV, EV><<<grid, TC_THREADS, smem, stream>>>(*a, a->wpack, R, tps, t.NT, t.NTp, t.nchunks, tmem_cols);
+    cf_launch(pw_tc_kernel<AV, EV>, grid, TC_THREADS, smem, stream, *a, a->wpack, R, tps, t.NT, t.NTp, t.nchunks, tmem_cols);
     return CF_OK;
 }
 
@@ -384,7 +386,7 @@ int cf_pw_conv_tc_v1(const cf_pw_args* a, cudaStream_t stream) {
     CF_CHECK_ARG((long long)cf_cdiv(R, TC_BM) * a->B < (1LL << 31), "too many row tiles");
     {
         long long total = (long long)t.ntiles * t.nchunks * t.NTp * 8;
-        pw_tc_pack_kernel<<<(unsigned)cf_cdiv64(total, 256), 256, 0, stream>>>(a->w, a->w_sn, a->w_sk, a->wpack, K, N, t.NT, t.NTp,
+        cf_launch(pw_tc_pack_kernel, (unsigned)cf_cdiv64(total, 256), 256, 0, stream, a->w, a->w_sn, a->w_sk, a->wpack, K, N, t.NT, t.NTp,
                                                                             t.ntiles, t.nchunks);
     }
     uint32_t tmem_cols = 32;

@@ -138,6 +138,7 @@ extern "C" int cf_pw_pack_nt(int K, int N) {
 extern "C" size_t cf_sizeof_pack_item(void) { return sizeof(cf_pack_item); }
 
 __global__ void __launch_bounds__(256) pw_pack_many_kernel(const cf_pack_item* __restrict__ items) {
+    cf_pdl_enter();
     const cf_pack_item it = items[blockIdx.x];
     const int NT = it.nt, NTp = (NT + 15) / 16 * 16;
     const int ntiles = (it.N + NT - 1) / NT, nchunks = (it.K + TC_KC - 1) / TC_KC;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) pw_pack_many_kernel(const cf_pack_item* _
 
 extern "C" int cf_pw_pack_many(const cf_pack_item* items, int n, cudaStream_t stream) {
     CF_CHECK_ARG(items && n > 0 && n <= 65535, "bad argument");
-    pw_pack_many_kernel<<<dim3((unsigned)n, 8), 256, 0, stream>>>(items);
+    cf_launch(pw_pack_many_kernel, dim3((unsigned)n, 8), 256, 0, stream, items);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -334,7 +335,7 @@ static int p2_run(const cf_pw_args* a, cudaStream_t stream, int* plan_nt) {
     p.dbg_1x = cf_env("CFNET_PW_TC_1X", 0);
     p.g_j = (int)(grid % p.ntiles);
     p.g_rt = (int)(grid / p.ntiles);
-    p2w8::pw_tc2_kernel<<<(unsigned)grid, (8 + 4 + 8) * 32, smem, stream>>>(*a, a->wpack, p, av, ev, tmx, tmx2);
+    cf_launch(p2w8::pw_tc2_kernel, (unsigned)grid, (8 + 4 + 8) * 32, smem, stream, *a, a->wpack, p, av, ev, tmx, tmx2);
     CF_COUNT_LAUNCH(prepacked ? 1 : 2);
     CF_CHECK_LAUNCH();
     return CF_OK;

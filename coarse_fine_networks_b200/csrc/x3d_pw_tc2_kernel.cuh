@@ -690,6 +690,7 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
 __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const cf_pw_args a, const float* __restrict__ pack, const P2Params p,
                                                                int av, int ev, const __grid_constant__ CUtensorMap tmx,
                                                                const __grid_constant__ CUtensorMap tmx2) {
+    cf_pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full[P2_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty[P2_MAX_STAGES];

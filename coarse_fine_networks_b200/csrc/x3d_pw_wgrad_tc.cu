@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const cf_pw_
                                                                     const __grid_constant__ CUtensorMap tm_dy,
                                                                     const __grid_constant__ CUtensorMap tm_dy2,
                                                                     const __grid_constant__ CUtensorMap tm_x) {
+    cf_pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full[WG_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty[WG_MAX_STAGES];
@@ -686,7 +687,7 @@ int cf_pw_wgrad_tc(const cf_pw_wgrad_args* a, cudaStream_t stream) {
             e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<DYM_, XM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX); \
             if (e == cudaSuccess) attr_done.mark();                                                                                     \
         }                                                                                                                     \
-        if (e == cudaSuccess) pw_wgrad_tc_kernel<DYM_, XM_><<<grid, WG_THREADS, smem, stream>>>(*a, p, tm_dy, tm_dy2, tm_x);                     \
+        if (e == cudaSuccess) cf_launch(pw_wgrad_tc_kernel<DYM_, XM_>, grid, WG_THREADS, smem, stream, *a, p, tm_dy, tm_dy2, tm_x);                     \
     } while (0)
 #define WG_LAUNCH_X(DYM_)                                                              \
     switch (a->x_mode) {                                                               \

@@ -28,6 +28,7 @@ struct StemParams {
 
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
                                                        const StemParams p) {
+    cf_pdl_enter();
     __shared__ __align__(16) float ws[ST_K * ST_CO];             // [k][n]
     for (int i = threadIdx.x; i < ST_K * ST_CO; i += 256) {
         const int k = i / ST_CO, n = i - k * ST_CO;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
                                                          const StemParams p, long long total_tiles, int tiles_per_sample) {
+    cf_pdl_enter();
     __shared__ __align__(16) float dys[ST_TILE * ST_CO];          // [pos][24]
     __shared__ __align__(16) float xgs[ST_TILE * ST_KP];          // [pos][28] (tap 27 = 0)
     __shared__ float red[6 * ST_CO * ST_KP];
@@ -178,7 +180,7 @@ int cf_stem_fwd_try(const cf_pw_args* a, cudaStream_t stream) {
     StemParams p = stem_params(a->B, a->g);
     if (a->B > 65535) return -1;
     dim3 grid((unsigned)cf_cdiv64(p.R, 256), (unsigned)a->B);
-    stem_fwd_kernel<<<grid, 256, 0, stream>>>(a->x, a->w, a->y, p);
+    cf_launch(stem_fwd_kernel, grid, 256, 0, stream, a->x, a->w, a->y, p);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
@@ -196,7 +198,7 @@ int cf_stem_wgrad_try(const cf_pw_wgrad_args* a, cudaStream_t stream) {
     if (nsm <= 0) nsm = 148;
     long long grid = (long long)nsm * 4;
     if (grid > total) grid = total;
-    stem_wgrad_kernel<<<(unsigned)grid, 256, 0, stream>>>(a->dy, a->x, a->dw, p, total, tps);
+    cf_launch(stem_wgrad_kernel, (unsigned)grid, 256, 0, stream, a->dy, a->x, a->dw, p, total, tps);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
     return CF_OK;
