@@ -282,6 +282,8 @@ def build_models(which, device, seed=0):
         coarse.replace_logits(N_CLASSES)
         coarse.rw6.dropout.p = 0.0
         coarse.fusion_streams = os.environ.get("CF_FUSION_STREAMS", "1") != "0"      # harness switch for same-box A/B runs
+    from coarse_fine_networks_b200 import x3d_ops
+    x3d_ops.WGRAD_STREAM = os.environ.get("CF_WGRAD_STREAM", "1") != "0"              # harness switch for same-box A/B runs
     mods = [m.to(device).train() for m in (fine, coarse) if m is not None]
     return fine, coarse, mods
 

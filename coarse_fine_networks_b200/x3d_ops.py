@@ -185,6 +185,36 @@ def join_side_streams():
         cur.wait_stream(s)
 
 
+WGRAD_STREAM = True            # pointwise weight-gradient kernels of a Bottleneck on a side stream (joined before the block returns)
+
+
+class _WgradStream:
+    """`with _WgradStream(dev) as ws: ws.run(fn)`: fn's kernels go to a dedicated side stream that first waits for the work
+    enqueued on the current stream so far; __exit__ joins.  Everything the side kernels read is kept alive by the caller's
+    locals until the join, so no allocator bookkeeping (record_stream) is needed."""
+
+    def __init__(self, device, enabled):
+        self.on = bool(enabled) and torch.device(device).type == "cuda"
+        if self.on:
+            self.main = torch.cuda.current_stream()
+            self.side = side_streams(device, 6)[5]
+
+    def __enter__(self):
+        return self
+
+    def run(self, fn):
+        if not self.on:
+            return fn()
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            return fn()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.main.wait_stream(self.side)
+        return False
+
+
 class StatsArena:
     """One zero-filled fp64 buffer for all the BatchNorm statistics / backward sums of a forward pass: ONE memset per
     network pass instead of two per block (the fp64 atomics of the producer epilogues accumulate into slices of it).
@@ -454,39 +484,42 @@ class BottleneckFn(torch.autograd.Function):
         residual_bwd(dout, out, y3, dz3, sm(0, Co), B, Co, Rout, res=yd, sums_res=sm(3, Co) if has_ds else None, dpool=dpooled,
                      pool_geom=ctx.pool_geom if dpooled is not None else (0, 0, 0, 0, 0))
         P3, Q3, R3 = bn_bwd_coeffs(sm(0, Co), g3, m3, i3, dg3, db3, B, Co, Rout, tr)
-        # conv3
-        pw_wgrad(dz3, y2, dw3, B, Ce, Co, g_out, dy2=y3, dy_mode=PRO_AFFINE2, dy_tabs=(P3, Q3, R3), x_mode=PRO_AFFINE_SWISH,
-                 x_tabs=(ga, gb))
-        dU = torch.empty_like(y2)
-        pw_conv(dz3, w3, dU, B, Co, Ce, g_out, w_sn=1, w_sk=Ce, x2=y3, pro=PRO_AFFINE2, pro_tabs=(P3, Q3, R3), epi=EPI_DSWISH,
-                aux=y2, epi_tabs=(ga, gb), stats=sm(1, Ce), stats_mode=STATS_SUM_AUX)
-        gate = cst = None
-        if has_se:
-            pooled, hid, gate = ctx.se_saved
-            cst = torch.empty(B, Ce, device=dev, dtype=torch.float32)
-            a = make("cf_se_bwd_args", sums=sm(1, Ce), stats_y=stats2, tab_a=a2, tab_b=bb2, w1=fw1, w2=fw2, pooled=pooled,
-                     hidden=hid, gate=gate, dw1=dfw1, db1=dfb1, dw2=dfw2, db2=dfb2, cst=cst, B=B, C=Ce, Wd=fw1.shape[0],
-                     rows_per_sample=Rout)
-            call_struct("cf_se_bwd", a)
-        P2, Q2, R2 = bn_bwd_coeffs(sm(1, Ce), g2, m2, i2, dg2, db2, B, Ce, Rout, tr, gate=gate, cst=cst)
-        # conv2 (depthwise): data gradient and weight gradient from one call (one pass over dU, y2, y1 for the stride-1 convs)
-        dz1 = torch.empty_like(y1)
-        dw_call("cf_dw_conv_dgrad", dU, w2, dz1, B, Ce, g_dw, x2=y2, pro=PRO_AFFINE2, pro_tabs=(P2, Q2, R2), aux=y1,
-                epi=EPI_DRELU, epi_tabs=(a1, bb1), stats=sm(2, Ce), stats_mode=STATS_SUM_AUX, dw_out=dw2)
-        P1, Q1, R1 = bn_bwd_coeffs(sm(2, Ce), g1, m1, i1, dg1, db1, B, Ce, Rin, tr)
-        # conv1
-        pw_wgrad(dz1, x, dw1, B, Cin, Ce, g_in, dy2=y1, dy_mode=PRO_AFFINE2, dy_tabs=(P1, Q1, R1))
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            pw_conv(dz1, w1, dx, B, Ce, Cin, g_in, w_sn=1, w_sk=Cin, x2=y1, pro=PRO_AFFINE2, pro_tabs=(P1, Q1, R1),
-                    epi=EPI_NONE if has_ds else EPI_ADD_AUX, aux=None if has_ds else dz3)
-        if has_ds:
-            Pd, Qd, Rd = bn_bwd_coeffs(sm(3, Co), gd, md, idd, dgd, dbd, B, Co, Rout, tr)
-            pw_wgrad(dz3, x, dwd, B, Cin, Co, g_ds, dy2=yd, dy_mode=PRO_AFFINE2, dy_tabs=(Pd, Qd, Rd), gather_in=1)
-            if dx is not None:
-                pw_conv(dz3, wd, dx, B, Co, Cin, g_ds, w_sn=1, w_sk=Cin, x2=yd, pro=PRO_AFFINE2, pro_tabs=(Pd, Qd, Rd),
-                        scatter_out=1, accumulate=1)
+        # The weight gradients of the three pointwise convs are leaves of the step (nothing reads them before the optimizer):
+        # they run on a side stream next to the data-gradient chain and are joined before this block's backward returns.
+        with _WgradStream(dev, WGRAD_STREAM) as ws:
+            # conv3
+            ws.run(lambda: pw_wgrad(dz3, y2, dw3, B, Ce, Co, g_out, dy2=y3, dy_mode=PRO_AFFINE2, dy_tabs=(P3, Q3, R3),
+                                    x_mode=PRO_AFFINE_SWISH, x_tabs=(ga, gb)))
+            dU = torch.empty_like(y2)
+            pw_conv(dz3, w3, dU, B, Co, Ce, g_out, w_sn=1, w_sk=Ce, x2=y3, pro=PRO_AFFINE2, pro_tabs=(P3, Q3, R3), epi=EPI_DSWISH,
+                    aux=y2, epi_tabs=(ga, gb), stats=sm(1, Ce), stats_mode=STATS_SUM_AUX)
+            gate = cst = None
+            if has_se:
+                pooled, hid, gate = ctx.se_saved
+                cst = torch.empty(B, Ce, device=dev, dtype=torch.float32)
+                a = make("cf_se_bwd_args", sums=sm(1, Ce), stats_y=stats2, tab_a=a2, tab_b=bb2, w1=fw1, w2=fw2, pooled=pooled,
+                         hidden=hid, gate=gate, dw1=dfw1, db1=dfb1, dw2=dfw2, db2=dfb2, cst=cst, B=B, C=Ce, Wd=fw1.shape[0],
+                         rows_per_sample=Rout)
+                call_struct("cf_se_bwd", a)
+            P2, Q2, R2 = bn_bwd_coeffs(sm(1, Ce), g2, m2, i2, dg2, db2, B, Ce, Rout, tr, gate=gate, cst=cst)
+            # conv2 (depthwise): data gradient and weight gradient from one call (one pass over dU, y2, y1 for the stride-1 convs)
+            dz1 = torch.empty_like(y1)
+            dw_call("cf_dw_conv_dgrad", dU, w2, dz1, B, Ce, g_dw, x2=y2, pro=PRO_AFFINE2, pro_tabs=(P2, Q2, R2), aux=y1,
+                    epi=EPI_DRELU, epi_tabs=(a1, bb1), stats=sm(2, Ce), stats_mode=STATS_SUM_AUX, dw_out=dw2)
+            P1, Q1, R1 = bn_bwd_coeffs(sm(2, Ce), g1, m1, i1, dg1, db1, B, Ce, Rin, tr)
+            # conv1
+            ws.run(lambda: pw_wgrad(dz1, x, dw1, B, Cin, Ce, g_in, dy2=y1, dy_mode=PRO_AFFINE2, dy_tabs=(P1, Q1, R1)))
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                pw_conv(dz1, w1, dx, B, Ce, Cin, g_in, w_sn=1, w_sk=Cin, x2=y1, pro=PRO_AFFINE2, pro_tabs=(P1, Q1, R1),
+                        epi=EPI_NONE if has_ds else EPI_ADD_AUX, aux=None if has_ds else dz3)
+            if has_ds:
+                Pd, Qd, Rd = bn_bwd_coeffs(sm(3, Co), gd, md, idd, dgd, dbd, B, Co, Rout, tr)
+                ws.run(lambda: pw_wgrad(dz3, x, dwd, B, Cin, Co, g_ds, dy2=yd, dy_mode=PRO_AFFINE2, dy_tabs=(Pd, Qd, Rd), gather_in=1))
+                if dx is not None:
+                    pw_conv(dz3, wd, dx, B, Co, Cin, g_ds, w_sn=1, w_sk=Cin, x2=yd, pro=PRO_AFFINE2, pro_tabs=(Pd, Qd, Rd),
+                            scatter_out=1, accumulate=1)
         return (dx, None, *rets)
 
 
