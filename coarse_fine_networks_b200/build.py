@@ -47,7 +47,7 @@ def _compile(src, verbose, obj_dir=OBJ_DIR, extra=()):
     return obj, True
 
 
-VARIANTS = {"cvt": ("-DCFNET_AB", "-DCFNET_TF32_CVT")}       # named experiment builds: libcfnet_b200_<name>.so
+VARIANTS = {"cvt": ("-DCFNET_AB", "-DCFNET_TF32_CVT"), "pdlwait": ("-DCFNET_AB", "-DCFNET_PDL_NOTRIGGER")}       # named experiment builds: libcfnet_b200_<name>.so
 
 
 def build(force=False, verbose=False, ab=False, variant=None):

@@ -66,13 +66,17 @@ static inline long long cf_cdiv64(long long a, long long b) { return (a + b - 1)
 #ifdef __CUDACC__
 // Programmatic dependent launch.  Every kernel launched through cf_launch() starts with cf_pdl_enter(): it waits until the
 // grid before it in the stream has completed and its writes are visible (griddepcontrol.wait: a no-op without a programmatic
-// edge), then lets the grid AFTER it be scheduled (launch_dependents).  The next kernel's CTAs are therefore placed on the
-// SMs while this one drains and sit at their own wait, instead of being launched after the drain: the data dependence is the
-// stream's usual one (nothing of a kernel runs before its predecessor has finished), only the launch latency between the
-// ~1 200 dependent kernels of a step is taken off the critical path.  Stream capture records the edge as programmatic.
-__device__ __forceinline__ void cf_pdl_enter() {
+// edge), so the data dependence is the stream's usual one; the launch itself travels the programmatic edge (recorded as such
+// by stream capture), which is cheaper than a full dependency between the ~1 200 kernels of a step.  The one-wave table kernels
+// (BatchNorm tables, SE) additionally let the grid AFTER them be scheduled while they run (cf_pdl_enter_early): its CTAs are
+// resident and parked at their own wait when the tables are ready.  Doing the same in the large kernels LOST 3.6 ms per step
+// (profiles/r02_ab_same_box.md section 14), so they do not trigger early.
+__device__ __forceinline__ void cf_pdl_enter() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void cf_pdl_enter_early() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifndef CFNET_PDL_NOTRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 
 template <typename... KArgs, typename... Args>

@@ -36,7 +36,7 @@ template <int V> __device__ __forceinline__ VecF<V> ldtab(const float* p) {
 
 // ---------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(const cf_bn_args a) {
-    cf_pdl_enter();
+    cf_pdl_enter_early();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.C) return;
     const int C = a.C, S = a.splits;
@@ -78,7 +78,7 @@ __global__ void bn_finalize_kernel(const cf_bn_args a) {
 }
 
 __global__ void bn_bwd_coeffs_kernel(const cf_bn_bwd_args a) {
-    cf_pdl_enter();
+    cf_pdl_enter_early();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.C) return;
     const int C = a.C, S = a.splits;
@@ -119,7 +119,7 @@ __global__ void bn_bwd_coeffs_kernel(const cf_bn_bwd_args a) {
 // SE forward: one CTA per sample
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) se_fwd_kernel(const cf_se_args a) {
-    cf_pdl_enter();
+    cf_pdl_enter_early();
     extern __shared__ float sm[];            // pooled[C] | hidden[Wd]
     const int b = blockIdx.x, tid = threadIdx.x, C = a.C, Wd = a.Wd;
     float* pooled = sm;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) se_fwd_kernel(const cf_se_args a) {
 }
 
 __global__ void __launch_bounds__(256) se_bwd_kernel(const cf_se_bwd_args a) {
-    cf_pdl_enter();
+    cf_pdl_enter_early();
     extern __shared__ float sm[];            // dlogit[C] | dpre[Wd]
     const int b = blockIdx.x, tid = threadIdx.x, C = a.C, Wd = a.Wd;
     float* dlog = sm;

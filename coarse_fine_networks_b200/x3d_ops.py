@@ -185,7 +185,9 @@ def join_side_streams():
         cur.wait_stream(s)
 
 
-WGRAD_STREAM = True            # pointwise weight-gradient kernels of a Bottleneck on a side stream (joined before the block returns)
+WGRAD_STREAM_ROWS = 1 << 16    # Bottlenecks with at most this many output rows per launch (B*T*H*W) run their pointwise weight
+                               # gradients on a side stream, joined before the block's backward returns; 0 = never.  Larger
+                               # layers fill the GPU with either chain and only time-slice (profiles/r02_ab_same_box.md)
 
 
 class _WgradStream:
@@ -486,7 +488,7 @@ class BottleneckFn(torch.autograd.Function):
         P3, Q3, R3 = bn_bwd_coeffs(sm(0, Co), g3, m3, i3, dg3, db3, B, Co, Rout, tr)
         # The weight gradients of the three pointwise convs are leaves of the step (nothing reads them before the optimizer):
         # they run on a side stream next to the data-gradient chain and are joined before this block's backward returns.
-        with _WgradStream(dev, WGRAD_STREAM) as ws:
+        with _WgradStream(dev, B * Rout <= WGRAD_STREAM_ROWS) as ws:
             # conv3
             ws.run(lambda: pw_wgrad(dz3, y2, dw3, B, Ce, Co, g_out, dy2=y3, dy_mode=PRO_AFFINE2, dy_tabs=(P3, Q3, R3),
                                     x_mode=PRO_AFFINE_SWISH, x_tabs=(ga, gb)))
