@@ -283,8 +283,6 @@ def build_models(which, device, seed=0):
         coarse.rw6.dropout.p = 0.0
         coarse.fusion_streams = os.environ.get("CF_FUSION_STREAMS", "1") != "0"      # harness switch for same-box A/B runs
     from coarse_fine_networks_b200 import x3d_ops
-    from coarse_fine_networks_b200 import train as _train
-    _train.OVERLAP_COARSE_FRONT = os.environ.get("CF_OVERLAP_FRONT", "1") != "0"
     x3d_ops.WGRAD_STREAM_ROWS = int(os.environ.get("CF_WGRAD_STREAM_ROWS", x3d_ops.WGRAD_STREAM_ROWS))   # harness switch for same-box A/B runs
     mods = [m.to(device).train() for m in (fine, coarse) if m is not None]
     return fine, coarse, mods

@@ -247,9 +247,6 @@ def lr_warmup(init_lr, cur_steps, warmup_steps, trainer):
         trainer.fusion_lr = lr_scale * init_lr
 
 
-OVERLAP_COARSE_FRONT = True    # coarse stem + layer1 on a side stream next to the fine stream (CUDA only)
-
-
 def coarse_fine_forward(fine_net, coarse_net, x_fine, start, n_coarse, feat_masks, detach_fine=False, meta=None):
     """Joint two-stream forward.  The fine stream (global_tower=True) runs over the whole clip
     x_fine [B,3,Tf,H,W]; the coarse stream sees the window x_fine[:, :, start:start+n_coarse] and the
@@ -258,28 +255,13 @@ def coarse_fine_forward(fine_net, coarse_net, x_fine, start, n_coarse, feat_mask
     n_coarse, Tf, 1] as in charades_coarse_fineFEAT.py:199-200.  detach_fine=True reproduces the
     reference's training semantics (no gradient into the fine stream)."""
     B, _, Tf = x_fine.shape[:3]
-    x_coarse = x_fine[:, :, start:start + n_coarse]
-    # The coarse stream's stem + layer1 (a quarter of the fine stream's frames at the same resolution) depend on the clip only:
-    # they are enqueued on a side stream BEFORE the fine stream, so they fill the SMs the fine stream's 14x14 / 7x7 stages leave
-    # idle; autograd replays their backward on the same stream, next to the fine stream's backward.
-    front = side = None
-    if OVERLAP_COARSE_FRONT and x_fine.is_cuda and hasattr(coarse_net, "forward_front"):
-        from . import x3d_ops
-        main = torch.cuda.current_stream()
-        side = x3d_ops.side_streams(x_fine.device, 7)[6]
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            front = coarse_net.forward_front(x_coarse)
     feat, _ = fine_net([x_fine, None])
     if detach_fine:
         feat = {k: v.detach() for k, v in feat.items()}
     if meta is None:                     # pass a prebuilt device tensor when capturing the step in a CUDA graph
         meta = torch.tensor([[float(start), float(n_coarse), float(Tf), 1.0]], device=x_fine.device).repeat(B, 1)
-    if front is None:
-        return coarse_net([x_coarse, feat, feat_masks, 0, meta])
-    main.wait_stream(side)
-    front.record_stream(main)
-    return coarse_net([x_coarse, feat, feat_masks, 0, meta], front=front)
+    x_coarse = x_fine[:, :, start:start + n_coarse]
+    return coarse_net([x_coarse, feat, feat_masks, 0, meta])
 
 
 # ----------------------------------------------------------------------------------------

@@ -249,39 +249,12 @@ class ResNet(_FineResNet):
             outs.append(o)
         return outs
 
-    def forward_front(self, x):
-        """Stem + layer1 (:633-638): the part of the coarse stream that does not see the fine features.  A caller that owns both
-        streams (train.coarse_fine_forward) runs it on a side stream next to the fine stream and hands the result to
-        forward(inp, front=...)."""
-        B = x.shape[0]
-        blocks = list(self.layer1)
-        n = 2 * B * 2 * self.conv1_s.weight.shape[0]
-        for blk in blocks:
-            n += 2 * 4 * B * max(blk.conv1.weight.shape[0], blk.conv3.weight.shape[0]) * 2
-        arena = X.StatsArena(n, x.device)
-        for blk in blocks:
-            blk._arena = arena
-        self._arena = arena
-        try:
-            return self.layer1(self._stem(x))
-        finally:
-            for blk in blocks:
-                blk._arena = None
-            self._arena = None
-
-    def forward(self, inp, front=None):
-        self._open_arena(inp[0].shape[0], inp[0].device)
-        try:
-            return self._forward(inp, front)
-        finally:
-            self._close_arena()
-
-    def _forward(self, inp, front=None):
+    def _forward(self, inp):
         x, feat, feat_masks, i, meta = inp
         t_in = x.shape[2]
         if self.t_pool != 'grid':
             raise NotImplementedError("only t_pool='grid' (the configuration of train_coarse_fineFEAT.py:107-109) is built")
-        x = front if front is not None else self.layer1(self._stem(x))        # :633-638
+        x = self.layer1(self._stem(x))                                         # :633-638
         x, gx = self.pool_1(x)                                                 # :646-649
         GX = self.gauss([meta, feat_masks, gx, t_in])                          # :650
         keys = ('layer1', 'layer2', 'layer3', 'layer4')

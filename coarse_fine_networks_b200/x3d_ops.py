@@ -177,11 +177,18 @@ def side_streams(device, n):
 
 
 def join_side_streams():
-    """Make the current stream wait for everything enqueued on the side streams so far."""
+    """Make the current stream wait for everything enqueued on the side streams so far.  Inside a CUDA-graph capture only the
+    side streams that were forked into the capture are waited for (waiting for a stream outside the capture would invalidate
+    it; such a stream holds no work of the captured step)."""
     if not _SIDE:
         return
     cur = torch.cuda.current_stream()
+    capturing = torch.cuda.is_current_stream_capturing()
     for s in _SIDE.get(str(cur.device), []):
+        if capturing:
+            with torch.cuda.stream(s):
+                if not torch.cuda.is_current_stream_capturing():
+                    continue
         cur.wait_stream(s)
 
 

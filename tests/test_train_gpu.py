@@ -186,6 +186,42 @@ def test_joint_two_stream_step_and_cuda_graph(pk):
     assert cos >= 0.99, cos
 
 
+def test_fine_stream_alone_in_a_cuda_graph_with_idle_side_streams(pk):
+    """The fine stream alone forks only the weight-gradient side stream; the other side streams of the pool (the fusion
+    block's) hold no work of the step and must not be pulled into the capture by join_side_streams()."""
+    from coarse_fine_networks_b200 import x3d_ops as X
+    X.side_streams(torch.device("cuda", torch.cuda.current_device()), 6)        # the full pool exists, as after a joint step
+    fine = pk.F.generate_model("S", n_classes=9, task="loc", base_bn_splits=1, dropout=0.0)
+    fine.load_state_dict(synth_state_dict(fine.state_dict(), 21))
+    fine = fine.cuda().train()
+    x = synth_tensor((2, 3, 4, 64, 64), seed=7).cuda()
+    labels = (synth_tensor((2, 9, 16), seed=8) > 1.2).float().cuda()
+    lmask = torch.ones(2, 16).cuda()
+    tr = pk.T.FlatTrainer([fine], lr=0.01)
+
+    def step():
+        loss, _ = pk.T.charades_loss(fine([x, None]), labels, lmask)
+        loss.backward()
+        X.join_side_streams()
+        return loss
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            loss_eager = step().item()
+            tr.zero_grad()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        gl = step()
+    tr.zero_grad()
+    g.replay()
+    torch.cuda.synchronize()
+    assert abs(gl.item() - loss_eager) <= 1e-4 * abs(loss_eager) + 1e-6
+    assert float(tr.flat_g.abs().max()) > 0
+
+
 def test_detached_fine_features_reference_semantics(pk):
     fine, coarse = _joint(pk)
     B, Tf, T = 1, 16, 8
