@@ -620,7 +620,11 @@ int cf_dw3s2_try(int mode, const cf_dw_args* a, cudaStream_t stream) {
     if (spc < 4) spc = 4;
     p.steps_per_cta = (int)spc;
     if (mode == 1) return npw == 1 ? s2_launch_dgrad<1, false>(a, p, stream) : s2_launch_dgrad<2, false>(a, p, stream);
+#ifdef CFNET_AB      // the one-pass stride-2 backward lost its same-box A/B (profiles/r02_ab_same_box.md section 5): experiment build only
     if (mode == 3) return npw == 1 ? s2_launch_dgrad<1, true>(a, p, stream) : s2_launch_dgrad<2, true>(a, p, stream);
+#else
+    if (mode == 3) return -1;
+#endif
     if (npw == 1) return mode == S2_FWD ? s2_launch<S2_FWD, 1>(a, p, stream) : s2_launch<S2_WGRAD, 1>(a, p, stream);
     return mode == S2_FWD ? s2_launch<S2_FWD, 2>(a, p, stream) : s2_launch<S2_WGRAD, 2>(a, p, stream);
 }
