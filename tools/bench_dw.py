@@ -71,6 +71,9 @@ for name, C, T, H, W, s in CASES:
          4 * (2 * n_out + 2 * n_in)),
         ("wgrad", lambda: X.dw_call("cf_dw_conv_wgrad", dU, w, dw, B, C, g, x2=y2, pro=X.PRO_AFFINE2, pro_tabs=tuple(tabs[:3]), aux=y1,
                                     epi_tabs=(tabs[3], tabs[4])), 4 * (2 * n_out + n_in)),
+        ("fused", lambda: X.dw_call("cf_dw_conv_dgrad", dU, w, dz1, B, C, g, x2=y2, pro=X.PRO_AFFINE2, pro_tabs=tuple(tabs[:3]), aux=y1,
+                                    epi=X.EPI_DRELU, epi_tabs=(tabs[3], tabs[4]), stats=stats, stats_mode=X.STATS_SUM_AUX, dw_out=dw),
+         4 * (2 * n_out + 2 * n_in)),
     ]
     for kind, fn, byt in runs:
         ms = timeit(fn)
