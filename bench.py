@@ -464,13 +464,14 @@ class TrainWorkload:
         rows = B * T * H * W
         alg = rows * (K + N) * 4
         ach = alg / (ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from `ncu --set full` (profiles/r01_full_pw_tc2.md:
-        # 309.5 + 637.5 MB for 3 211 264 rows of the same 24 -> 54 problem = 294.9 B per row against 312 algorithmic:
-        # no re-reads; the difference is output still in L2 when the kernel ends), scaled to this launch's rows
-        traffic = 294.9 * rows
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from `ncu --set full` (profiles/r02_full_pw_tc.md, the
+        # TMA-fed kernel of this round: 308.7 + 634.5 MB for 3 211 264 rows of the same 24 -> 54 problem = 293.7 B per row
+        # against 312 algorithmic: no re-reads; the difference is output still in L2 when the kernel ends; round 1 measured
+        # 294.9), scaled to this launch's rows
+        traffic = 293.7 * rows
         roof = {"bound": "hbm", "kernel": "pw_tc2_kernel (tcgen05 3xTF32, TMA-fed producers; layer1.0.conv1 24->54 @112x112, all B*Tf frames, BN-stat epilogue)",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
-                "traffic_basis": "ncu --set full, r01_full_pw_tc2.md, per-row figure x rows of this launch",
+                "traffic_basis": "ncu --set full, profiles/r02_full_pw_tc.md, per-row figure x rows of this launch",
                 "peak_basis": peaks["basis"], "algorithmic_bytes": alg, "kernel_ms": ms}
         # the same kernel FAMILY on the other layer-1 launch shapes of the step (56x56, all B*Tf frames), time-weighted: the
         # best launch above is the friendliest one (no prologue, no aux); these carry the BatchNorm / Swish / BN-backward work
