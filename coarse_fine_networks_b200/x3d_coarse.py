@@ -15,6 +15,7 @@ What differs from the reference on purpose (same results):
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import fusion_ops as FU
 from . import gridpool_ops as G
@@ -46,8 +47,15 @@ class RewightLayer(nn.Module):
         """x [B,C,Tf,h,w] -> (bias, scale) at the base resolution: [B,ch,Tl,h,w] ([B,ch,Tl,1,1] if pool)."""
         x = X.cl(x)
         B, C, Tf, h, w = x.shape
-        if mask.shape[1] != Tf:
-            raise NotImplementedError("mask / feature length mismatch (x3d_coarse.py:205-207) is not built")
+        if mask.shape[1] != Tf:                                            # :205-207 (two tiny resamplings, as the reference)
+            mask = F.adaptive_max_pool1d(mask.unsqueeze(1), Tf).squeeze(1)
+            GX = F.adaptive_avg_pool2d(GX.unsqueeze(1), (Tf, None)).squeeze(1)
+        if GX.shape[0] != B:                                               # multi-crop testing (:209-211): crops share the features
+            n = GX.shape[0] // B
+            x = X.cl(x.repeat_interleave(n, dim=0))
+            mask = mask.repeat_interleave(n, dim=0)
+            B = GX.shape[0]
+        mask, GX = mask.contiguous(), GX.contiguous()
         Tl = GX.shape[2]
         P = h * w
         rows = FU.rows_of(x)                                               # [B, Tf*P, C]
@@ -73,8 +81,6 @@ class RewightLayer(nn.Module):
 
     def forward(self, inp):
         x, lx, mask, gx, i, GX, isMixing = inp
-        if x.shape[0] != lx.shape[0]:
-            raise NotImplementedError("multi-crop testing (x3d_coarse.py:209-211) is not built")
         x1, x2 = self.forward_base(x, mask, GX, isMixing)
         if not self.pool and x.shape[3] != self.height:
             x1 = FU.NearestUpFn.apply(x1, self.height, self.height)
@@ -91,11 +97,17 @@ class Gaussian(nn.Module):
 
     def forward(self, inp):
         meta, mask, gx, tx = inp
-        if tx is None:
-            raise NotImplementedError("Gaussian without a Grid Pool CDF (t_pool != 'grid') is not built")
-        if gx.shape[0] != meta.shape[0]:
-            raise NotImplementedError("multi-crop testing (x3d_coarse.py:264-266) is not built")
-        return FU.GaussianFn.apply(gx, meta[:, 0].float(), mask, float(tx), float(self.ratio))
+        b, b2 = meta.shape[0], gx.shape[0]
+        st = meta[:, 0].float()
+        if tx is None:                                       # :272-274: no Grid Pool, the coarse steps are a uniform grid 0..Tl-1
+            gx = torch.arange(gx.shape[2], device=gx.device, dtype=torch.float32).repeat(b2, 1)
+            tx = 1.0
+        if b2 != b:                                          # multi-crop testing (:264-266, :279): crop k starts k*step later
+            n = b2 // b
+            off = meta[:, 3].float().view(-1, 1) * torch.arange(n, device=meta.device, dtype=torch.float32).view(1, -1)
+            st = (st.view(-1, 1) + off).reshape(-1)
+            mask = mask.repeat_interleave(n, dim=0)
+        return FU.GaussianFn.apply(gx.contiguous(), st.contiguous(), mask.contiguous(), float(tx), float(self.ratio))
 
 
 class MixingLayer(nn.Module):
@@ -252,11 +264,17 @@ class ResNet(_FineResNet):
     def _forward(self, inp):
         x, feat, feat_masks, i, meta = inp
         t_in = x.shape[2]
-        if self.t_pool != 'grid':
-            raise NotImplementedError("only t_pool='grid' (the configuration of train_coarse_fineFEAT.py:107-109) is built")
         x = self.layer1(self._stem(x))                                         # :633-638
-        x, gx = self.pool_1(x)                                                 # :646-649
-        GX = self.gauss([meta, feat_masks, gx, t_in])                          # :650
+        if self.t_pool == 'grid':
+            x, gx = self.pool_1(x)                                             # :646-649
+            GX = self.gauss([meta, feat_masks, gx, t_in])                      # :650
+        else:                                                                  # :640-645, :652 (not used by the shipped scripts)
+            gx = None
+            if self.t_pool in ('avg', 'max'):
+                x = X.cl(self.pool_1(x))                                       # nn.AvgPool3d / nn.MaxPool3d over 4 frames
+            elif self.t_pool == 'stride':
+                x = X.cl(x[:, :, ::4])
+            GX = self.gauss([meta, feat_masks, x, None])
         keys = ('layer1', 'layer2', 'layer3', 'layer4')
         rws = (self.rw2, self.rw3, self.rw4, self.rw5)
         layers = (self.layer2, self.layer3, self.layer4, None)
@@ -288,6 +306,8 @@ class ResNet(_FineResNet):
         (b6, s6), = self._join_branches(rw6_pending)                           # :719-720 (started right after the Gaussian)
         lg = logits.unsqueeze(3).unsqueeze(4)
         x = FU.FilmFn.apply(lg, s6, b6).squeeze(4).squeeze(3)                  # :721
+        if self.t_pool != 'grid':
+            return x
         x = GridUnpool([x, gx, True])                                          # :724
         return G.linear_upsample_t(x, (x.shape[2] - 1) * 4)                    # :725
 

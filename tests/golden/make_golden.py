@@ -275,6 +275,49 @@ def gen_coarse_net():
     save("coarse_net", out_eval=out_eval, out_train=out, **gr)
 
 
+def gen_coarse_variants():
+    """Branches of x3d_coarse.ResNet.forward the shipped scripts do not take, through the unmodified reference:
+    t_pool in {avg, max, stride, None} (:640-652: AvgPool3d / MaxPool3d / x[:,:,::4] / no pooling, Gaussian on a uniform grid,
+    no Grid Unpool), multi-crop testing (:209-211, :264-266: coarse batch = crops x feature batch) and a feature mask longer
+    than the features (:205-207).  Same net and weights as coarse_net.npz; B=1, T=8, Tf=12, eval mode (+ one backward)."""
+    depth = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
+    T, Tf = 8, 12
+    feat = {k: synth_tensor((1, c, Tf, 7, 7), seed=84 + i).abs() for i, (k, c) in enumerate(depth.items())}
+    out = {}
+
+    def net(t_pool):
+        torch.manual_seed(81)
+        m = ref_coarse.generate_model("M", n_classes=400, feat_depth=depth, task="loc", base_bn_splits=1, dropout=0.0,
+                                      t_pool=t_pool, learnedMixing=True, isMixing=True)
+        m.replace_logits(12)
+        m.rw6.dropout.p = 0.0
+        fill_state_dict(m, seed=82)
+        return m.eval()
+
+    x = synth_tensor((1, 3, T, 224, 224), seed=83)
+    for t_pool in ("avg", "max", "stride", None):
+        m = net(t_pool)
+        with torch.no_grad():
+            out[f"t_pool_{t_pool}/out_eval"] = m([x, feat, torch.ones(1, Tf), 0, torch.tensor([[2., 8., 12., 1.]])])
+    # gradients through the average-pool variant (eval-mode BatchNorm: well conditioned at B=1)
+    m = net("avg")
+    o = m([x, feat, torch.ones(1, Tf), 0, torch.tensor([[2., 8., 12., 1.]])])
+    (o * synth_tensor(tuple(o.shape), seed=91)).sum().backward()
+    for k in ("rw2.at1.weight", "rw6.fc4.weight", "mix3.conv_at.weight", "layer2.0.conv1.weight", "layer1.0.conv1.weight", "fc2.weight"):
+        out["t_pool_avg/grad/" + k] = dict(m.named_parameters())[k].grad
+    # multi-crop: two crops of one video (coarse batch 2, features / mask / meta batch 1, crop step meta[:,3] = 2)
+    m = net("grid")
+    with torch.no_grad():
+        m.pool_1.conv3.weight.mul_(8.0)
+        x2 = synth_tensor((2, 3, T, 224, 224), seed=92)
+        out["multicrop/out_eval"] = m([x2, feat, torch.ones(1, Tf), 0, torch.tensor([[1., 8., 12., 2.]])])
+        # feature mask of 24 steps for 12 feature steps (:205-207), last 6 masked out
+        mask = torch.ones(1, 24)
+        mask[:, 18:] = 0
+        out["mask_resize/out_eval"] = m([x, feat, mask, 0, torch.tensor([[2., 8., 24., 1.]])])
+    save("coarse_variants", **out)
+
+
 def gen_apmeter():
     """apmeter.py:98-136 through the reference's own APMeter: unweighted (as the scripts use it,
     train_coarse_fineFEAT.py:241-263) and weighted, batches added in pieces, ties in the scores, a class without positives."""
@@ -641,6 +684,6 @@ def gen_param_order():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["interp1d", "gridpool", "gridpool_cfgshape", "gridunpool", "gaussian", "rewight",
                              "mixing", "bottleneck", "fine_net", "coarse_net", "apmeter", "clip_pipeline", "charades_loader", "cfg4", "cfg2",
-                             "coarse_b4", "param_order"]
+                             "coarse_b4", "param_order", "coarse_variants"]
     for w in which:
         globals()["gen_" + w]()

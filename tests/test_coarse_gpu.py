@@ -314,6 +314,55 @@ def test_coarse_net_golden(mods):
     assert e_news[(9 * n) // 10] <= max(6.0 * e_refs[(9 * n) // 10], 5e-3), (e_news[(9 * n) // 10], e_refs[(9 * n) // 10])
 
 
+def _variant_model(mods, t_pool):
+    depth = {"layer1": 24, "layer2": 48, "layer3": 96, "layer4": 192, "conv5": 432}
+    m = mods.C.generate_model("M", n_classes=400, feat_depth=depth, task="loc", base_bn_splits=1, dropout=0.0,
+                              t_pool=t_pool, learnedMixing=True, isMixing=True)
+    m.replace_logits(12)
+    m.rw6.dropout.p = 0.0
+    m.load_state_dict(synth_state_dict(m.state_dict(), 82), strict=True)
+    feat = {k: synth_tensor((1, c, 12, 7, 7), seed=84 + i).abs().cuda() for i, (k, c) in enumerate(depth.items())}
+    return m.cuda().eval(), feat
+
+
+@pytest.mark.parametrize("t_pool", ["avg", "max", "stride", None])
+def test_coarse_net_other_temporal_pools(mods, t_pool):
+    """x3d_coarse.py:640-652 branches the shipped scripts do not take (AvgPool3d / MaxPool3d / x[:,:,::4] / no pooling; Gaussian
+    on the uniform grid; no Grid Unpool), against the unmodified reference (coarse_variants.npz)."""
+    g = load("coarse_variants")
+    m, feat = _variant_model(mods, t_pool)
+    x = synth_tensor((1, 3, 8, 224, 224), seed=83).cuda()
+    mask, meta = torch.ones(1, 12, device="cuda"), torch.tensor([[2., 8., 12., 1.]], device="cuda")
+    if t_pool != "avg":
+        with torch.no_grad():
+            out = m([x, feat, mask, 0, meta])
+        relmax(out, g[f"t_pool_{t_pool}/out_eval"], 1e-3, f"t_pool={t_pool} eval logits")
+        return
+    out = m([x, feat, mask, 0, meta])
+    relmax(out, g["t_pool_avg/out_eval"], 1e-3, "t_pool=avg eval logits")
+    (out * synth_tensor(tuple(out.shape), seed=91).cuda()).sum().backward()
+    params = dict(m.named_parameters())
+    for k, gr in sub(g, "t_pool_avg/grad/").items():                # eval-mode BatchNorm: well conditioned at B=1
+        relmax(params[k].grad, gr, 3e-2, f"t_pool=avg grad {k}")   # whole-net fp32 gradients: percent-level (see the fp64 test below)
+
+
+def test_coarse_net_multicrop_and_mask_resize(mods):
+    """Multi-crop testing (x3d_coarse.py:209-211, 264-266: two crops of one video share its features, crop k starts k*step
+    later) and a feature mask longer than the features (:205-207), against the unmodified reference."""
+    g = load("coarse_variants")
+    m, feat = _variant_model(mods, "grid")
+    with torch.no_grad():
+        m.pool_1.conv3.weight.mul_(8.0)
+        x2 = synth_tensor((2, 3, 8, 224, 224), seed=92).cuda()
+        out = m([x2, feat, torch.ones(1, 12, device="cuda"), 0, torch.tensor([[1., 8., 12., 2.]], device="cuda")])
+        relmax(out, g["multicrop/out_eval"], 1e-3, "multi-crop eval logits")
+        x = synth_tensor((1, 3, 8, 224, 224), seed=83).cuda()
+        mask = torch.ones(1, 24, device="cuda")
+        mask[:, 18:] = 0
+        out = m([x, feat, mask, 0, torch.tensor([[2., 8., 24., 1.]], device="cuda")])
+        relmax(out, g["mask_resize/out_eval"], 1e-3, "mask-resize eval logits")
+
+
 def test_coarse_net_eval_mode_all_grads_vs_fp64(mods):
     """Every parameter gradient of the whole coarse net (running-statistics BatchNorm) against the oracle in fp64.
 
