@@ -459,6 +459,7 @@ extern "C" int cf_bn_finalize(const cf_bn_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->gamma && a->beta && a->tab_a && a->tab_b && a->mean && a->invstd, "null pointer");
     CF_CHECK_ARG(a->B > 0 && a->C > 0 && a->splits > 0 && a->B % a->splits == 0, "bad shape (B % splits)");
     CF_CHECK_ARG(a->training ? (a->stats != nullptr) : (a->running_mean && a->running_var), "missing statistics");
+    if (cf_env("CFNET_BN_SKIP", 0)) return CF_OK;       // timing experiment (experiment build): what the table launches cost
     cf_launch(bn_finalize_kernel, cf_cdiv(a->C, 128), 128, 0, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
@@ -468,6 +469,7 @@ extern "C" int cf_bn_finalize(const cf_bn_args* a, cudaStream_t stream) {
 extern "C" int cf_bn_bwd_coeffs(const cf_bn_bwd_args* a, cudaStream_t stream) {
     CF_CHECK_ARG(a && a->sums && a->gamma && a->mean && a->invstd && a->tab_p && a->tab_q && a->tab_r, "null pointer");
     CF_CHECK_ARG(a->B > 0 && a->C > 0 && a->splits > 0 && a->B % a->splits == 0, "bad shape (B % splits)");
+    if (cf_env("CFNET_BN_SKIP", 0)) return CF_OK;
     cf_launch(bn_bwd_coeffs_kernel, cf_cdiv(a->C, 128), 128, 0, stream, *a);
     CF_COUNT_LAUNCH(1);
     CF_CHECK_LAUNCH();
