@@ -47,7 +47,8 @@ def _compile(src, verbose, obj_dir=OBJ_DIR, extra=()):
     return obj, True
 
 
-VARIANTS = {"cvt": ("-DCFNET_AB", "-DCFNET_TF32_CVT"), "pdlwait": ("-DCFNET_AB", "-DCFNET_PDL_NOTRIGGER")}       # named experiment builds: libcfnet_b200_<name>.so
+VARIANTS = {"cvt": ("-DCFNET_AB", "-DCFNET_TF32_CVT"), "pdlwait": ("-DCFNET_AB", "-DCFNET_PDL_NOTRIGGER"),
+            "p2timing": ("-DCFNET_AB", "-DCFNET_P2_TIMING")}      # per-role cycle counters of pw_tc2_kernel (tools/bench_pw.py)       # named experiment builds: libcfnet_b200_<name>.so
 
 
 def build(force=False, verbose=False, ab=False, variant=None):

@@ -485,7 +485,7 @@ template <int EV, int EPI, int SMODE, bool FULL>
 __device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const P2Params& p, int b, int r0, int ncol, const float* __restrict__ cp,
                                               float* __restrict__ dp, const float* __restrict__ ap, size_t gstep, int rs, int rows_valid,
                                               const float* bi, const float* ea, const float* eb, bool has_bias, float* s1, float* s2) {
-    constexpr int CPR = 32 / EV, RPP = 128 / CPR, NPASS = TC_BM / RPP;
+    constexpr int CPR = 32 / EV, RPP = 32 / CPR, NPASS = 32 / RPP;      // a warp stores its own 32 rows, RPP rows per pass
     constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX || EPI == CF_EPI_AFFINE_ADD_RELU;
     constexpr bool NEED_AUX = EPI_AUX || SMODE == CF_STATS_SUM_AUX;
     float ax[NEED_AUX ? NPASS : 1][EV];
@@ -546,9 +546,10 @@ template <int EV, int EPI, int SMODE>
 __device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const P2Params& p, const float* __restrict__ Cs, float* __restrict__ redw,
                                               int b, int r0, int rows_valid, int R, int n0, int col0, int nvalid, int gt) {
     constexpr int CPR = 32 / EV;             // column groups per row
-    constexpr int RPP = 128 / CPR;           // rows per pass
+    constexpr int RPP = 32 / CPR;            // rows per pass of one warp
     const int N = a.N;
-    const int cg = gt % CPR, rs = gt / CPR;
+    const int lane = gt & 31;
+    const int cg = lane % CPR, rs = (gt & ~31) + lane / CPR;     // the warp stores the 32 rows it brought from TMEM itself
     const int nl = col0 + cg * EV;           // column within the channel tile
     const bool active = nl < nvalid;         // nvalid and nl are multiples of EV: a column group is all-valid or all-padding
     float s1[EV], s2[EV];
@@ -619,7 +620,7 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
     const int ew = warp - P2_EPI_WARP0;
     const int grp = ew >> 2;
     const int qd = warp & 3;                                 // TMEM lane quadrant this warp may read
-    const int gt = (ew & 3) * 32 + lane;                     // thread index within the group (phase 2)
+    const int gt = qd * 32 + lane;                           // row of the tile this thread brings from TMEM; its warp stores rows qd*32..+31
     const int et = ew * 32 + lane;
     float* Cs = Cs_all + grp * P2_CS_FLOATS;
     float* redw = red + (ew & 3) * 2 * P2_RED_N;                // this warp's row of the statistics table
@@ -657,14 +658,14 @@ __device__ __forceinline__ void p2_epilogue(const cf_pw_args& a, const P2Params&
                 if (lane == 0) mbar_arrive(&tempty[acc]);
             }
             P2_ACC(2, tt);                                   // 2: tcgen05.ld + release
-            named_bar_sync(2 + grp, 128);                    // the previous slab's readers are done with Cs
+            __syncwarp();                                    // this warp's rows of Cs: its previous slab has been read
             P2_ACC(3, tt);                                   // 3: group barriers
             float* dst = Cs + row_own * P2_CS_LD;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(r32[4 * i], r32[4 * i + 1], r32[4 * i + 2], r32[4 * i + 3]);
             P2_ACC(4, tt);                                   // 4: accumulator rows -> shared slab
-            named_bar_sync(2 + grp, 128);
+            __syncwarp();
             P2_ACC(3, tt);
             p2_store_slab<EV, EPI, SMODE>(a, p, Cs, redw, it.b, it.r0, rows_valid, p.R, n0, slab * 32, nvalid, gt);
             P2_ACC(5, tt);                                   // 5: slab -> global (+ aux, activation, statistics partials)
