@@ -9,13 +9,13 @@ for k in ${@:-pw_tc pw_swish pw_dgrad3 pw_dgrad1 wgrad1 wgrad3 dw_fused}; do
     wgrad*) pat="pw_wgrad_tc_kernel";;
     dw_fused) pat="dw3_kernel";;
   esac
-  rep=/tmp/r02_full_$k
+  rep=/tmp/r02g_full_$k
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$pat -s 4 -c 1 -f -o $rep \
-      python profiles/run_kernel.py $k 4 64 > gpurun_out/r02_ncu_$k.log 2>&1
-  tail -1 gpurun_out/r02_ncu_$k.log
-  python profiles/summarize.py full $rep.ncu-rep gpurun_out/r02_full_$k.md
-  python profiles/summarize.py mix $rep.ncu-rep gpurun_out/r02_full_$k.md
-  ncu -i $rep.ncu-rep --page source --csv 2>/dev/null | cut -d, -f1-12 | gzip -9 > gpurun_out/r02_src_$k.csv.gz
+      python profiles/run_kernel.py $k 4 64 > gpurun_out/r02g_ncu_$k.log 2>&1
+  tail -1 gpurun_out/r02g_ncu_$k.log
+  python profiles/summarize.py full $rep.ncu-rep gpurun_out/r02g_full_$k.md
+  python profiles/summarize.py mix $rep.ncu-rep gpurun_out/r02g_full_$k.md
+  ncu -i $rep.ncu-rep --page source --csv 2>/dev/null | cut -d, -f1-12 | gzip -9 > gpurun_out/r02g_src_$k.csv.gz
   rm -f $rep.ncu-rep
 done
 ls -la gpurun_out | tail -20
