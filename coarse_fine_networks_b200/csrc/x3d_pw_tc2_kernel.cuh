@@ -481,53 +481,9 @@ __device__ __forceinline__ void p2_fma2(float& c0, float& c1, float a0, float a1
 }
 
 // FULL: all 128 rows of the tile are valid (every tile but the last one of a sample): no per-pass row checks
-// one store pass of a thread: EV columns of one row, shared slab -> (bias, activation, statistics) -> global
-template <int EV, int EPI, int SMODE, bool SCAT>
-__device__ __forceinline__ void p2_store_one(const cf_pw_args& a, const P2Params& p, int b, int row, int ncol, const float* __restrict__ cp,
-                                             float* __restrict__ dp, const float* axe, const float* bi, const float* ea, const float* eb,
-                                             bool has_bias, float* s1, float* s2) {
-    float vv[EV];
-    P2Vec<EV>::ldrw(cp, vv);
-    if (has_bias) {
-#pragma unroll
-        for (int e = 0; e < EV; e += 2) p2_add2(vv[e], vv[e + 1], bi[e], bi[e + 1]);
-    }
-#pragma unroll
-    for (int e = 0; e < EV; ++e) {
-        float t = vv[e];
-        if (EPI == CF_EPI_RELU) t = fmaxf(t, 0.f);
-        else if (EPI == CF_EPI_DRELU) t = (fmaf(ea[e], axe[e], eb[e]) > 0.f) ? t : 0.f;
-        else if (EPI == CF_EPI_DSWISH) t *= p2_dswish(fmaf(ea[e], axe[e], eb[e]));
-        else if (EPI == CF_EPI_ADD_AUX) t += axe[e];
-        else if (EPI == CF_EPI_SIGMOID) t = p2_sigmoid(t);
-        else if (EPI == CF_EPI_AFFINE) t = fmaf(ea[e], t, eb[e]);
-        else if (EPI == CF_EPI_AFFINE_ADD_RELU) t = fmaxf(fmaf(ea[e], t, eb[e]) + axe[e], 0.f);
-        vv[e] = t;
-    }
-    if (SMODE != CF_STATS_NONE) {
-#pragma unroll
-        for (int e = 0; e < EV; e += 2) {
-            p2_add2(s1[e], s1[e + 1], vv[e], vv[e + 1]);
-            if (SMODE == CF_STATS_SUM_AUX) p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], axe[e], axe[e + 1]);
-            else p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], vv[e], vv[e + 1]);
-        }
-    }
-    if (SCAT) {                                                  // strided 1x1x1 conv, data gradient: y[map(row)] += result
-        float* sp = a.y + (size_t)b * p.g_sample_stride + p2_map_row(p, row) * a.N + ncol;
-        float old[EV];
-        P2Vec<EV>::ldrw(sp, old);
-#pragma unroll
-        for (int e = 0; e < EV; ++e) vv[e] += old[e];
-        P2Vec<EV>::st(sp, vv);
-    } else {
-        P2Vec<EV>::st(dp, vv);
-    }
-}
-
-// all 32 rows of the warp valid, dense output (every tile but the last one of a sample): unrolled, auxiliary rows prefetched
-template <int EV, int EPI, int SMODE>
+template <int EV, int EPI, int SMODE, bool FULL>
 __device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const P2Params& p, int b, int r0, int ncol, const float* __restrict__ cp,
-                                              float* __restrict__ dp, const float* __restrict__ ap, size_t gstep, int rs,
+                                              float* __restrict__ dp, const float* __restrict__ ap, size_t gstep, int rs, int rows_valid,
                                               const float* bi, const float* ea, const float* eb, bool has_bias, float* s1, float* s2) {
     constexpr int CPR = 32 / EV, RPP = 32 / CPR, NPASS = 32 / RPP;      // a warp stores its own 32 rows, RPP rows per pass
     constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX || EPI == CF_EPI_AFFINE_ADD_RELU;
@@ -535,31 +491,54 @@ __device__ __forceinline__ void p2_store_rows(const cf_pw_args& a, const P2Param
     float ax[NEED_AUX ? NPASS : 1][EV];
     if (NEED_AUX) {
 #pragma unroll
-        for (int i = 0; i < NPASS; ++i, ap += gstep) P2Vec<EV>::ld(ap, ax[NEED_AUX ? i : 0]);
+        for (int i = 0; i < NPASS; ++i, ap += gstep) {
+            if (FULL || rs + i * RPP < rows_valid) P2Vec<EV>::ld(ap, ax[NEED_AUX ? i : 0]);
+            else {
+#pragma unroll
+                for (int e = 0; e < EV; ++e) ax[NEED_AUX ? i : 0][e] = 0.f;
+            }
+        }
     }
 #pragma unroll
-    for (int i = 0; i < NPASS; ++i, dp += gstep, cp += RPP * P2_CS_LD)
-        p2_store_one<EV, EPI, SMODE, false>(a, p, b, 0, ncol, cp, dp, ax[NEED_AUX ? i : 0], bi, ea, eb, has_bias, s1, s2);
-}
-
-// the ragged last tile of a sample and the scattered output of the strided data gradient: a rolled loop (rare or small; kept
-// compact so that its row predicates are not hoisted into the common path: ncu source view, 48 issue slots per slab)
-template <int EV, int EPI, int SMODE, bool SCAT>
-__device__ __forceinline__ void p2_store_rows_rolled(const cf_pw_args& a, const P2Params& p, int b, int r0, int ncol, const float* __restrict__ cp,
-                                                     float* __restrict__ dp, const float* __restrict__ ap, size_t gstep, int rs, int rows_valid,
-                                                     const float* bi, const float* ea, const float* eb, bool has_bias, float* s1, float* s2) {
-    constexpr int CPR = 32 / EV, RPP = 32 / CPR, NPASS = 32 / RPP;
-    constexpr bool EPI_AUX = EPI == CF_EPI_DRELU || EPI == CF_EPI_DSWISH || EPI == CF_EPI_ADD_AUX || EPI == CF_EPI_AFFINE_ADD_RELU;
-    constexpr bool NEED_AUX = EPI_AUX || SMODE == CF_STATS_SUM_AUX;
-    int npv = rows_valid > rs ? (rows_valid - rs + RPP - 1) / RPP : 0;
-    if (npv > NPASS) npv = NPASS;
-#pragma unroll 1
-    for (int i = 0; i < npv; ++i, dp += gstep, cp += RPP * P2_CS_LD) {
-        float axe[EV];
+    for (int i = 0; i < NPASS; ++i, dp += gstep, cp += RPP * P2_CS_LD) {
+        if (!FULL && rs + i * RPP >= rows_valid) break;
+        float vv[EV];
+        P2Vec<EV>::ldrw(cp, vv);
+        if (has_bias) {
 #pragma unroll
-        for (int e = 0; e < EV; ++e) axe[e] = 0.f;
-        if (NEED_AUX) P2Vec<EV>::ld(ap + (size_t)i * gstep, axe);
-        p2_store_one<EV, EPI, SMODE, SCAT>(a, p, b, r0 + rs + i * RPP, ncol, cp, dp, axe, bi, ea, eb, has_bias, s1, s2);
+            for (int e = 0; e < EV; e += 2) p2_add2(vv[e], vv[e + 1], bi[e], bi[e + 1]);
+        }
+        const float* axe = ax[NEED_AUX ? i : 0];
+#pragma unroll
+        for (int e = 0; e < EV; ++e) {
+            float t = vv[e];
+            if (EPI == CF_EPI_RELU) t = fmaxf(t, 0.f);
+            else if (EPI == CF_EPI_DRELU) t = (fmaf(ea[e], axe[e], eb[e]) > 0.f) ? t : 0.f;
+            else if (EPI == CF_EPI_DSWISH) t *= p2_dswish(fmaf(ea[e], axe[e], eb[e]));
+            else if (EPI == CF_EPI_ADD_AUX) t += axe[e];
+            else if (EPI == CF_EPI_SIGMOID) t = p2_sigmoid(t);
+            else if (EPI == CF_EPI_AFFINE) t = fmaf(ea[e], t, eb[e]);
+            else if (EPI == CF_EPI_AFFINE_ADD_RELU) t = fmaxf(fmaf(ea[e], t, eb[e]) + axe[e], 0.f);
+            vv[e] = t;
+        }
+        if (SMODE != CF_STATS_NONE) {
+#pragma unroll
+            for (int e = 0; e < EV; e += 2) {
+                p2_add2(s1[e], s1[e + 1], vv[e], vv[e + 1]);
+                if (SMODE == CF_STATS_SUM_AUX) p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], axe[e], axe[e + 1]);
+                else p2_fma2(s2[e], s2[e + 1], vv[e], vv[e + 1], vv[e], vv[e + 1]);
+            }
+        }
+        if (p.gmode == 2) {                                      // strided 1x1x1 conv, data gradient: y[map(row)] += result
+            float* sp = a.y + (size_t)b * p.g_sample_stride + p2_map_row(p, r0 + rs + i * RPP) * a.N + ncol;
+            float old[EV];
+            P2Vec<EV>::ldrw(sp, old);
+#pragma unroll
+            for (int e = 0; e < EV; ++e) vv[e] += old[e];
+            P2Vec<EV>::st(sp, vv);
+        } else {
+            P2Vec<EV>::st(dp, vv);
+        }
     }
 }
 
@@ -590,12 +569,10 @@ __device__ __forceinline__ void p2_store_slab(const cf_pw_args& a, const P2Param
         const size_t gstep = (size_t)RPP * N;
         const float* cp = Cs + rs * P2_CS_LD + cg * EV;
         const float* ap = a.aux ? a.aux + g0 : nullptr;
-        if (p.gmode == 2)
-            p2_store_rows_rolled<EV, EPI, SMODE, true>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
-        else if (rows_valid == TC_BM)
-            p2_store_rows<EV, EPI, SMODE>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, bi, ea, eb, a.bias != nullptr, s1, s2);
+        if (rows_valid == TC_BM)
+            p2_store_rows<EV, EPI, SMODE, true>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
         else
-            p2_store_rows_rolled<EV, EPI, SMODE, false>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
+            p2_store_rows<EV, EPI, SMODE, false>(a, p, b, r0, n, cp, a.y + g0, ap, gstep, rs, rows_valid, bi, ea, eb, a.bias != nullptr, s1, s2);
     }
     if (SMODE != CF_STATS_NONE) {
         // column sums: the 32 / CPR row groups of a warp meet by shuffle, then the first CPR lanes add into THIS WARP's
